@@ -1,0 +1,85 @@
+"""ctypes declarations for include/eg_b200.h (the C ABI of libeg_b200.so)."""
+import ctypes as C
+import pathlib
+
+PKG = pathlib.Path(__file__).resolve().parent
+DEFAULT_LIB = PKG / "libeg_b200.so"
+
+SUCCESS, ERR_INVALID_ARG, ERR_INVALID_ELEMENT, ERR_IDENTITY_KEY, ERR_NO_RECEIVER, ERR_NO_DEVICE, ERR_CUDA, \
+    ERR_OUT_OF_MEMORY, ERR_LEN_MISMATCH = range(9)
+STATUS_NAMES = ["SUCCESS", "ERR_INVALID_ARG", "ERR_INVALID_ELEMENT", "ERR_IDENTITY_KEY", "ERR_NO_RECEIVER",
+                "ERR_NO_DEVICE", "ERR_CUDA", "ERR_OUT_OF_MEMORY", "ERR_LEN_MISMATCH"]
+
+V_OK, V_MALFORMED, V_CHALLENGE_MISMATCH, V_CHOICE_SUM, V_CHOICE_RANGE, V_QV_CREDIT_RANGE, V_QV_CREDIT_EQUIV = range(7)
+V_QV_VARIANT_BASE = 16
+
+
+class Range(C.Structure):
+    _fields_ = [("n_rings", C.c_uint32), ("reserved", C.c_uint32), ("size", C.c_uint64 * 64), ("step", C.c_uint64 * 64)]
+
+    @property
+    def rings(self):
+        return [(self.size[i], self.step[i]) for i in range(self.n_rings)]
+
+    @property
+    def rings_size(self):
+        return sum(self.size[i] for i in range(self.n_rings))
+
+
+class QvParams(C.Structure):
+    _fields_ = [("options", C.c_uint32), ("reserved", C.c_uint32), ("credits", C.c_uint64), ("vote_range", Range),
+                ("credit_range", Range)]
+
+
+class KeySet(C.Structure):
+    _fields_ = [("shares", C.c_uint32), ("threshold", C.c_uint32), ("shared_key", C.c_uint8 * 32),
+                ("participant_keys", (C.c_uint8 * 32) * 64)]
+
+
+P8 = C.c_void_p   # byte buffers are passed as raw addresses (host numpy arrays or device pointers)
+
+PROTOTYPES = {
+    "eg_ctx_create": (C.c_int32, [C.c_int, C.POINTER(C.c_void_p)]),
+    "eg_ctx_destroy": (None, [C.c_void_p]),
+    "eg_last_error": (C.c_char_p, [C.c_void_p]),
+    "eg_version": (C.c_char_p, []),
+    "eg_ctx_set_receiver": (C.c_int32, [C.c_void_p, P8]),
+    "eg_elements_validate": (C.c_int32, [C.c_void_p, C.c_size_t, P8, P8]),
+    "eg_scalars_validate": (C.c_int32, [C.c_void_p, C.c_size_t, P8, P8]),
+    "eg_scalars_from_wide": (C.c_int32, [C.c_void_p, C.c_size_t, P8, P8]),
+    "eg_double_mul_generator_batch": (C.c_int32, [C.c_void_p, C.c_size_t, P8, P8, P8, P8, P8]),
+    "eg_mul_generator_batch": (C.c_int32, [C.c_void_p, C.c_size_t, P8, P8, P8]),
+    "eg_ciphertexts_sum": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_size_t, P8, P8, P8]),
+    "eg_verify_zero_batch": (C.c_int32, [C.c_void_p, C.c_size_t, P8, P8, P8]),
+    "eg_verify_bool_batch": (C.c_int32, [C.c_void_p, C.c_size_t, P8, P8, P8]),
+    "eg_verify_choice_batch": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_uint32, C.c_int, P8, P8, P8, P8, P8]),
+    "eg_verify_bool_batch_dev": (C.c_int32, [C.c_void_p, C.c_size_t, P8, P8, P8]),
+    "eg_verify_choice_batch_dev": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_uint32, C.c_int, P8, P8, P8, P8, P8]),
+    "eg_kernel_launch_count": (C.c_uint64, [C.c_void_p]),
+    "eg_last_timings": (C.c_int32, [C.c_void_p, C.POINTER(C.c_float * 5)]),
+    "eg_ctx_stream": (C.c_void_p, [C.c_void_p]),
+    "eg_last_commit_stats": (C.c_int32, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_float)]),
+    "eg_selftest_field": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "eg_ctx_set_chunk_items": (C.c_int32, [C.c_void_p, C.c_size_t]),
+}
+
+
+def load(path=None):
+    """Loads the C-ABI library.  Fails loudly when it has not been built: there is no fallback."""
+    path = pathlib.Path(path) if path else DEFAULT_LIB
+    if not path.exists():
+        raise RuntimeError(f"{path} is missing: build it with `python -m elastic_elgamal_b200.build` "
+                           "(the engine has no CPU fallback)")
+    lib = C.CDLL(str(path))
+    missing = []
+    for name, (res, args) in PROTOTYPES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError:
+            missing.append(name)
+            continue
+        fn.restype = res
+        fn.argtypes = args
+    if missing:
+        raise RuntimeError(f"{path} does not export: {', '.join(missing)}")
+    return lib

@@ -1,0 +1,1173 @@
+// eg_b200.cu -- the C ABI (include/eg_b200.h) and kernel launches of the B200 batch engine.
+//
+// Host side: context / scratch management, per-election transcript prefixes (computed once with the same
+// __host__ __device__ Merlin code the kernels use), slot tables that describe which equation of which
+// proof each thread evaluates, chunked execution.  All group / field / hash arithmetic of a batch runs in
+// the kernels below; there is no CPU path (eg_ctx_create fails without a device).
+#ifdef EG_HOSTSIM
+#include "hostsim_cuda.h"      // test-only stand-in for the CUDA runtime (tests/hostsim): malloc/memcpy, no device
+#else
+#include <cuda_runtime.h>
+#endif
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/eg_b200.h"
+#include "kernels.cuh"
+
+using namespace eg;
+
+// =================================================================== kernels
+//
+// Every kernel is a thin __global__ wrapper around a body in kernels.cuh.  launch_*() is the only place a
+// kernel is started; under EG_HOSTSIM (tests/hostsim, test harness only) the same bodies run in a host loop.
+
+#define EG_COMMIT_THREADS 128
+#define EG_TALLY_THREADS 128
+#define EG_TALLY_BLOCKS 148       // per slot: one CTA per SM
+
+#ifndef EG_HOSTSIM
+
+__global__ void __launch_bounds__(256) k_decode(const decode_params P) {
+    size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= P.n * (size_t)P.n_slots) return;
+    decode_body(P, tid % P.n, (int)(tid / P.n));
+}
+
+__global__ void __launch_bounds__(256) k_scalars(const scalars_params P) {
+    size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= P.n) return;
+    scalars_body(P, tid);
+}
+
+// The hot kernel.  Both 12 KB fixed-base tables are staged in shared memory once per CTA.
+__global__ void __launch_bounds__(EG_COMMIT_THREADS) k_commit(const commit_params P) {
+    __shared__ uint32_t s_tab[2 * EG_FIXED_TABLE_WORDS];
+    for (int k = threadIdx.x; k < EG_FIXED_TABLE_WORDS; k += blockDim.x) {
+        s_tab[k] = P.table_g[k];
+        s_tab[EG_FIXED_TABLE_WORDS + k] = P.table_k[k];
+    }
+    __syncthreads();
+    size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= P.n * (size_t)P.n_slots) return;
+    commit_body(P, tid % P.n, (int)(tid / P.n), s_tab, s_tab + EG_FIXED_TABLE_WORDS);
+}
+
+__global__ void __launch_bounds__(128) k_ring_hash(const ring_hash_params P) {
+    size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= P.n * (size_t)P.n_slots) return;
+    ring_hash_body(P, tid % P.n, (int)(tid / P.n));
+}
+
+__global__ void __launch_bounds__(128) k_ring_final(const ring_final_params P) {
+    size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= P.n) return;
+    ring_final_body(P, tid);
+}
+
+__global__ void __launch_bounds__(128) k_logeq_final(const logeq_final_params P) {
+    size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= P.n) return;
+    logeq_final_body(P, tid);
+}
+
+__global__ void __launch_bounds__(128) k_choice_sum(const choice_sum_params P) {
+    size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= 2 * P.n) return;
+    choice_sum_body(P, tid % P.n, (int)(tid / P.n));
+}
+
+__global__ void __launch_bounds__(128) k_range_last(const range_last_params P) {
+    size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= 2 * P.n) return;
+    range_last_body(P, tid % P.n, (int)(tid / P.n));
+}
+
+__global__ void __launch_bounds__(256) k_verdict(const verdict_params P) {
+    size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= P.n) return;
+    verdict_body(P, tid);
+}
+
+__global__ void k_build_table(const uint32_t *enc_words, int use_generator, uint32_t *table, uint32_t *status) {
+    build_table_body(threadIdx.x, enc_words, use_generator, table, status);
+}
+
+__global__ void k_admissible(const uint64_t *values, int count, uint32_t *adm) {
+    int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid < count) admissible_body(tid, values, adm);
+}
+
+// --- tally: masked point sums (warp-shuffle tree -> block -> grid) -------------------------------------
+
+__device__ __forceinline__ void shfl_point_down(ge_ext &q, const ge_ext &p, int delta) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        q.X.v[k] = __shfl_down_sync(0xffffffffu, p.X.v[k], delta);
+        q.Y.v[k] = __shfl_down_sync(0xffffffffu, p.Y.v[k], delta);
+        q.Z.v[k] = __shfl_down_sync(0xffffffffu, p.Z.v[k], delta);
+        q.T.v[k] = __shfl_down_sync(0xffffffffu, p.T.v[k], delta);
+    }
+}
+
+// partial[(slot * gridDim.x + block) * 32 ..] = sum over this block's items with verdict OK of pts[slot]
+__global__ void __launch_bounds__(EG_TALLY_THREADS) k_tally_partial(const uint32_t *pts, size_t n, const uint8_t *verdicts,
+                                                                    uint32_t *partial) {
+    __shared__ uint32_t s_pt[EG_TALLY_THREADS / 32][32];
+    const int slot = blockIdx.y;
+    ge_ext acc = ge_identity(), q;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        if (verdicts[i] == 0) {
+            planar_load_point(q, pts, n, slot, i);
+            ge_add(acc, acc, q);
+        }
+    }
+#pragma unroll 1
+    for (int delta = 16; delta >= 1; delta >>= 1) {
+        shfl_point_down(q, acc, delta);
+        ge_add(acc, acc, q);          // lanes >= delta compute values that are never read
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) point_to_words32(s_pt[warp], acc);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int wp = 1; wp < EG_TALLY_THREADS / 32; wp++) {
+            point_from_words32(q, s_pt[wp]);
+            ge_add(acc, acc, q);
+        }
+        point_to_words32(partial + ((size_t)slot * gridDim.x + blockIdx.x) * 32, acc);
+    }
+}
+
+// running[slot] (+)= sum of `count` partial points; one warp per slot.  If `encode_out` is set the total is encoded.
+__global__ void __launch_bounds__(32) k_tally_final(const uint32_t *partial, int count, uint32_t *running, int accumulate,
+                                                    uint8_t *encode_out) {
+    const int slot = blockIdx.x, lane = threadIdx.x;
+    ge_ext acc = ge_identity(), q;
+    for (int i = lane; i < count; i += 32) {
+        point_from_words32(q, partial + ((size_t)slot * count + i) * 32);
+        ge_add(acc, acc, q);
+    }
+#pragma unroll 1
+    for (int delta = 16; delta >= 1; delta >>= 1) {
+        shfl_point_down(q, acc, delta);
+        ge_add(acc, acc, q);
+    }
+    if (lane == 0) {
+        uint32_t *r = running + (size_t)slot * 32;
+        if (accumulate) { point_from_words32(q, r); ge_add(acc, acc, q); }
+        point_to_words32(r, acc);
+        if (encode_out) {
+            uint32_t w[8];
+            ge_encode(w, acc);
+            store32_bytes(encode_out + 32 * slot, w);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_elements_validate(const uint8_t *enc, size_t n, uint8_t *ok) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) elements_validate_body(i, enc, ok);
+}
+
+__global__ void __launch_bounds__(256) k_scalars_validate(const uint8_t *s, size_t n, uint8_t *ok) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) scalars_validate_body(i, s, ok);
+}
+
+__global__ void __launch_bounds__(256) k_scalars_from_wide(const uint8_t *wide, size_t n, uint8_t *out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) scalars_from_wide_body(i, wide, out);
+}
+
+__global__ void __launch_bounds__(EG_COMMIT_THREADS) k_double_mul(const uint8_t *a, const uint8_t *A, const uint8_t *b, size_t n,
+                                                                  int mode, const uint32_t *table_g, uint8_t *out, uint8_t *okv) {
+    __shared__ uint32_t s_tab[EG_FIXED_TABLE_WORDS];
+    for (int k = threadIdx.x; k < EG_FIXED_TABLE_WORDS; k += blockDim.x) s_tab[k] = table_g[k];
+    __syncthreads();
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) double_mul_body(i, a, A, b, mode, s_tab, out, okv);
+}
+
+__global__ void k_ciphertexts_sum(const uint8_t *parts, size_t n_parts, size_t n_cts, uint8_t *out, uint32_t *bad) {
+    size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid < 2 * n_cts) ciphertexts_sum_body(tid, parts, n_parts, n_cts, out, bad);
+}
+
+// on-device self-test of the tuned field arithmetic against the portable formulation (eg_selftest_field)
+__global__ void __launch_bounds__(128) k_selftest_field(size_t n, uint64_t seed, unsigned long long *mismatches) {
+    size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= n) return;
+    uint64_t x = seed + 0x9e3779b97f4a7c15ULL * (tid + 1);
+    fe a, b;
+    for (int i = 0; i < 8; i++) {
+        x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ULL; x ^= x >> 27; x *= 0x94d049bb133111ebULL; x ^= x >> 31;
+        a.v[i] = (uint32_t)x; b.v[i] = (uint32_t)(x >> 32);
+        x += 0x9e3779b97f4a7c15ULL;
+    }
+    // edge patterns on the first threads: all ones, p, p-1, 2^256-38, small values
+    const int e = (int)(tid % 64);
+    if (tid < 4096) {
+        if (e == 0) for (int i = 0; i < 8; i++) a.v[i] = 0xffffffffu;
+        if (e == 1) for (int i = 0; i < 8; i++) b.v[i] = 0xffffffffu;
+        if (e == 2) { for (int i = 0; i < 8; i++) a.v[i] = b.v[i] = 0xffffffffu; }
+        if (e == 3) { for (int i = 1; i < 7; i++) a.v[i] = 0xffffffffu; a.v[0] = 0xffffffedu; a.v[7] = 0x7fffffffu; }
+        if (e == 4) { for (int i = 1; i < 8; i++) a.v[i] = 0xffffffffu; a.v[0] = 0xffffffdau; }
+        if (e == 5) { a = fe_zero(); }
+        if (e == 6) { a = fe_one(); for (int i = 0; i < 8; i++) b.v[i] = 0xffffffffu; }
+        if (e == 7) { for (int i = 0; i < 8; i++) a.v[i] = (i & 1) ? 0xffffffffu : 0u; }
+    }
+    fe m1, m2, s1, s2, d;
+    fe_mul(m1, a, b); fe_mul_portable(m2, a, b);
+    fe_sq(s1, a); fe_sq_portable(s2, a);
+    unsigned bad = 0;
+    fe_sub(d, m1, m2); if (!fe_iszero(d)) bad++;
+    fe_sub(d, s1, s2); if (!fe_iszero(d)) bad++;
+    fe_mul_portable(m2, a, a); fe_sub(d, s1, m2); if (!fe_iszero(d)) bad++;
+    // (a + b) - b == a and a * 1 == a through the carry-chain add/sub
+    fe t; fe_add(t, a, b); fe_sub(t, t, b); fe_sub(d, t, a); if (!fe_iszero(d)) bad++;
+    if (bad) atomicAdd(mismatches, (unsigned long long)bad);
+}
+
+#endif  // !EG_HOSTSIM
+
+// =================================================================== context
+
+struct dev_buf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct eg_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool has_receiver = false;
+    uint8_t key[32];
+    uint32_t *d_table_g = nullptr, *d_table_k = nullptr, *d_status = nullptr;
+    std::string err;
+    uint64_t launches = 0, commit_launches = 0, commit_tasks = 0;
+    float timings[5] = {0, 0, 0, 0, 0};
+    cudaEvent_t ev[8];
+    std::vector<cudaEvent_t> commit_ev;     // pairs (start, stop) around every k_commit launch of the current call
+    size_t commit_ev_used = 0;
+    uint64_t call_commit_tasks = 0, call_commit_launches = 0;
+    // grow-only scratch
+    dev_buf pts, enc, commit, chal, flags, res[3], in[4], verdicts, partial, running, adm, misc;
+    std::map<std::string, std::vector<uint64_t>> adm_cache_key;
+    size_t chunk_items = 0;   // 0 = default
+};
+
+struct eg_dlog_table {
+    eg_ctx *ctx;
+    uint64_t lo, hi;
+    size_t cap;
+    uint32_t *d_keys;     // cap * 8 words
+    uint64_t *d_vals;     // cap
+};
+
+static eg_status fail(eg_ctx *ctx, eg_status st, const char *what, cudaError_t ce = cudaSuccess) {
+    if (ctx) {
+        ctx->err = what;
+        if (ce != cudaSuccess) { ctx->err += ": "; ctx->err += cudaGetErrorString(ce); }
+    }
+    return st;
+}
+
+#define CU(call)                                                            \
+    do {                                                                    \
+        cudaError_t ce_ = (call);                                           \
+        if (ce_ != cudaSuccess) return fail(ctx, EG_ERR_CUDA, #call, ce_);  \
+    } while (0)
+
+static eg_status ensure(eg_ctx *ctx, dev_buf &b, size_t bytes) {
+    if (b.cap >= bytes) return EG_SUCCESS;
+    if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+    size_t want = bytes + bytes / 8;
+    cudaError_t ce = cudaMalloc(&b.p, want);
+    if (ce != cudaSuccess) { cudaGetLastError(); return fail(ctx, EG_ERR_OUT_OF_MEMORY, "cudaMalloc scratch", ce); }
+    b.cap = want;
+    return EG_SUCCESS;
+}
+
+#define TRY(expr)                              \
+    do {                                       \
+        eg_status st_ = (expr);                \
+        if (st_ != EG_SUCCESS) return st_;     \
+    } while (0)
+
+static inline unsigned grid_for(size_t threads, unsigned block) { return (unsigned)((threads + block - 1) / block); }
+
+// ------------------------------------------------------------------- launchers (the only kernel start sites)
+
+#ifdef EG_HOSTSIM
+#define EG_FOR_HOST(total, stmt) for (size_t tid = 0; tid < (size_t)(total); tid++) { stmt; }
+#endif
+
+static void launch_decode(eg_ctx *ctx, const decode_params &P) {
+    size_t total = P.n * (size_t)P.n_slots;
+#ifdef EG_HOSTSIM
+    EG_FOR_HOST(total, decode_body(P, tid % P.n, (int)(tid / P.n)))
+#else
+    k_decode<<<grid_for(total, 256), 256, 0, ctx->stream>>>(P);
+#endif
+    ctx->launches++;
+}
+
+static void launch_scalars(eg_ctx *ctx, const scalars_params &P) {
+#ifdef EG_HOSTSIM
+    EG_FOR_HOST(P.n, scalars_body(P, tid))
+#else
+    k_scalars<<<grid_for(P.n, 256), 256, 0, ctx->stream>>>(P);
+#endif
+    ctx->launches++;
+}
+
+static void launch_commit(eg_ctx *ctx, const commit_params &P) {
+    size_t total = P.n * (size_t)P.n_slots;
+    if (ctx->commit_ev_used + 2 > ctx->commit_ev.size()) {
+        cudaEvent_t a = nullptr, b = nullptr;
+        cudaEventCreate(&a); cudaEventCreate(&b);
+        ctx->commit_ev.push_back(a); ctx->commit_ev.push_back(b);
+    }
+    cudaEvent_t e_start = ctx->commit_ev[ctx->commit_ev_used], e_stop = ctx->commit_ev[ctx->commit_ev_used + 1];
+    ctx->commit_ev_used += 2;
+    cudaEventRecord(e_start, ctx->stream);
+#ifdef EG_HOSTSIM
+    EG_FOR_HOST(total, commit_body(P, tid % P.n, (int)(tid / P.n), P.table_g, P.table_k))
+#else
+    k_commit<<<grid_for(total, EG_COMMIT_THREADS), EG_COMMIT_THREADS, 0, ctx->stream>>>(P);
+#endif
+    cudaEventRecord(e_stop, ctx->stream);
+    ctx->launches++;
+    ctx->commit_launches++;
+    ctx->commit_tasks += total;
+    ctx->call_commit_tasks += total;
+    ctx->call_commit_launches++;
+}
+
+static void launch_ring_hash(eg_ctx *ctx, const ring_hash_params &P) {
+    size_t total = P.n * (size_t)P.n_slots;
+#ifdef EG_HOSTSIM
+    EG_FOR_HOST(total, ring_hash_body(P, tid % P.n, (int)(tid / P.n)))
+#else
+    k_ring_hash<<<grid_for(total, 128), 128, 0, ctx->stream>>>(P);
+#endif
+    ctx->launches++;
+}
+
+static void launch_ring_final(eg_ctx *ctx, const ring_final_params &P) {
+#ifdef EG_HOSTSIM
+    EG_FOR_HOST(P.n, ring_final_body(P, tid))
+#else
+    k_ring_final<<<grid_for(P.n, 128), 128, 0, ctx->stream>>>(P);
+#endif
+    ctx->launches++;
+}
+
+static void launch_logeq_final(eg_ctx *ctx, const logeq_final_params &P) {
+#ifdef EG_HOSTSIM
+    EG_FOR_HOST(P.n, logeq_final_body(P, tid))
+#else
+    k_logeq_final<<<grid_for(P.n, 128), 128, 0, ctx->stream>>>(P);
+#endif
+    ctx->launches++;
+}
+
+static void launch_choice_sum(eg_ctx *ctx, const choice_sum_params &P) {
+#ifdef EG_HOSTSIM
+    EG_FOR_HOST(2 * P.n, choice_sum_body(P, tid % P.n, (int)(tid / P.n)))
+#else
+    k_choice_sum<<<grid_for(2 * P.n, 128), 128, 0, ctx->stream>>>(P);
+#endif
+    ctx->launches++;
+}
+
+static void launch_range_last(eg_ctx *ctx, const range_last_params &P) {
+#ifdef EG_HOSTSIM
+    EG_FOR_HOST(2 * P.n, range_last_body(P, tid % P.n, (int)(tid / P.n)))
+#else
+    k_range_last<<<grid_for(2 * P.n, 128), 128, 0, ctx->stream>>>(P);
+#endif
+    ctx->launches++;
+}
+
+static void launch_verdict(eg_ctx *ctx, const verdict_params &P) {
+#ifdef EG_HOSTSIM
+    EG_FOR_HOST(P.n, verdict_body(P, tid))
+#else
+    k_verdict<<<grid_for(P.n, 256), 256, 0, ctx->stream>>>(P);
+#endif
+    ctx->launches++;
+}
+
+static void launch_build_table(eg_ctx *ctx, const uint32_t *enc_words, int use_generator, uint32_t *table, uint32_t *status) {
+#ifdef EG_HOSTSIM
+    EG_FOR_HOST(EG_FIXED_TABLE_ENTRIES, build_table_body((int)tid, enc_words, use_generator, table, status))
+#else
+    k_build_table<<<1, EG_FIXED_TABLE_ENTRIES, 0, ctx->stream>>>(enc_words, use_generator, table, status);
+#endif
+    ctx->launches++;
+}
+
+static void launch_admissible(eg_ctx *ctx, const uint64_t *values, int count, uint32_t *adm) {
+#ifdef EG_HOSTSIM
+    EG_FOR_HOST(count, admissible_body((int)tid, values, adm))
+#else
+    k_admissible<<<grid_for(count, 64), 64, 0, ctx->stream>>>(values, count, adm);
+#endif
+    ctx->launches++;
+}
+
+// per-slot masked sums of planar points into `partial` (blocks per slot returned)
+static int launch_tally_partial(eg_ctx *ctx, const uint32_t *pts, size_t n, int n_slots, const uint8_t *verdicts, uint32_t *partial) {
+    const int blocks = (int)std::max<size_t>(1, std::min<size_t>(EG_TALLY_BLOCKS, (n + EG_TALLY_THREADS - 1) / EG_TALLY_THREADS));
+#ifdef EG_HOSTSIM
+    for (int slot = 0; slot < n_slots; slot++)
+        for (int b = 0; b < blocks; b++) {
+            ge_ext acc = ge_identity(), q;
+            for (size_t i = (size_t)b; i < n; i += (size_t)blocks)
+                if (verdicts[i] == 0) { planar_load_point(q, pts, n, slot, i); ge_add(acc, acc, q); }
+            point_to_words32(partial + ((size_t)slot * blocks + b) * 32, acc);
+        }
+#else
+    dim3 grid(blocks, n_slots);
+    k_tally_partial<<<grid, EG_TALLY_THREADS, 0, ctx->stream>>>(pts, n, verdicts, partial);
+#endif
+    ctx->launches++;
+    return blocks;
+}
+
+static void launch_tally_final(eg_ctx *ctx, const uint32_t *partial, int count, int n_slots, uint32_t *running, int accumulate,
+                               uint8_t *encode_out) {
+#ifdef EG_HOSTSIM
+    for (int slot = 0; slot < n_slots; slot++) {
+        ge_ext acc = ge_identity(), q;
+        for (int i = 0; i < count; i++) { point_from_words32(q, partial + ((size_t)slot * count + i) * 32); ge_add(acc, acc, q); }
+        uint32_t *r = running + (size_t)slot * 32;
+        if (accumulate) { point_from_words32(q, r); ge_add(acc, acc, q); }
+        point_to_words32(r, acc);
+        if (encode_out) { uint32_t w[8]; ge_encode(w, acc); store32_bytes(encode_out + 32 * slot, w); }
+    }
+#else
+    k_tally_final<<<n_slots, 32, 0, ctx->stream>>>(partial, count, running, accumulate, encode_out);
+#endif
+    ctx->launches++;
+}
+
+static void launch_elements_validate(eg_ctx *ctx, const uint8_t *enc, size_t n, uint8_t *ok) {
+#ifdef EG_HOSTSIM
+    EG_FOR_HOST(n, elements_validate_body(tid, enc, ok))
+#else
+    k_elements_validate<<<grid_for(n, 128), 128, 0, ctx->stream>>>(enc, n, ok);
+#endif
+    ctx->launches++;
+}
+
+static void launch_scalars_validate(eg_ctx *ctx, const uint8_t *sc_in, size_t n, uint8_t *ok) {
+#ifdef EG_HOSTSIM
+    EG_FOR_HOST(n, scalars_validate_body(tid, sc_in, ok))
+#else
+    k_scalars_validate<<<grid_for(n, 256), 256, 0, ctx->stream>>>(sc_in, n, ok);
+#endif
+    ctx->launches++;
+}
+
+static void launch_scalars_from_wide(eg_ctx *ctx, const uint8_t *wide, size_t n, uint8_t *out) {
+#ifdef EG_HOSTSIM
+    EG_FOR_HOST(n, scalars_from_wide_body(tid, wide, out))
+#else
+    k_scalars_from_wide<<<grid_for(n, 256), 256, 0, ctx->stream>>>(wide, n, out);
+#endif
+    ctx->launches++;
+}
+
+static void launch_double_mul(eg_ctx *ctx, const uint8_t *a, const uint8_t *A, const uint8_t *b, size_t n, int mode, uint8_t *out, uint8_t *okv) {
+#ifdef EG_HOSTSIM
+    EG_FOR_HOST(n, double_mul_body(tid, a, A, b, mode, ctx->d_table_g, out, okv))
+#else
+    k_double_mul<<<grid_for(n, EG_COMMIT_THREADS), EG_COMMIT_THREADS, 0, ctx->stream>>>(a, A, b, n, mode, ctx->d_table_g, out, okv);
+#endif
+    ctx->launches++;
+}
+
+static void launch_ciphertexts_sum(eg_ctx *ctx, const uint8_t *parts, size_t n_parts, size_t n_cts, uint8_t *out, uint32_t *bad) {
+#ifdef EG_HOSTSIM
+    EG_FOR_HOST(2 * n_cts, ciphertexts_sum_body(tid, parts, n_parts, n_cts, out, bad))
+#else
+    k_ciphertexts_sum<<<grid_for(2 * n_cts, 64), 64, 0, ctx->stream>>>(parts, n_parts, n_cts, out, bad);
+#endif
+    ctx->launches++;
+}
+
+extern "C" const char *eg_version(void) { return "eg_b200 0.1.0 sm_100a"; }
+
+extern "C" const char *eg_last_error(const eg_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" uint64_t eg_kernel_launch_count(const eg_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" void *eg_ctx_stream(const eg_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+extern "C" eg_status eg_last_commit_stats(const eg_ctx *ctx, uint64_t *launches, uint64_t *tasks, float *ms) {
+    if (!ctx) return EG_ERR_INVALID_ARG;
+    if (launches) *launches = ctx->call_commit_launches;
+    if (tasks) *tasks = ctx->call_commit_tasks;
+    if (ms) *ms = ctx->timings[2];
+    return EG_SUCCESS;
+}
+
+extern "C" eg_status eg_last_timings(const eg_ctx *ctx, float out_ms[5]) {
+    if (!ctx || !out_ms) return EG_ERR_INVALID_ARG;
+    for (int i = 0; i < 5; i++) out_ms[i] = ctx->timings[i];
+    return EG_SUCCESS;
+}
+
+
+extern "C" eg_status eg_selftest_field(eg_ctx *ctx, size_t n, uint64_t seed, uint64_t *mismatches) {
+    if (!ctx || !mismatches) return EG_ERR_INVALID_ARG;
+    CU(cudaSetDevice(ctx->device));
+    *mismatches = 0;
+#ifndef EG_HOSTSIM
+    unsigned long long *d = (unsigned long long *)(ctx->d_status + 64);
+    CU(cudaMemsetAsync(d, 0, 8, ctx->stream));
+    k_selftest_field<<<grid_for(n, 128), 128, 0, ctx->stream>>>(n, seed, d);
+    ctx->launches++;
+    unsigned long long h = 0;
+    CU(cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    *mismatches = h;
+#else
+    (void)n; (void)seed;
+#endif
+    return EG_SUCCESS;
+}
+
+extern "C" eg_status eg_ctx_set_chunk_items(eg_ctx *ctx, size_t items) {
+    if (!ctx) return EG_ERR_INVALID_ARG;
+    ctx->chunk_items = items;
+    return EG_SUCCESS;
+}
+
+extern "C" eg_status eg_ctx_create(int device_id, eg_ctx **out) {
+    if (!out) return EG_ERR_INVALID_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0 || device_id < 0 || device_id >= count) {
+        cudaGetLastError();
+        return EG_ERR_NO_DEVICE;
+    }
+    eg_ctx *ctx = new (std::nothrow) eg_ctx();
+    if (!ctx) return EG_ERR_OUT_OF_MEMORY;
+    ctx->device = device_id;
+    auto bail = [&](eg_status st) { eg_ctx_destroy(ctx); return st; };
+    if (cudaSetDevice(device_id) != cudaSuccess) return bail(EG_ERR_NO_DEVICE);
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(EG_ERR_CUDA);
+    for (auto &e : ctx->ev) if (cudaEventCreate(&e) != cudaSuccess) return bail(EG_ERR_CUDA);
+    if (cudaMalloc(&ctx->d_table_g, EG_FIXED_TABLE_WORDS * 4) != cudaSuccess) return bail(EG_ERR_OUT_OF_MEMORY);
+    if (cudaMalloc(&ctx->d_table_k, EG_FIXED_TABLE_WORDS * 4) != cudaSuccess) return bail(EG_ERR_OUT_OF_MEMORY);
+    if (cudaMalloc(&ctx->d_status, 1024) != cudaSuccess) return bail(EG_ERR_OUT_OF_MEMORY);
+    launch_build_table(ctx, nullptr, 1, ctx->d_table_g, ctx->d_status);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) return bail(EG_ERR_CUDA);
+    *out = ctx;
+    return EG_SUCCESS;
+}
+
+extern "C" void eg_ctx_destroy(eg_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    dev_buf *bufs[] = {&ctx->pts, &ctx->enc, &ctx->commit, &ctx->chal, &ctx->flags, &ctx->res[0], &ctx->res[1], &ctx->res[2],
+                       &ctx->in[0], &ctx->in[1], &ctx->in[2], &ctx->in[3], &ctx->verdicts, &ctx->partial, &ctx->running,
+                       &ctx->adm, &ctx->misc};
+    for (dev_buf *b : bufs) if (b->p) cudaFree(b->p);
+    if (ctx->d_table_g) cudaFree(ctx->d_table_g);
+    if (ctx->d_table_k) cudaFree(ctx->d_table_k);
+    if (ctx->d_status) cudaFree(ctx->d_status);
+    for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
+    for (auto &e : ctx->commit_ev) if (e) cudaEventDestroy(e);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" eg_status eg_ctx_set_receiver(eg_ctx *ctx, const uint8_t key[32]) {
+    if (!ctx || !key) return EG_ERR_INVALID_ARG;
+    CU(cudaSetDevice(ctx->device));
+    uint32_t *d_key = ctx->d_status + 8;
+    CU(cudaMemcpyAsync(d_key, key, 32, cudaMemcpyHostToDevice, ctx->stream));
+    launch_build_table(ctx, d_key, 0, ctx->d_table_k, ctx->d_status);
+    uint32_t status = 0;
+    CU(cudaMemcpyAsync(&status, ctx->d_status, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    if (status == 1) { ctx->has_receiver = false; return fail(ctx, EG_ERR_INVALID_ELEMENT, "receiver key does not represent a group element"); }
+    if (status == 2) { ctx->has_receiver = false; return fail(ctx, EG_ERR_IDENTITY_KEY, "receiver key is the group identity"); }
+    memcpy(ctx->key, key, 32);
+    ctx->has_receiver = true;
+    return EG_SUCCESS;
+}
+
+// =================================================================== ring-proof engine
+
+// Host description of one batch of RingProof::verify calls sharing a shape (ring.rs:302-374).
+struct ring_job {
+    uint32_t n_rings = 0;
+    uint32_t sizes[EG_MAX_RINGS];
+    uint32_t ct_p_index[EG_MAX_RINGS];      // ring r ciphertext: R at ct_p_index[r], B at +1
+    uint32_t ct_enc_index[EG_MAX_RINGS];    // enc(R) at ct_enc_index[r], enc(B) at +1
+    int32_t adm_index[EG_MAX_RINGS];        // admissible value j of ring r (j >= 1) at adm_index[r] + j; -1: [O, G] pair
+    uint8_t proof_buf = 0;                  // input buffer of the ring proof (e0 | responses)
+    uint32_t proof_offset = 0;              // byte offset of the proof inside the item
+    uint32_t commit_index0 = 0;             // planar commitments: ring r -> commit_index0 + 2r (+1)
+    uint32_t chal_index0 = 0;               // planar challenges: ring r -> chal_index0 + r
+    transcript prefix;                      // after initialize_transcript (ring.rs:290-293)
+    uint32_t *d_result = nullptr;
+};
+
+static void host_ring_initialize(transcript &t, const uint8_t key[32]) {      // ring.rs:290-293
+    merlin_append_message(t, EG_LBL("dom-sep"), (const uint8_t *)"multi_ring_enc", 14);
+    merlin_append_message(t, EG_LBL("K"), key, 32);
+}
+
+// Launch every stage of the ring engine.  `extra` are additional commit slots evaluated together with stage 0
+// (e.g. the sum proof of an EncryptedChoice), so that the first launch is as wide as possible.
+static eg_status run_ring_job(eg_ctx *ctx, const ring_job &job, const in_bufs &in, size_t n, const commit_slot *extra, int n_extra,
+                              const uint32_t *d_adm) {
+    uint32_t max_size = 0, starts[EG_MAX_RINGS], start = 0;
+    for (uint32_t r = 0; r < job.n_rings; r++) { starts[r] = start; start += job.sizes[r]; max_size = std::max(max_size, job.sizes[r]); }
+    for (uint32_t j = 0; j < max_size; j++) {
+        // ---- commitments of equation j for every ring that has one (ring.rs:342-350)
+        uint32_t r0 = 0;
+        bool first_launch = true;
+        while (r0 < job.n_rings || (first_launch && j == 0 && n_extra > 0)) {
+            commit_params cp;
+            memset(&cp, 0, sizeof cp);
+            cp.in = in; cp.n = n;
+            cp.pts = (const uint32_t *)ctx->pts.p; cp.chal = (const uint32_t *)ctx->chal.p; cp.commit = (uint32_t *)ctx->commit.p;
+            cp.adm = d_adm; cp.table_g = ctx->d_table_g; cp.table_k = ctx->d_table_k;
+            int ns = 0;
+            if (first_launch && j == 0)
+                for (int k = 0; k < n_extra; k++) cp.slots[ns++] = extra[k];
+            first_launch = false;
+            for (; r0 < job.n_rings && ns + 2 <= EG_MAX_SLOTS; r0++) {
+                if (job.sizes[r0] <= j) continue;
+                for (int side = 0; side < 2; side++) {
+                    commit_slot s;
+                    memset(&s, 0, sizeof s);
+                    s.p_index = job.ct_p_index[r0] + side;
+                    s.adm_index = -1;
+                    if (side == 1 && j >= 1) s.adm_index = job.adm_index[r0] + (int32_t)j;
+                    s.base = (uint8_t)side;
+                    s.e_planar = j > 0;
+                    s.e_buf = job.proof_buf; s.s_buf = job.proof_buf;
+                    s.e_offset = j > 0 ? job.chal_index0 + r0 : job.proof_offset;
+                    s.s_offset = job.proof_offset + 32 * (1 + starts[r0] + j);
+                    s.out_index = job.commit_index0 + 2 * r0 + side;
+                    cp.slots[ns++] = s;
+                }
+            }
+            if (ns == 0) break;
+            cp.n_slots = ns;
+            launch_commit(ctx, cp);
+        }
+        // ---- next challenge for rings with a further equation (ring.rs:354-360)
+        r0 = 0;
+        while (r0 < job.n_rings) {
+            ring_hash_params hp;
+            memset(&hp, 0, sizeof hp);
+            hp.n = n; hp.prefix = job.prefix;
+            hp.enc = (const uint32_t *)ctx->enc.p; hp.commit = (const uint32_t *)ctx->commit.p; hp.chal = (uint32_t *)ctx->chal.p;
+            int ns = 0;
+            for (; r0 < job.n_rings && ns < EG_MAX_SLOTS; r0++) {
+                if (job.sizes[r0] <= j + 1) continue;
+                ring_hash_slot s;
+                s.ring_index = r0; s.eq_index = j;
+                s.enc_index = job.ct_enc_index[r0];
+                s.commit_index = job.commit_index0 + 2 * r0;
+                s.chal_index = job.chal_index0 + r0;
+                hp.slots[ns++] = s;
+            }
+            if (ns == 0) break;
+            hp.n_slots = ns;
+            launch_ring_hash(ctx, hp);
+        }
+    }
+    ring_final_params fp;
+    memset(&fp, 0, sizeof fp);
+    fp.in = in; fp.n = n; fp.n_rings = job.n_rings; fp.commit_index0 = job.commit_index0;
+    fp.proof_buf = job.proof_buf; fp.cc_offset = job.proof_offset; fp.prefix = job.prefix;
+    fp.commit = (const uint32_t *)ctx->commit.p; fp.result = job.d_result;
+    launch_ring_final(ctx, fp);
+    return EG_SUCCESS;
+}
+
+// The [O, G] admissible pair used by bool / choice rings: index 1 holds cached(G)
+static eg_status ensure_bool_adm(eg_ctx *ctx) {
+    if (ctx->adm.p && ctx->adm_cache_key.count("bool")) return EG_SUCCESS;
+    TRY(ensure(ctx, ctx->adm, 4096 * 128));
+    uint64_t vals[2] = {0, 1};
+    uint64_t *d_vals = (uint64_t *)(ctx->d_status + 32);   // byte 128 of the 1 KB status block
+    CU(cudaMemcpyAsync(d_vals, vals, sizeof vals, cudaMemcpyHostToDevice, ctx->stream));
+    launch_admissible(ctx, d_vals, 2, (uint32_t *)ctx->adm.p);
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->adm_cache_key.clear();
+    ctx->adm_cache_key["bool"] = {0, 1};
+    return EG_SUCCESS;
+}
+
+static size_t default_chunk(const eg_ctx *ctx) { return ctx->chunk_items ? ctx->chunk_items : ((size_t)1 << 18); }
+
+static eg_status begin_call(eg_ctx *ctx) {
+    if (!ctx) return EG_ERR_INVALID_ARG;
+    if (!ctx->has_receiver) return fail(ctx, EG_ERR_NO_RECEIVER, "eg_ctx_set_receiver has not been called");
+    CU(cudaSetDevice(ctx->device));
+    ctx->err.clear();
+    ctx->commit_ev_used = 0;
+    ctx->call_commit_tasks = 0;
+    ctx->call_commit_launches = 0;
+    return EG_SUCCESS;
+}
+
+static eg_status finish_call(eg_ctx *ctx) {
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    float commit_ms = 0;
+    for (size_t k = 0; k + 1 < ctx->commit_ev_used; k += 2) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, ctx->commit_ev[k], ctx->commit_ev[k + 1]) == cudaSuccess) commit_ms += ms;
+    }
+    ctx->timings[2] = commit_ms;
+    return EG_SUCCESS;
+}
+
+// =================================================================== verify_bool
+
+// one chunk, device pointers
+static eg_status verify_bool_chunk(eg_ctx *ctx, size_t n, const uint8_t *d_cts, const uint8_t *d_proofs, uint8_t *d_verdicts) {
+    TRY(ensure(ctx, ctx->pts, n * 2 * 128));
+    TRY(ensure(ctx, ctx->enc, n * 2 * 32));
+    TRY(ensure(ctx, ctx->commit, n * 2 * 32));
+    TRY(ensure(ctx, ctx->chal, n * 1 * 32));
+    TRY(ensure(ctx, ctx->flags, n * 4));
+    TRY(ensure(ctx, ctx->res[0], n * 4));
+    TRY(ensure_bool_adm(ctx));
+    CU(cudaMemsetAsync(ctx->flags.p, 0, n * 4, ctx->stream));
+    in_bufs in;
+    memset(&in, 0, sizeof in);
+    in.buf[0] = d_cts; in.stride[0] = 64;
+    in.buf[1] = d_proofs; in.stride[1] = 96;
+
+    decode_params dp;
+    memset(&dp, 0, sizeof dp);
+    dp.in = in; dp.n = n; dp.n_slots = 2;
+    for (int k = 0; k < 2; k++) { dp.slots[k].buf = 0; dp.slots[k].want_enc = 1; dp.slots[k].enc_index = (uint16_t)k; dp.slots[k].offset = 32 * k; dp.slots[k].p_index = k; }
+    dp.pts = (uint32_t *)ctx->pts.p; dp.enc = (uint32_t *)ctx->enc.p; dp.flags = (uint32_t *)ctx->flags.p;
+    launch_decode(ctx, dp);
+
+    scalars_params sp;
+    memset(&sp, 0, sizeof sp);
+    sp.in = in; sp.n = n; sp.n_slots = 1; sp.slots[0].buf = 1; sp.slots[0].offset = 0; sp.slots[0].count = 3;
+    sp.flags = (uint32_t *)ctx->flags.p;
+    launch_scalars(ctx, sp);
+
+    ring_job job;
+    job.n_rings = 1; job.sizes[0] = 2; job.ct_p_index[0] = 0; job.ct_enc_index[0] = 0; job.adm_index[0] = 0;
+    job.proof_buf = 1; job.proof_offset = 0; job.commit_index0 = 0; job.chal_index0 = 0;
+    merlin_new(job.prefix, EG_LBL("bool_encryption"));            // keys/impls.rs:111
+    host_ring_initialize(job.prefix, ctx->key);
+    job.d_result = (uint32_t *)ctx->res[0].p;
+    TRY(run_ring_job(ctx, job, in, n, nullptr, 0, (const uint32_t *)ctx->adm.p));
+
+    verdict_params vp;
+    memset(&vp, 0, sizeof vp);
+    vp.n = n; vp.flags = (const uint32_t *)ctx->flags.p; vp.n_checks = 1;
+    vp.check[0] = (const uint32_t *)ctx->res[0].p; vp.check_stride[0] = 1; vp.code[0] = EG_V_CHALLENGE_MISMATCH;
+    vp.verdicts = d_verdicts;
+    launch_verdict(ctx, vp);
+    return EG_SUCCESS;
+}
+
+extern "C" eg_status eg_verify_bool_batch_dev(eg_ctx *ctx, size_t n, const uint8_t *d_cts, const uint8_t *d_proofs, uint8_t *d_verdicts) {
+    TRY(begin_call(ctx));
+    if (n == 0) return EG_SUCCESS;
+    if (!d_cts || !d_proofs || !d_verdicts) return fail(ctx, EG_ERR_INVALID_ARG, "null pointer");
+    const size_t chunk = default_chunk(ctx);
+    for (size_t off = 0; off < n; off += chunk) {
+        size_t m = std::min(chunk, n - off);
+        TRY(verify_bool_chunk(ctx, m, d_cts + 64 * off, d_proofs + 96 * off, d_verdicts + off));
+    }
+    return finish_call(ctx);
+}
+
+extern "C" eg_status eg_verify_bool_batch(eg_ctx *ctx, size_t n, const uint8_t *cts, const uint8_t *proofs, uint8_t *verdicts) {
+    TRY(begin_call(ctx));
+    if (n == 0) return EG_SUCCESS;
+    if (!cts || !proofs || !verdicts) return fail(ctx, EG_ERR_INVALID_ARG, "null pointer");
+    const size_t chunk = default_chunk(ctx);
+    TRY(ensure(ctx, ctx->in[0], std::min(chunk, n) * 64));
+    TRY(ensure(ctx, ctx->in[1], std::min(chunk, n) * 96));
+    TRY(ensure(ctx, ctx->verdicts, std::min(chunk, n)));
+    for (size_t off = 0; off < n; off += chunk) {
+        size_t m = std::min(chunk, n - off);
+        CU(cudaMemcpyAsync(ctx->in[0].p, cts + 64 * off, m * 64, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->in[1].p, proofs + 96 * off, m * 96, cudaMemcpyHostToDevice, ctx->stream));
+        TRY(verify_bool_chunk(ctx, m, (const uint8_t *)ctx->in[0].p, (const uint8_t *)ctx->in[1].p, (uint8_t *)ctx->verdicts.p));
+        CU(cudaMemcpyAsync(verdicts + off, ctx->verdicts.p, m, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    return finish_call(ctx);
+}
+
+// =================================================================== verify_zero
+
+static eg_status verify_zero_chunk(eg_ctx *ctx, size_t n, const uint8_t *d_cts, const uint8_t *d_proofs, uint8_t *d_verdicts) {
+    TRY(ensure(ctx, ctx->pts, n * 2 * 128));
+    TRY(ensure(ctx, ctx->enc, n * 2 * 32));
+    TRY(ensure(ctx, ctx->commit, n * 2 * 32));
+    TRY(ensure(ctx, ctx->flags, n * 4));
+    TRY(ensure(ctx, ctx->res[0], n * 4));
+    CU(cudaMemsetAsync(ctx->flags.p, 0, n * 4, ctx->stream));
+    in_bufs in;
+    memset(&in, 0, sizeof in);
+    in.buf[0] = d_cts; in.stride[0] = 64;
+    in.buf[1] = d_proofs; in.stride[1] = 64;
+    decode_params dp;
+    memset(&dp, 0, sizeof dp);
+    dp.in = in; dp.n = n; dp.n_slots = 2;
+    for (int k = 0; k < 2; k++) { dp.slots[k].buf = 0; dp.slots[k].want_enc = 1; dp.slots[k].enc_index = (uint16_t)k; dp.slots[k].offset = 32 * k; dp.slots[k].p_index = k; }
+    dp.pts = (uint32_t *)ctx->pts.p; dp.enc = (uint32_t *)ctx->enc.p; dp.flags = (uint32_t *)ctx->flags.p;
+    launch_decode(ctx, dp);
+    scalars_params sp;
+    memset(&sp, 0, sizeof sp);
+    sp.in = in; sp.n = n; sp.n_slots = 1; sp.slots[0].buf = 1; sp.slots[0].offset = 0; sp.slots[0].count = 2;
+    sp.flags = (uint32_t *)ctx->flags.p;
+    launch_scalars(ctx, sp);
+    // log_equality.rs:160-164: [x]G = [-c]R + [s]G ; [x]K = [-c]B + [s]K
+    commit_params cp;
+    memset(&cp, 0, sizeof cp);
+    cp.in = in; cp.n = n; cp.n_slots = 2;
+    cp.pts = (const uint32_t *)ctx->pts.p; cp.commit = (uint32_t *)ctx->commit.p;
+    cp.table_g = ctx->d_table_g; cp.table_k = ctx->d_table_k;
+    for (int side = 0; side < 2; side++) {
+        commit_slot &s = cp.slots[side];
+        s.p_index = side; s.adm_index = -1; s.base = (uint8_t)side; s.e_planar = 0; s.e_buf = 1; s.s_buf = 1;
+        s.e_offset = 0; s.s_offset = 32; s.out_index = side;
+    }
+    launch_commit(ctx, cp);
+    logeq_final_params lp;
+    memset(&lp, 0, sizeof lp);
+    lp.in = in; lp.n = n; lp.pow_enc_index = 0; lp.commit_index = 0; lp.proof_buf = 1; lp.c_offset = 0;
+    merlin_new(lp.prefix, EG_LBL("zero_encryption"));              // keys/impls.rs:67
+    merlin_append_message(lp.prefix, EG_LBL("dom-sep"), (const uint8_t *)"log_eq", 6);
+    merlin_append_message(lp.prefix, EG_LBL("K"), ctx->key, 32);
+    lp.enc = (const uint32_t *)ctx->enc.p; lp.commit = (const uint32_t *)ctx->commit.p; lp.result = (uint32_t *)ctx->res[0].p;
+    launch_logeq_final(ctx, lp);
+    verdict_params vp;
+    memset(&vp, 0, sizeof vp);
+    vp.n = n; vp.flags = (const uint32_t *)ctx->flags.p; vp.n_checks = 1;
+    vp.check[0] = (const uint32_t *)ctx->res[0].p; vp.check_stride[0] = 1; vp.code[0] = EG_V_CHALLENGE_MISMATCH;
+    vp.verdicts = d_verdicts;
+    launch_verdict(ctx, vp);
+    return EG_SUCCESS;
+}
+
+extern "C" eg_status eg_verify_zero_batch(eg_ctx *ctx, size_t n, const uint8_t *cts, const uint8_t *proofs, uint8_t *verdicts) {
+    TRY(begin_call(ctx));
+    if (n == 0) return EG_SUCCESS;
+    if (!cts || !proofs || !verdicts) return fail(ctx, EG_ERR_INVALID_ARG, "null pointer");
+    const size_t chunk = default_chunk(ctx);
+    TRY(ensure(ctx, ctx->in[0], std::min(chunk, n) * 64));
+    TRY(ensure(ctx, ctx->in[1], std::min(chunk, n) * 64));
+    TRY(ensure(ctx, ctx->verdicts, std::min(chunk, n)));
+    for (size_t off = 0; off < n; off += chunk) {
+        size_t m = std::min(chunk, n - off);
+        CU(cudaMemcpyAsync(ctx->in[0].p, cts + 64 * off, m * 64, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->in[1].p, proofs + 64 * off, m * 64, cudaMemcpyHostToDevice, ctx->stream));
+        TRY(verify_zero_chunk(ctx, m, (const uint8_t *)ctx->in[0].p, (const uint8_t *)ctx->in[1].p, (uint8_t *)ctx->verdicts.p));
+        CU(cudaMemcpyAsync(verdicts + off, ctx->verdicts.p, m, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    return finish_call(ctx);
+}
+
+// =================================================================== EncryptedChoice::verify + tally
+
+// planar indexes for a choice chunk with m options:
+//   points   : 0..2m-1 ciphertexts (R_k at 2k, B_k at 2k+1), 2m: sum R, 2m+1: sum B - G
+//   enc      : same numbering
+//   commit   : ring r -> 2r, 2r+1 ; sum proof -> 2m, 2m+1
+//   chal     : ring r -> r
+static eg_status verify_choice_chunk(eg_ctx *ctx, size_t n, uint32_t m, int single, const uint8_t *d_choices, const uint8_t *d_rings,
+                                     const uint8_t *d_sums, uint8_t *d_verdicts, bool want_tally, bool first_chunk) {
+    const uint32_t np = 2 * m + 2;
+    TRY(ensure(ctx, ctx->pts, n * np * 128));
+    TRY(ensure(ctx, ctx->enc, n * np * 32));
+    TRY(ensure(ctx, ctx->commit, n * np * 32));
+    TRY(ensure(ctx, ctx->chal, n * m * 32));
+    TRY(ensure(ctx, ctx->flags, n * 4));
+    TRY(ensure(ctx, ctx->res[0], n * 4));
+    TRY(ensure(ctx, ctx->res[1], n * 4));
+    TRY(ensure_bool_adm(ctx));
+    CU(cudaMemsetAsync(ctx->flags.p, 0, n * 4, ctx->stream));
+    in_bufs in;
+    memset(&in, 0, sizeof in);
+    in.buf[0] = d_choices; in.stride[0] = 64 * m;
+    in.buf[1] = d_rings; in.stride[1] = 32 * (1 + 2 * m);
+    in.buf[2] = d_sums; in.stride[2] = 64;
+
+    CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+    // ---- decode all 2m input elements (serde / from_bytes stage of the reference)
+    for (uint32_t k0 = 0; k0 < 2 * m; k0 += EG_MAX_SLOTS) {
+        decode_params dp;
+        memset(&dp, 0, sizeof dp);
+        dp.in = in; dp.n = n;
+        int ns = 0;
+        for (uint32_t k = k0; k < 2 * m && ns < EG_MAX_SLOTS; k++, ns++) {
+            dp.slots[ns].buf = 0; dp.slots[ns].want_enc = 1; dp.slots[ns].enc_index = (uint16_t)k;
+            dp.slots[ns].offset = 32 * k; dp.slots[ns].p_index = k;
+        }
+        dp.n_slots = ns;
+        dp.pts = (uint32_t *)ctx->pts.p; dp.enc = (uint32_t *)ctx->enc.p; dp.flags = (uint32_t *)ctx->flags.p;
+        launch_decode(ctx, dp);
+    }
+    scalars_params sp;
+    memset(&sp, 0, sizeof sp);
+    sp.in = in; sp.n = n; sp.n_slots = single ? 2 : 1;
+    sp.slots[0].buf = 1; sp.slots[0].offset = 0; sp.slots[0].count = 1 + 2 * m;
+    sp.slots[1].buf = 2; sp.slots[1].offset = 0; sp.slots[1].count = 2;
+    sp.flags = (uint32_t *)ctx->flags.p;
+    launch_scalars(ctx, sp);
+
+    commit_slot extra[2];
+    int n_extra = 0;
+    if (single) {
+        // ---- choice.rs:363 + :83-86: sum ciphertext, powers (sum R, sum B - G)
+        choice_sum_params cs;
+        memset(&cs, 0, sizeof cs);
+        cs.n = n; cs.options = m; cs.out_p_index = 2 * m; cs.out_enc_index = 2 * m;
+        cs.pts = (uint32_t *)ctx->pts.p; cs.enc = (uint32_t *)ctx->enc.p;
+        launch_choice_sum(ctx, cs);
+        for (int side = 0; side < 2; side++) {
+            commit_slot &s = extra[side];
+            memset(&s, 0, sizeof s);
+            s.p_index = 2 * m + side; s.adm_index = -1; s.base = (uint8_t)side; s.e_planar = 0; s.e_buf = 2; s.s_buf = 2;
+            s.e_offset = 0; s.s_offset = 32; s.out_index = 2 * m + side;
+        }
+        n_extra = 2;
+    }
+    CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+
+    ring_job job;
+    job.n_rings = m;
+    for (uint32_t r = 0; r < m; r++) { job.sizes[r] = 2; job.ct_p_index[r] = 2 * r; job.ct_enc_index[r] = 2 * r; job.adm_index[r] = 0; }
+    job.proof_buf = 1; job.proof_offset = 0; job.commit_index0 = 0; job.chal_index0 = 0;
+    merlin_new(job.prefix, EG_LBL("encrypted_choice_ranges"));       // choice.rs:376
+    host_ring_initialize(job.prefix, ctx->key);
+    job.d_result = (uint32_t *)ctx->res[1].p;
+    TRY(run_ring_job(ctx, job, in, n, extra, n_extra, (const uint32_t *)ctx->adm.p));
+
+    if (single) {
+        logeq_final_params lp;
+        memset(&lp, 0, sizeof lp);
+        lp.in = in; lp.n = n; lp.pow_enc_index = 2 * m; lp.commit_index = 2 * m; lp.proof_buf = 2; lp.c_offset = 0;
+        merlin_new(lp.prefix, EG_LBL("choice_encryption_sum"));      // choice.rs:91
+        merlin_append_message(lp.prefix, EG_LBL("dom-sep"), (const uint8_t *)"log_eq", 6);
+        merlin_append_message(lp.prefix, EG_LBL("K"), ctx->key, 32);
+        lp.enc = (const uint32_t *)ctx->enc.p; lp.commit = (const uint32_t *)ctx->commit.p; lp.result = (uint32_t *)ctx->res[0].p;
+        launch_logeq_final(ctx, lp);
+    }
+    verdict_params vp;
+    memset(&vp, 0, sizeof vp);
+    vp.n = n; vp.flags = (const uint32_t *)ctx->flags.p;
+    int nc = 0;
+    if (single) { vp.check[nc] = (const uint32_t *)ctx->res[0].p; vp.check_stride[nc] = 1; vp.code[nc] = EG_V_CHOICE_SUM; nc++; }
+    vp.check[nc] = (const uint32_t *)ctx->res[1].p; vp.check_stride[nc] = 1; vp.code[nc] = EG_V_CHOICE_RANGE; nc++;
+    vp.n_checks = nc;
+    vp.verdicts = d_verdicts;
+    launch_verdict(ctx, vp);
+    CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+
+    if (want_tally) {
+        // ---- examples/voting.rs:200-203: totals += verified choices
+        TRY(ensure(ctx, ctx->partial, (size_t)2 * m * EG_TALLY_BLOCKS * 128));
+        TRY(ensure(ctx, ctx->running, (size_t)2 * m * 128));
+        const int blocks = launch_tally_partial(ctx, (const uint32_t *)ctx->pts.p, n, (int)(2 * m), d_verdicts, (uint32_t *)ctx->partial.p);
+        launch_tally_final(ctx, (const uint32_t *)ctx->partial.p, blocks, (int)(2 * m), (uint32_t *)ctx->running.p, first_chunk ? 0 : 1, nullptr);
+    }
+    CU(cudaEventRecord(ctx->ev[3], ctx->stream));
+    return EG_SUCCESS;
+}
+
+static eg_status tally_emit(eg_ctx *ctx, uint32_t m, uint8_t *d_tally_out) {
+    // encode the running totals: reuse k_tally_final with zero new partials
+    launch_tally_final(ctx, (const uint32_t *)ctx->partial.p, 0, (int)(2 * m), (uint32_t *)ctx->running.p, 1, d_tally_out);
+    return EG_SUCCESS;
+}
+
+static void collect_timings(eg_ctx *ctx, float acc[5]) {
+    float a = 0, b = 0, c = 0;
+    if (cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]) == cudaSuccess) acc[0] += a;
+    if (cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[2]) == cudaSuccess) acc[1] += b;
+    if (cudaEventElapsedTime(&c, ctx->ev[2], ctx->ev[3]) == cudaSuccess) acc[3] += c;
+    acc[4] += a + b + c;
+}
+
+extern "C" eg_status eg_verify_choice_batch_dev(eg_ctx *ctx, size_t n, uint32_t options, int single, const uint8_t *d_choices,
+                                                const uint8_t *d_rings, const uint8_t *d_sums, uint8_t *d_verdicts, uint8_t *d_tally) {
+    TRY(begin_call(ctx));
+    if (options == 0 || options > EG_MAX_RINGS) return fail(ctx, EG_ERR_INVALID_ARG, "options must be in 1..64");
+    if (n && (!d_choices || !d_rings || !d_verdicts || (single && !d_sums))) return fail(ctx, EG_ERR_INVALID_ARG, "null pointer");
+    float acc[5] = {0, 0, 0, 0, 0};
+    const size_t chunk = default_chunk(ctx);
+    TRY(ensure(ctx, ctx->partial, (size_t)2 * options * EG_TALLY_BLOCKS * 128));
+    TRY(ensure(ctx, ctx->running, (size_t)2 * options * 128));
+    bool first = true;
+    for (size_t off = 0; off < n; off += chunk) {
+        size_t m = std::min(chunk, n - off);
+        TRY(verify_choice_chunk(ctx, m, options, single, d_choices + 64 * options * off, d_rings + 32 * (1 + 2 * options) * off,
+                                d_sums ? d_sums + 64 * off : nullptr, d_verdicts + off, d_tally != nullptr, first));
+        first = false;
+        CU(cudaStreamSynchronize(ctx->stream));
+        collect_timings(ctx, acc);
+    }
+    if (d_tally) {
+        if (first) {   // n == 0: the empty sum is the identity ciphertext in every option
+            launch_tally_final(ctx, (const uint32_t *)ctx->partial.p, 0, (int)(2 * options), (uint32_t *)ctx->running.p, 0, d_tally);
+        } else {
+            TRY(tally_emit(ctx, options, d_tally));
+        }
+    }
+    { float keep = ctx->timings[2]; memcpy(ctx->timings, acc, sizeof acc); ctx->timings[2] = keep; }
+    return finish_call(ctx);
+}
+
+extern "C" eg_status eg_verify_choice_batch(eg_ctx *ctx, size_t n, uint32_t options, int single, const uint8_t *choices,
+                                            const uint8_t *rings, const uint8_t *sums, uint8_t *verdicts, uint8_t *tally) {
+    TRY(begin_call(ctx));
+    if (options == 0 || options > EG_MAX_RINGS) return fail(ctx, EG_ERR_INVALID_ARG, "options must be in 1..64");
+    if (n && (!choices || !rings || !verdicts || (single && !sums))) return fail(ctx, EG_ERR_INVALID_ARG, "null pointer");
+    float acc[5] = {0, 0, 0, 0, 0};
+    const size_t chunk = default_chunk(ctx), cm = std::min(chunk, std::max<size_t>(n, 1));
+    const size_t ring_stride = 32 * (1 + 2 * (size_t)options);
+    TRY(ensure(ctx, ctx->in[0], cm * 64 * options));
+    TRY(ensure(ctx, ctx->in[1], cm * ring_stride));
+    TRY(ensure(ctx, ctx->in[2], cm * 64));
+    TRY(ensure(ctx, ctx->verdicts, cm));
+    TRY(ensure(ctx, ctx->misc, 64 * (size_t)options));
+    TRY(ensure(ctx, ctx->partial, (size_t)2 * options * EG_TALLY_BLOCKS * 128));
+    TRY(ensure(ctx, ctx->running, (size_t)2 * options * 128));
+    bool first = true;
+    for (size_t off = 0; off < n; off += chunk) {
+        size_t m = std::min(chunk, n - off);
+        CU(cudaMemcpyAsync(ctx->in[0].p, choices + 64 * options * off, m * 64 * options, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->in[1].p, rings + ring_stride * off, m * ring_stride, cudaMemcpyHostToDevice, ctx->stream));
+        if (single) CU(cudaMemcpyAsync(ctx->in[2].p, sums + 64 * off, m * 64, cudaMemcpyHostToDevice, ctx->stream));
+        TRY(verify_choice_chunk(ctx, m, options, single, (const uint8_t *)ctx->in[0].p, (const uint8_t *)ctx->in[1].p,
+                                single ? (const uint8_t *)ctx->in[2].p : nullptr, (uint8_t *)ctx->verdicts.p, tally != nullptr, first));
+        first = false;
+        CU(cudaMemcpyAsync(verdicts + off, ctx->verdicts.p, m, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        collect_timings(ctx, acc);
+    }
+    if (tally) {
+        if (first) {
+            launch_tally_final(ctx, (const uint32_t *)ctx->partial.p, 0, (int)(2 * options), (uint32_t *)ctx->running.p, 0, (uint8_t *)ctx->misc.p);
+        } else {
+            TRY(tally_emit(ctx, options, (uint8_t *)ctx->misc.p));
+        }
+        CU(cudaMemcpyAsync(tally, ctx->misc.p, 64 * (size_t)options, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    { float keep = ctx->timings[2]; memcpy(ctx->timings, acc, sizeof acc); ctx->timings[2] = keep; }
+    return finish_call(ctx);
+}
+
+// =================================================================== group-level helpers
+
+extern "C" eg_status eg_elements_validate(eg_ctx *ctx, size_t n, const uint8_t *encodings, uint8_t *ok) {
+    if (!ctx || (n && (!encodings || !ok))) return EG_ERR_INVALID_ARG;
+    CU(cudaSetDevice(ctx->device));
+    if (n == 0) return EG_SUCCESS;
+    TRY(ensure(ctx, ctx->in[0], n * 32));
+    TRY(ensure(ctx, ctx->verdicts, n));
+    CU(cudaMemcpyAsync(ctx->in[0].p, encodings, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    launch_elements_validate(ctx, (const uint8_t *)ctx->in[0].p, n, (uint8_t *)ctx->verdicts.p);
+    CU(cudaMemcpyAsync(ok, ctx->verdicts.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+    return finish_call(ctx);
+}
+
+extern "C" eg_status eg_scalars_validate(eg_ctx *ctx, size_t n, const uint8_t *scalars, uint8_t *ok) {
+    if (!ctx || (n && (!scalars || !ok))) return EG_ERR_INVALID_ARG;
+    CU(cudaSetDevice(ctx->device));
+    if (n == 0) return EG_SUCCESS;
+    TRY(ensure(ctx, ctx->in[0], n * 32));
+    TRY(ensure(ctx, ctx->verdicts, n));
+    CU(cudaMemcpyAsync(ctx->in[0].p, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    launch_scalars_validate(ctx, (const uint8_t *)ctx->in[0].p, n, (uint8_t *)ctx->verdicts.p);
+    CU(cudaMemcpyAsync(ok, ctx->verdicts.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+    return finish_call(ctx);
+}
+
+extern "C" eg_status eg_scalars_from_wide(eg_ctx *ctx, size_t n, const uint8_t *wide, uint8_t *scalars) {
+    if (!ctx || (n && (!wide || !scalars))) return EG_ERR_INVALID_ARG;
+    CU(cudaSetDevice(ctx->device));
+    if (n == 0) return EG_SUCCESS;
+    TRY(ensure(ctx, ctx->in[0], n * 64));
+    TRY(ensure(ctx, ctx->in[1], n * 32));
+    CU(cudaMemcpyAsync(ctx->in[0].p, wide, n * 64, cudaMemcpyHostToDevice, ctx->stream));
+    launch_scalars_from_wide(ctx, (const uint8_t *)ctx->in[0].p, n, (uint8_t *)ctx->in[1].p);
+    CU(cudaMemcpyAsync(scalars, ctx->in[1].p, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    return finish_call(ctx);
+}
+
+static eg_status double_mul_impl(eg_ctx *ctx, size_t n, const uint8_t *a, const uint8_t *A, const uint8_t *b, int mode, uint8_t *out, uint8_t *ok) {
+    if (!ctx || (n && (!b || !out || (mode == 0 && (!a || !A))))) return EG_ERR_INVALID_ARG;
+    CU(cudaSetDevice(ctx->device));
+    if (n == 0) return EG_SUCCESS;
+    TRY(ensure(ctx, ctx->in[0], n * 32));
+    TRY(ensure(ctx, ctx->in[1], n * 32));
+    TRY(ensure(ctx, ctx->in[2], n * 32));
+    TRY(ensure(ctx, ctx->in[3], n * 32));
+    TRY(ensure(ctx, ctx->verdicts, n));
+    if (mode == 0) {
+        CU(cudaMemcpyAsync(ctx->in[0].p, a, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->in[1].p, A, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CU(cudaMemcpyAsync(ctx->in[2].p, b, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    launch_double_mul(ctx, (const uint8_t *)ctx->in[0].p, (const uint8_t *)ctx->in[1].p, (const uint8_t *)ctx->in[2].p, n, mode,
+                      (uint8_t *)ctx->in[3].p, (uint8_t *)ctx->verdicts.p);
+    CU(cudaMemcpyAsync(out, ctx->in[3].p, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ok) CU(cudaMemcpyAsync(ok, ctx->verdicts.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+    return finish_call(ctx);
+}
+
+extern "C" eg_status eg_double_mul_generator_batch(eg_ctx *ctx, size_t n, const uint8_t *a, const uint8_t *A, const uint8_t *b,
+                                                   uint8_t *out, uint8_t *ok) {
+    return double_mul_impl(ctx, n, a, A, b, 0, out, ok);
+}
+
+extern "C" eg_status eg_mul_generator_batch(eg_ctx *ctx, size_t n, const uint8_t *k, uint8_t *out, uint8_t *ok) {
+    return double_mul_impl(ctx, n, nullptr, nullptr, k, 1, out, ok);
+}
+
+extern "C" eg_status eg_ciphertexts_sum(eg_ctx *ctx, size_t n_parts, size_t n_cts, const uint8_t *parts, uint8_t *out, uint8_t *ok) {
+    if (!ctx || !out || (n_parts && !parts)) return EG_ERR_INVALID_ARG;
+    CU(cudaSetDevice(ctx->device));
+    if (n_cts == 0) return EG_SUCCESS;
+    TRY(ensure(ctx, ctx->in[0], std::max<size_t>(1, n_parts) * n_cts * 64));
+    TRY(ensure(ctx, ctx->in[1], n_cts * 64));
+    uint32_t *d_bad = ctx->d_status + 4;
+    CU(cudaMemsetAsync(d_bad, 0, 4, ctx->stream));
+    if (n_parts) CU(cudaMemcpyAsync(ctx->in[0].p, parts, n_parts * n_cts * 64, cudaMemcpyHostToDevice, ctx->stream));
+    launch_ciphertexts_sum(ctx, (const uint8_t *)ctx->in[0].p, n_parts, n_cts, (uint8_t *)ctx->in[1].p, d_bad);
+    uint32_t bad = 0;
+    CU(cudaMemcpyAsync(out, ctx->in[1].p, n_cts * 64, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    TRY(finish_call(ctx));
+    if (ok) *ok = bad ? 0 : 1;
+    return EG_SUCCESS;
+}

@@ -1,0 +1,156 @@
+"""Thin numpy-facing wrapper over the C ABI: one Engine = one eg_ctx = one GPU."""
+import ctypes as C
+
+import numpy as np
+
+from . import _ffi
+
+
+class EngineError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__(f"{_ffi.STATUS_NAMES[status] if 0 <= status < len(_ffi.STATUS_NAMES) else status}: {message}")
+        self.status = status
+
+
+def _u8(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+def _addr(a):
+    return None if a is None else a.ctypes.data
+
+
+class Engine:
+    """Owns an eg_ctx on `device`.  `lib_path` exists for the test harness; the default is the in-tree CUDA library."""
+
+    def __init__(self, device=0, lib_path=None):
+        self.lib = _ffi.load(lib_path)
+        h = C.c_void_p()
+        st = self.lib.eg_ctx_create(device, C.byref(h))
+        if st != _ffi.SUCCESS:
+            raise EngineError(st, "eg_ctx_create failed (no CUDA device? the engine has no CPU fallback)")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.eg_ctx_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def _check(self, st):
+        if st != _ffi.SUCCESS:
+            raise EngineError(st, self.lib.eg_last_error(self.h).decode())
+
+    @property
+    def kernel_launches(self):
+        return self.lib.eg_kernel_launch_count(self.h)
+
+    @property
+    def stream(self):
+        return self.lib.eg_ctx_stream(self.h)
+
+    def last_timings(self):
+        t = (C.c_float * 5)()
+        self._check(self.lib.eg_last_timings(self.h, C.byref(t)))
+        return dict(zip(("decode_ms", "verify_ms", "commit_kernel_ms", "tally_ms", "total_ms"), t))
+
+    def last_commit_stats(self):
+        launches, tasks, ms = C.c_uint64(0), C.c_uint64(0), C.c_float(0)
+        self._check(self.lib.eg_last_commit_stats(self.h, C.byref(launches), C.byref(tasks), C.byref(ms)))
+        return {"launches": launches.value, "tasks": tasks.value, "ms": ms.value}
+
+    def selftest_field(self, n=1 << 16, seed=1):
+        m = C.c_uint64(0)
+        self._check(self.lib.eg_selftest_field(self.h, n, seed, C.byref(m)))
+        return m.value
+
+    def set_chunk_items(self, items):
+        self._check(self.lib.eg_ctx_set_chunk_items(self.h, items))
+
+    # ---- PublicKey::from_bytes
+    def set_receiver(self, key):
+        key = _u8(np.frombuffer(bytes(key), dtype=np.uint8), (32,))
+        self._check(self.lib.eg_ctx_set_receiver(self.h, _addr(key)))
+
+    # ---- group helpers
+    def elements_validate(self, enc):
+        enc = _u8(enc, (-1, 32))
+        ok = np.empty(enc.shape[0], np.uint8)
+        self._check(self.lib.eg_elements_validate(self.h, enc.shape[0], _addr(enc), _addr(ok)))
+        return ok.astype(bool)
+
+    def scalars_validate(self, s):
+        s = _u8(s, (-1, 32))
+        ok = np.empty(s.shape[0], np.uint8)
+        self._check(self.lib.eg_scalars_validate(self.h, s.shape[0], _addr(s), _addr(ok)))
+        return ok.astype(bool)
+
+    def scalars_from_wide(self, wide):
+        wide = _u8(wide, (-1, 64))
+        out = np.empty((wide.shape[0], 32), np.uint8)
+        self._check(self.lib.eg_scalars_from_wide(self.h, wide.shape[0], _addr(wide), _addr(out)))
+        return out
+
+    def double_mul_generator(self, a, A, b):
+        a, A, b = _u8(a, (-1, 32)), _u8(A, (-1, 32)), _u8(b, (-1, 32))
+        n = a.shape[0]
+        out, ok = np.empty((n, 32), np.uint8), np.empty(n, np.uint8)
+        self._check(self.lib.eg_double_mul_generator_batch(self.h, n, _addr(a), _addr(A), _addr(b), _addr(out), _addr(ok)))
+        return out, ok.astype(bool)
+
+    def mul_generator(self, k):
+        k = _u8(k, (-1, 32))
+        n = k.shape[0]
+        out, ok = np.empty((n, 32), np.uint8), np.empty(n, np.uint8)
+        self._check(self.lib.eg_mul_generator_batch(self.h, n, _addr(k), _addr(out), _addr(ok)))
+        return out, ok.astype(bool)
+
+    def ciphertexts_sum(self, parts):
+        parts = _u8(parts)
+        n_parts, n_cts = parts.shape[0], parts.shape[1]
+        parts = parts.reshape(n_parts, n_cts, 64)
+        out, ok = np.empty((n_cts, 64), np.uint8), np.zeros(1, np.uint8)
+        self._check(self.lib.eg_ciphertexts_sum(self.h, n_parts, n_cts, _addr(parts), _addr(out), _addr(ok)))
+        return out, bool(ok[0])
+
+    # ---- proofs
+    def verify_zero(self, cts, proofs):
+        cts, proofs = _u8(cts, (-1, 64)), _u8(proofs, (-1, 64))
+        n = cts.shape[0]
+        assert proofs.shape[0] == n
+        v = np.empty(n, np.uint8)
+        self._check(self.lib.eg_verify_zero_batch(self.h, n, _addr(cts), _addr(proofs), _addr(v)))
+        return v
+
+    def verify_bool(self, cts, proofs):
+        cts, proofs = _u8(cts, (-1, 64)), _u8(proofs, (-1, 96))
+        n = cts.shape[0]
+        assert proofs.shape[0] == n
+        v = np.empty(n, np.uint8)
+        self._check(self.lib.eg_verify_bool_batch(self.h, n, _addr(cts), _addr(proofs), _addr(v)))
+        return v
+
+    def verify_choice(self, options, choices, rings, sums=None, single=True, tally=True):
+        choices = _u8(choices, (-1, options, 64))
+        n = choices.shape[0]
+        rings = _u8(rings, (n, 1 + 2 * options, 32))
+        if single:
+            sums = _u8(sums, (n, 64))
+        v = np.empty(n, np.uint8)
+        t = np.empty((options, 64), np.uint8) if tally else None
+        self._check(self.lib.eg_verify_choice_batch(self.h, n, options, int(single), _addr(choices), _addr(rings),
+                                                    _addr(sums) if single else None, _addr(v), _addr(t)))
+        return v, t
+
+    # ---- device-pointer variants (ints are raw device addresses, e.g. torch.Tensor.data_ptr())
+    def verify_bool_dev(self, n, d_cts, d_proofs, d_verdicts):
+        self._check(self.lib.eg_verify_bool_batch_dev(self.h, n, d_cts, d_proofs, d_verdicts))
+
+    def verify_choice_dev(self, n, options, single, d_choices, d_rings, d_sums, d_verdicts, d_tally):
+        self._check(self.lib.eg_verify_choice_batch_dev(self.h, n, options, int(single), d_choices, d_rings, d_sums,
+                                                        d_verdicts, d_tally))

@@ -1,0 +1,222 @@
+/*
+ * eg_b200.h -- C ABI of the B200 batch engine for elastic-elgamal's verification hot path.
+ *
+ * This is the drop-in boundary: a batch entry point that is semantically
+ *     items.iter().map(|x| x.verify(&params))          (+ the homomorphic tally fold)
+ * for the reference's per-item calls.  Every function cites the reference interface it replaces.
+ * A Rust `-sys` crate binds these symbols 1:1 (see INTEGRATION.md and rust/); nothing here depends on
+ * torch, NCCL or C++ types: plain pointers and sizes only.
+ *
+ * Conventions
+ *   - All byte layouts follow the reference's `to_bytes` forms: Ciphertext = R || B (64 B,
+ *     src/encryption.rs:155-160); RingProof = e0 || s_0 || ... (src/proofs/ring.rs:383-393);
+ *     LogEqualityProof = c || s (src/proofs/log_equality.rs:184-189); VerifiableDecryption = 32 B element
+ *     (src/decryption.rs:118-122).  Batches are contiguous arrays of such items.
+ *   - Host entry points (`eg_*_batch`) take HOST pointers and copy to/from the device themselves.
+ *     `_dev` variants take DEVICE pointers on the context's device and run on the context's stream
+ *     (results are complete when the call returns).
+ *   - The return value reports API / CUDA failures only.  Per-item outcomes are verdict bytes that
+ *     enumerate the reference's error variants in the reference's precedence order.
+ *   - Never unwinds across the boundary.  A context is used from one host thread at a time (!Sync);
+ *     different contexts are independent.  There is no CPU fallback: without a CUDA device
+ *     eg_ctx_create fails with EG_ERR_NO_DEVICE.
+ */
+#ifndef EG_B200_H
+#define EG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct eg_ctx eg_ctx;
+typedef struct eg_dlog_table eg_dlog_table;
+typedef int32_t eg_status;
+
+enum {
+    EG_SUCCESS = 0,
+    EG_ERR_INVALID_ARG = 1,       /* null pointer, zero options, inconsistent sizes (reference: assert!/panic! on the caller side) */
+    EG_ERR_INVALID_ELEMENT = 2,   /* PublicKeyConversionError::InvalidGroupElement, src/keys/mod.rs:166-167 */
+    EG_ERR_IDENTITY_KEY = 3,      /* PublicKeyConversionError::IdentityKey, src/keys/mod.rs:168-169 */
+    EG_ERR_NO_RECEIVER = 4,       /* a verification entry point was called before eg_ctx_set_receiver */
+    EG_ERR_NO_DEVICE = 5,         /* no usable CUDA device (there is no CPU fallback) */
+    EG_ERR_CUDA = 6,              /* CUDA runtime failure; see eg_last_error */
+    EG_ERR_OUT_OF_MEMORY = 7,
+    EG_ERR_LEN_MISMATCH = 8       /* VerificationError::LenMismatch / OptionsLenMismatch (src/proofs/mod.rs:70-78,
+                                     src/app/choice.rs:149-158): in a fixed-stride batch this is an API-level error */
+};
+
+/* Per-item verdicts (uint8_t).  0 = Ok(..); the rest mirror the reference's error enums. */
+enum {
+    EG_V_OK = 0,
+    EG_V_MALFORMED = 1,           /* an element does not decode or a scalar is not canonical: the reference rejects
+                                     these before `verify`, in from_bytes / serde (src/proofs/ring.rs:397-414,
+                                     src/serde.rs:195-198,258-261, src/decryption.rs:168-177) */
+    EG_V_CHALLENGE_MISMATCH = 2,  /* VerificationError::ChallengeMismatch, src/proofs/mod.rs:63-69 */
+    EG_V_CHOICE_SUM = 3,          /* ChoiceVerificationError::Sum, src/app/choice.rs:93 */
+    EG_V_CHOICE_RANGE = 4,        /* ChoiceVerificationError::Range, src/app/choice.rs:379 */
+    EG_V_QV_CREDIT_RANGE = 5,     /* QuadraticVotingError::CreditRange, src/app/quadratic_voting.rs:315-316 */
+    EG_V_QV_CREDIT_EQUIV = 6,     /* QuadraticVotingError::CreditEquivalence, src/app/quadratic_voting.rs:325-326 */
+    EG_V_QV_VARIANT_BASE = 16     /* + option index: QuadraticVotingError::Variant{index}, src/app/quadratic_voting.rs:305 */
+};
+
+/* ---- context ------------------------------------------------------------------------------------ */
+
+/* Creates a context on CUDA device `device_id` (one context per GPU / per process rank).
+ * Owns a stream, the fixed-base tables for G and for the receiver key, transcript prefixes, scratch. */
+eg_status eg_ctx_create(int device_id, eg_ctx **out);
+void      eg_ctx_destroy(eg_ctx *ctx);
+/* Human-readable description of the last failure on this context ("" if none). Never NULL. */
+const char *eg_last_error(const eg_ctx *ctx);
+/* Library build identification: "eg_b200 <version> sm_100a". */
+const char *eg_version(void);
+
+/* PublicKey::<Ristretto>::from_bytes (src/keys/mod.rs:161-176): validates K (decodable, not the identity),
+ * keeps its bytes for the transcripts (PublicKey::as_bytes :188-190) and builds K's fixed-base table. */
+eg_status eg_ctx_set_receiver(eg_ctx *ctx, const uint8_t key[32]);
+
+/* ---- group-level helpers (Group / ElementOps / ScalarOps for Ristretto, src/group/ristretto.rs) -- */
+
+/* ElementOps::deserialize_element :93-95 over a batch: ok[i] = 1 if encodings[i] decodes */
+eg_status eg_elements_validate(eg_ctx *ctx, size_t n, const uint8_t *encodings /* n*32 */, uint8_t *ok /* n */);
+/* ScalarOps::deserialize_scalar :59-62 over a batch: ok[i] = 1 if canonical (< l) */
+eg_status eg_scalars_validate(eg_ctx *ctx, size_t n, const uint8_t *scalars /* n*32 */, uint8_t *ok /* n */);
+/* ScalarOps::scalar_from_random_bytes :34-38: 64 bytes -> canonical scalar */
+eg_status eg_scalars_from_wide(eg_ctx *ctx, size_t n, const uint8_t *wide /* n*64 */, uint8_t *scalars /* n*32 */);
+/* Group::vartime_double_mul_generator :131-137 over a batch: out[i] = [a_i]A_i + [b_i]G.
+ * ok[i] = 0 (and out[i] = identity encoding) if A_i does not decode or a scalar is not canonical. */
+eg_status eg_double_mul_generator_batch(eg_ctx *ctx, size_t n, const uint8_t *a /* n*32 */, const uint8_t *A /* n*32 */,
+                                        const uint8_t *b /* n*32 */, uint8_t *out /* n*32 */, uint8_t *ok /* n */);
+/* Group::mul_generator :105-107 over a batch: out[i] = [k_i]G */
+eg_status eg_mul_generator_batch(eg_ctx *ctx, size_t n, const uint8_t *k /* n*32 */, uint8_t *out /* n*32 */, uint8_t *ok);
+/* Ciphertext + Ciphertext folded over a batch (src/encryption.rs:163-172): out = sum of the n_parts rows,
+ * each row = n_cts ciphertexts.  Used to combine per-GPU partial tallies. ok = 0 if any element is malformed. */
+eg_status eg_ciphertexts_sum(eg_ctx *ctx, size_t n_parts, size_t n_cts, const uint8_t *parts /* n_parts*n_cts*64 */,
+                             uint8_t *out /* n_cts*64 */, uint8_t *ok /* 1 */);
+
+/* ---- proofs and applications ------------------------------------------------------------------- */
+
+/* PublicKey::verify_zero (src/keys/impls.rs:59-69) -> LogEqualityProof::verify (src/proofs/log_equality.rs:153-180) */
+eg_status eg_verify_zero_batch(eg_ctx *ctx, size_t n, const uint8_t *cts /* n*64 */, const uint8_t *proofs /* n*64 */,
+                               uint8_t *verdicts /* n */);
+/* PublicKey::verify_bool (src/keys/impls.rs:101-113) -> RingProof::verify (src/proofs/ring.rs:302-374) */
+eg_status eg_verify_bool_batch(eg_ctx *ctx, size_t n, const uint8_t *cts /* n*64 */, const uint8_t *proofs /* n*96 */,
+                               uint8_t *verdicts /* n */);
+/* EncryptedChoice::verify (src/app/choice.rs:358-380) for n ballots with `options` options each, followed by the
+ * tally fold of examples/voting.rs:200-203 over the ballots whose verdict is EG_V_OK.
+ *   single != 0: SingleChoice (sum proofs checked first, src/app/choice.rs:77-95); 0: MultiChoice (sums may be NULL).
+ *   tally (options*64, may be NULL): sum of the verified ballots' ciphertexts, Ciphertext::to_bytes form. */
+eg_status eg_verify_choice_batch(eg_ctx *ctx, size_t n, uint32_t options, int single,
+                                 const uint8_t *choices /* n*options*64 */, const uint8_t *ring_proofs /* n*(1+2*options)*32 */,
+                                 const uint8_t *sum_proofs /* n*64 or NULL */, uint8_t *verdicts /* n */,
+                                 uint8_t *tally /* options*64 or NULL */);
+
+/* RangeDecomposition (src/proofs/range.rs:106-108): rings listed as in `Display` (:110-124), most significant
+ * first; ring i admits the values step[i] * {0, .., size[i]-1}. */
+typedef struct {
+    uint32_t n_rings;
+    uint32_t reserved;
+    uint64_t size[64];
+    uint64_t step[64];
+} eg_range;
+
+/* RangeDecomposition::optimal (src/proofs/range.rs:148-153) */
+eg_status eg_range_optimal(uint64_t upper_bound, eg_range *out);
+/* Display for RangeDecomposition (src/proofs/range.rs:110-124); returns the length written (no NUL counted) */
+size_t    eg_range_display(const eg_range *range, char *buf, size_t cap);
+
+/* PublicKey::verify_range (src/keys/impls.rs:143-151) -> RangeProof::verify (src/proofs/range.rs:547-577);
+ * `transcript_label` is the Transcript::new label ("ciphertext_range" for verify_range). */
+eg_status eg_verify_range_batch(eg_ctx *ctx, const eg_range *range, const char *transcript_label, size_t n,
+                                const uint8_t *cts /* n*64 */, const uint8_t *partial_cts /* n*(n_rings-1)*64 */,
+                                const uint8_t *ring_proofs /* n*(1+sum(size))*32 */, uint8_t *verdicts /* n */);
+
+/* QuadraticVotingParams::new (src/app/quadratic_voting.rs:63-76) */
+typedef struct {
+    uint32_t options;
+    uint32_t reserved;
+    uint64_t credits;
+    eg_range vote_range;     /* optimal(isqrt(credits) + 1) */
+    eg_range credit_range;   /* optimal(credits + 1) */
+} eg_qv_params;
+eg_status eg_qv_params_new(uint32_t options, uint64_t credits, eg_qv_params *out);
+size_t    eg_qv_ballot_size(const eg_qv_params *params);
+/* QuadraticVotingBallot::verify (src/app/quadratic_voting.rs:291-329) + tally of the vote ciphertexts.
+ * Ballot bytes: for each option ct | partial cts | ring proof; then credit ct | partial cts | ring proof;
+ * then SumOfSquaresProof = challenge | 2*options responses | sum response (src/proofs/mul.rs:86-93). */
+eg_status eg_verify_qv_batch(eg_ctx *ctx, const eg_qv_params *params, size_t n, const uint8_t *ballots,
+                             uint8_t *verdicts /* n */, uint8_t *tally /* options*64 or NULL */);
+
+/* PublicKeySet (src/sharing/key_set.rs:19-26) */
+typedef struct {
+    uint32_t shares, threshold;
+    uint8_t shared_key[32];
+    uint8_t participant_keys[64][32];
+} eg_keyset;
+
+/* PublicKeySet::verify_share (src/sharing/key_set.rs:209-228) for n_tallies ciphertexts x n_shares candidate shares
+ * each; share j of every tally comes from participant `indexes[j]`. */
+eg_status eg_verify_shares_batch(eg_ctx *ctx, const eg_keyset *keyset, size_t n_tallies, uint32_t n_shares,
+                                 const uint32_t *indexes /* n_shares */, const uint8_t *cts /* n_tallies*64 */,
+                                 const uint8_t *shares /* n_tallies*n_shares*32 */,
+                                 const uint8_t *proofs /* n_tallies*n_shares*64 */,
+                                 uint8_t *verdicts /* n_tallies*n_shares */);
+
+/* DiscreteLogTable::new (src/encryption.rs:267-284) for the values lo..hi (exclusive); lives on the device */
+eg_status eg_dlog_table_create(eg_ctx *ctx, uint64_t lo, uint64_t hi, eg_dlog_table **out);
+void      eg_dlog_table_destroy(eg_dlog_table *table);
+
+/* Params::combine_shares (src/sharing/mod.rs:302-325) on the first `threshold` shares of every tally, then
+ * VerifiableDecryption::decrypt (src/decryption.rs:138-144) through DiscreteLogTable::get (src/encryption.rs:287-297).
+ * found[i] = 1 and values[i] set when the decrypted element is in the table (identity -> 0), found[i] = 0 when it
+ * is not (Option::None), found[i] = 2 when an input element does not decode. */
+eg_status eg_combine_decrypt_batch(eg_ctx *ctx, uint32_t threshold, const uint32_t *indexes /* threshold */,
+                                   size_t n_tallies, uint32_t share_stride /* shares per tally in `shares` */,
+                                   const uint8_t *cts /* n_tallies*64 */, const uint8_t *shares,
+                                   const eg_dlog_table *table, uint64_t *values /* n */, uint8_t *found /* n */);
+
+/* ---- encryption side (synthetic workload generation and encrypt_* drop-ins) -------------------- */
+
+/* PublicKey::encrypt_bool (src/keys/impls.rs:77-89) with caller-supplied randomness: item i consumes
+ * three 64-byte blocks in the reference's draw order: r, x, s_forged. */
+eg_status eg_encrypt_bool_batch(eg_ctx *ctx, size_t n, const uint8_t *values /* n */, const uint8_t *wide_rand /* n*3*64 */,
+                                uint8_t *cts /* n*64 */, uint8_t *proofs /* n*96 */);
+/* EncryptedChoice::single (src/app/choice.rs:288-303): item i consumes 3*options + 1 blocks (r, x, forged s per
+ * option in option order; then the sum-proof nonce). */
+eg_status eg_encrypt_choice_batch(eg_ctx *ctx, size_t n, uint32_t options, const uint32_t *choice /* n */,
+                                  const uint8_t *wide_rand /* n*(3*options+1)*64 */, uint8_t *choices,
+                                  uint8_t *ring_proofs, uint8_t *sum_proofs);
+
+/* ---- device-pointer variants (inputs already resident in HBM; same semantics) ------------------- */
+eg_status eg_verify_bool_batch_dev(eg_ctx *ctx, size_t n, const uint8_t *d_cts, const uint8_t *d_proofs, uint8_t *d_verdicts);
+eg_status eg_verify_choice_batch_dev(eg_ctx *ctx, size_t n, uint32_t options, int single, const uint8_t *d_choices,
+                                     const uint8_t *d_ring_proofs, const uint8_t *d_sum_proofs, uint8_t *d_verdicts,
+                                     uint8_t *d_tally);
+eg_status eg_verify_range_batch_dev(eg_ctx *ctx, const eg_range *range, const char *transcript_label, size_t n,
+                                    const uint8_t *d_cts, const uint8_t *d_partial_cts, const uint8_t *d_ring_proofs,
+                                    uint8_t *d_verdicts);
+
+/* ---- instrumentation --------------------------------------------------------------------------- */
+/* Number of kernels this context has launched since creation (bench.py's `gpu_launches`). */
+uint64_t  eg_kernel_launch_count(const eg_ctx *ctx);
+/* Device time in ms of the last batch call (CUDA events on the context's stream), split by stage:
+ * [0] decode + derived ciphertexts, [1] commitments + transcripts + verdicts, [2] the k_commit launches alone
+ * (one event pair per launch), [3] tally, [4] total of [0]+[1]+[3]. */
+eg_status eg_last_timings(const eg_ctx *ctx, float out_ms[5]);
+/* The dominant kernel (k_commit, one thread per verification-equation side) in the last batch call: number of
+ * launches, number of equation sides evaluated, summed device time of those launches. */
+eg_status eg_last_commit_stats(const eg_ctx *ctx, uint64_t *launches, uint64_t *tasks, float *ms);
+/* On-device self-test of the tuned GF(2^255-19) multiply / square / add / sub against the portable formulation on
+ * n pseudo-random and edge-case operands; *mismatches must come back 0. */
+eg_status eg_selftest_field(eg_ctx *ctx, size_t n, uint64_t seed, uint64_t *mismatches);
+/* Tuning knob: items processed per internal chunk (0 = default 262144).  Results do not depend on it. */
+eg_status eg_ctx_set_chunk_items(eg_ctx *ctx, size_t items);
+/* Raw CUDA stream handle (cudaStream_t) so callers can order their own work / time with events on it. */
+void     *eg_ctx_stream(const eg_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EG_B200_H */

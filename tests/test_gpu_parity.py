@@ -1,0 +1,101 @@
+"""`-m gpu` parity tests proper: the CUDA library (libeg_b200.so, through its C ABI) against the CPU oracle on
+the same seeded inputs -- bit-exact verdicts, encodings and tallies -- plus size-independent properties at
+BASELINE.json sizes (tally round trip, chunking invariance)."""
+import random
+
+import numpy as np
+import pytest
+
+import oracle as O
+import parity_common as PC
+import workloads as W
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def env():
+    from elastic_elgamal_b200 import Engine
+    e = Engine(device=0)           # fails loudly without a GPU / without the built extension
+    sk, pk = W.receiver()
+    e.set_receiver(pk)
+    yield e, sk, pk
+    e.close()
+
+
+def test_field_selftest(env):
+    assert env[0].selftest_field(n=1 << 20, seed=7) == 0
+
+
+def test_group_helpers(env):
+    PC.check_group_helpers(env[0], n=300)
+
+
+def test_ciphertexts_sum(env):
+    PC.check_ciphertexts_sum(env[0], env[2])
+
+
+def test_verify_zero(env):
+    PC.check_verify_zero(env[0], env[2], n=200)
+
+
+def test_verify_bool_config1_shape(env):
+    # BASELINE config 1 (benches/basics.rs:60-82 shape) at a size the oracle checks in seconds
+    PC.check_verify_bool(env[0], env[2], n=2000, seed=31)
+
+
+@pytest.mark.parametrize("options", [2, 3, 5, 10, 15])          # tests/integration/basic.rs:164
+def test_verify_choice_sizes(env, options):
+    PC.check_verify_choice(env[0], env[2], options=options, n=300, single=True, frac=0.2)
+
+
+def test_verify_choice_multi(env):
+    PC.check_verify_choice(env[0], env[2], options=5, n=300, single=False, frac=0.2)
+
+
+def test_verify_choice_headline_shape(env):
+    v = PC.check_verify_choice(env[0], env[2], options=5, n=4000, single=True, frac=0.01)
+    assert set(v.tolist()) >= {O.OK}
+
+
+def test_choice_tally_round_trip(env):
+    PC.check_choice_tally_decrypts(env[0], env[2], env[1], options=5, n=1000)
+
+
+def test_empty_and_ragged(env):
+    PC.check_empty_and_tiny(env[0], env[2])
+
+
+def test_chunking_invariance(env):
+    e, sk, pk = env
+    cts, rings, sums = O.gen_choice_batch(pk, 5, W.SEED_CHOICE, 777)
+    cts, rings, sums = cts.copy(), rings.copy(), sums.copy()
+    W.tamper_choice(cts, rings, sums, random.Random(5), frac=0.05)
+    base_v, base_t = e.verify_choice(5, cts, rings, sums)
+    for chunk in (100, 256, 1000):
+        e.set_chunk_items(chunk)
+        v, t = e.verify_choice(5, cts, rings, sums)
+        assert (v == base_v).all() and (t == base_t).all()
+    e.set_chunk_items(0)
+    ov, ot = O.verify_choice_batch(pk, 5, True, cts, rings, sums)
+    assert (base_v == ov).all() and (base_t == ot).all()
+
+
+def test_large_batch_properties(env):
+    """At 256k ballots the oracle is too slow to check every item; use size-independent properties: a tiled batch
+    must give tiled verdicts, and its tally must decrypt to the per-option counts of the accepted ballots."""
+    e, sk, pk = env
+    base = 4096
+    cts, rings, sums = O.gen_choice_batch(pk, 5, W.SEED_CHOICE, base)
+    cts, rings, sums = cts.copy(), rings.copy(), sums.copy()
+    W.tamper_choice(cts, rings, sums, random.Random(9), frac=0.01)
+    ov, _ = O.verify_choice_batch(pk, 5, True, cts, rings, sums)
+    reps = 64
+    big = (np.tile(cts, (reps, 1, 1)), np.tile(rings, (reps, 1, 1)), np.tile(sums, (reps, 1)))
+    v, t = e.verify_choice(5, *big)
+    assert (v.reshape(reps, base) == ov[None, :]).all()
+    table = O.DlogTable(0, reps * base + 1)
+    accepted = (ov == 0)
+    for k in range(5):
+        expect = reps * int(np.count_nonzero(accepted[k::5]))
+        assert table.get(O.decrypt_to_element(sk, bytes(t[k]))) == expect

@@ -1,0 +1,69 @@
+"""`-m "not gpu"` coverage of the product's host orchestration and kernel bodies: the C ABI library compiled for
+the CPU by tests/hostsim (TEST HARNESS ONLY -- it is not a product path) must agree with the oracle bit for bit.
+The same checks run against the real CUDA library in tests/test_gpu_parity.py."""
+import pytest
+
+import oracle as O
+import parity_common as PC
+import workloads as W
+from elastic_elgamal_b200 import Engine
+from hostsim.build_hostsim import build
+
+
+@pytest.fixture(scope="module")
+def env():
+    e = Engine(lib_path=build())
+    sk, pk = W.receiver()
+    e.set_receiver(pk)
+    yield e, sk, pk
+    e.close()
+
+
+def test_group_helpers(env):
+    PC.check_group_helpers(env[0], n=6)
+
+
+def test_ciphertexts_sum(env):
+    PC.check_ciphertexts_sum(env[0], env[2])
+
+
+def test_verify_zero(env):
+    PC.check_verify_zero(env[0], env[2], n=14)
+
+
+def test_verify_bool(env):
+    PC.check_verify_bool(env[0], env[2], n=24)
+
+
+def test_verify_choice_single(env):
+    PC.check_verify_choice(env[0], env[2], options=5, n=16, single=True, frac=0.5)
+
+
+def test_verify_choice_multi(env):
+    PC.check_verify_choice(env[0], env[2], options=3, n=8, single=False, frac=0.5)
+
+
+def test_choice_tally_round_trip(env):
+    PC.check_choice_tally_decrypts(env[0], env[2], env[1], options=3, n=7)
+
+
+def test_empty_and_tiny(env):
+    e, sk, pk = env
+    PC.check_empty_and_tiny(e, pk)
+
+
+def test_receiver_validation(env):
+    e, sk, pk = env
+    from elastic_elgamal_b200 import EngineError
+    from elastic_elgamal_b200 import _ffi
+    with pytest.raises(EngineError) as ei:
+        e.set_receiver(bytes(32))                       # keys/mod.rs:168-169 IdentityKey
+    assert ei.value.status == _ffi.ERR_IDENTITY_KEY
+    with pytest.raises(EngineError) as ei:
+        e.set_receiver(W.BAD_POINT)                     # keys/mod.rs:166-167 InvalidGroupElement
+    assert ei.value.status == _ffi.ERR_INVALID_ELEMENT
+    with pytest.raises(EngineError) as ei:
+        import numpy as np
+        e.verify_bool(np.zeros((1, 64), np.uint8), np.zeros((1, 96), np.uint8))
+    assert ei.value.status == _ffi.ERR_NO_RECEIVER
+    e.set_receiver(pk)
