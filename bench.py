@@ -165,7 +165,7 @@ def int32_peak():
     """Measured INT32 multiply-add issue rate (lane-ops / s) of this GPU: tools/microbench/int_pipe_bench."""
     exe = ROOT / "tools" / "microbench" / "int_pipe_bench"
     try:
-        out = subprocess.run([str(exe), "2048"], check=True, stdout=subprocess.PIPE, text=True, timeout=120).stdout
+        out = subprocess.run([str(exe), "8192"], check=True, stdout=subprocess.PIPE, text=True, timeout=120).stdout
         data = json.loads(out.strip().splitlines()[-1])
         return data
     except Exception as exc:      # the bench line then carries peak = None
@@ -314,7 +314,11 @@ def main():
     # ---------------- roofline of the dominant kernel + CPU baseline (rank 0)
     peak = int32_peak()
     imad = peak.get("tests", {}).get("imad", {})
-    peak_ops = imad.get("per_s")
+    clk = sampler.summary()
+    # peak = measured IMAD lane-ops per clock per SM x SMs x the SM clock observed during the timed region
+    peak_ops = None
+    if imad.get("per_clk_per_sm") and clk.get("sm_mhz"):
+        peak_ops = imad["per_clk_per_sm"] * peak.get("sms", 148) * clk["sm_mhz"] * 1e6
     achieved_ops = commit_tasks * FIELD_OPS_PER_COMMIT * IMAD_PER_FIELD_OP / (commit_ms * 1e-3) if commit_ms > 0 else None
     traffic = None
     tfile = ROOT / "profiles" / "k_commit_traffic.json"
@@ -328,7 +332,8 @@ def main():
         "achieved": achieved_ops / 1e12 if achieved_ops else None, "peak": peak_ops / 1e12 if peak_ops else None,
         "unit": "T int32 multiply-add lane-ops/s",
         "frac": (achieved_ops / peak_ops) if achieved_ops and peak_ops else None,
-        "peak_source": "measured live: tools/microbench/int_pipe_bench `imad` (MEASURED_PEAKS.json has no integer peak)",
+        "peak_source": "measured live: tools/microbench/int_pipe_bench `imad` lane-ops/clk/SM x SMs x SM clock sampled during the timed "
+                       "region (MEASURED_PEAKS.json has no integer peak)",
         "traffic": traffic,
         "launches": commit_launches, "avg_launch_ms": commit_ms / max(1, commit_launches),
         "share_of_step": commit_ms / dev_ms if dev_ms else None,

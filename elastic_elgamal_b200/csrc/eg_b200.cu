@@ -29,7 +29,12 @@ using namespace eg;
 // Every kernel is a thin __global__ wrapper around a body in kernels.cuh.  launch_*() is the only place a
 // kernel is started; under EG_HOSTSIM (tests/hostsim, test harness only) the same bodies run in a host loop.
 
+#ifndef EG_COMMIT_THREADS
 #define EG_COMMIT_THREADS 128
+#endif
+#ifndef EG_COMMIT_MINBLOCKS
+#define EG_COMMIT_MINBLOCKS 4
+#endif
 #define EG_TALLY_THREADS 128
 #define EG_TALLY_BLOCKS 148       // per slot: one CTA per SM
 
@@ -48,7 +53,7 @@ __global__ void __launch_bounds__(256) k_scalars(const scalars_params P) {
 }
 
 // The hot kernel.  Both 12 KB fixed-base tables are staged in shared memory once per CTA.
-__global__ void __launch_bounds__(EG_COMMIT_THREADS) k_commit(const commit_params P) {
+__global__ void __launch_bounds__(EG_COMMIT_THREADS, EG_COMMIT_MINBLOCKS) k_commit(const commit_params P) {
     __shared__ uint32_t s_tab[2 * EG_FIXED_TABLE_WORDS];
     for (int k = threadIdx.x; k < EG_FIXED_TABLE_WORDS; k += blockDim.x) {
         s_tab[k] = P.table_g[k];

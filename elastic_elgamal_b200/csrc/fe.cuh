@@ -195,8 +195,25 @@ EG_HD void fe_sq_portable(fe &r, const fe &a) {
 
 namespace eg {
 
+// On the device fe_mul / fe_sq are real (non-inlined) functions taking and returning their operands BY VALUE: the
+// CUDA ABI keeps such small aggregates in registers (no local-memory traffic), and every point formula becomes a
+// short sequence of calls.  This keeps the hot loops of the multi-scalar kernels inside the instruction cache:
+// with everything inlined k_commit was 229 KB of SASS and ncu showed `no_instruction` as its top stall reason
+// (profiles/r1_k_commit_inlined.txt).
+#if defined(__CUDA_ARCH__) && !defined(EG_INLINE_FE)
+#if defined(EG_PORTABLE_FE)
+static __device__ __noinline__ fe fe_mul_call(const fe a, const fe b) { fe r; fe_mul_portable(r, a, b); return r; }
+static __device__ __noinline__ fe fe_sq_call(const fe a) { fe r; fe_sq_portable(r, a); return r; }
+#else
+static __device__ __noinline__ fe fe_mul_call(const fe a, const fe b) { fe r; fe_mul_ptx(r, a, b); return r; }
+static __device__ __noinline__ fe fe_sq_call(const fe a) { fe r; fe_sq_ptx(r, a); return r; }
+#endif
+#endif
+
 EG_HD void fe_mul(fe &r, const fe &a, const fe &b) {
-#if defined(__CUDA_ARCH__) && !defined(EG_PORTABLE_FE)
+#if defined(__CUDA_ARCH__) && !defined(EG_INLINE_FE)
+    r = fe_mul_call(a, b);
+#elif defined(__CUDA_ARCH__) && !defined(EG_PORTABLE_FE)
     fe_mul_ptx(r, a, b);
 #else
     fe_mul_portable(r, a, b);
@@ -204,7 +221,9 @@ EG_HD void fe_mul(fe &r, const fe &a, const fe &b) {
 }
 
 EG_HD void fe_sq(fe &r, const fe &a) {
-#if defined(__CUDA_ARCH__) && !defined(EG_PORTABLE_FE)
+#if defined(__CUDA_ARCH__) && !defined(EG_INLINE_FE)
+    r = fe_sq_call(a);
+#elif defined(__CUDA_ARCH__) && !defined(EG_PORTABLE_FE)
     fe_sq_ptx(r, a);
 #else
     fe_sq_portable(r, a);

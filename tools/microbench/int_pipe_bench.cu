@@ -95,6 +95,10 @@ int main(int argc, char **argv) {
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     std::vector<result> results;
 
+    // spin for ~0.4 s first so that the SM clock has ramped up from idle before anything is measured
+    for (int w = 0; w < 40; w++) k_pipe<0><<<sms * 4, 256>>>(1 << 15, 0x9e3779b1u, 12345u, sink, cycles);
+    cudaDeviceSynchronize();
+
     auto run = [&](const char *name, auto launch, int blocks, int threads, double lane_ops_per_thread) {
         launch(blocks, threads);   // warm-up
         cudaDeviceSynchronize();
