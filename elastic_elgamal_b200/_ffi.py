@@ -55,6 +55,17 @@ PROTOTYPES = {
     "eg_verify_choice_batch": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_uint32, C.c_int, P8, P8, P8, P8, P8]),
     "eg_verify_bool_batch_dev": (C.c_int32, [C.c_void_p, C.c_size_t, P8, P8, P8]),
     "eg_verify_choice_batch_dev": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_uint32, C.c_int, P8, P8, P8, P8, P8]),
+    "eg_range_optimal": (C.c_int32, [C.c_uint64, C.POINTER(Range)]),
+    "eg_range_display": (C.c_size_t, [C.POINTER(Range), C.c_char_p, C.c_size_t]),
+    "eg_verify_range_batch": (C.c_int32, [C.c_void_p, C.POINTER(Range), C.c_char_p, C.c_size_t, P8, P8, P8, P8]),
+    "eg_verify_range_batch_dev": (C.c_int32, [C.c_void_p, C.POINTER(Range), C.c_char_p, C.c_size_t, P8, P8, P8, P8]),
+    "eg_qv_params_new": (C.c_int32, [C.c_uint32, C.c_uint64, C.POINTER(QvParams)]),
+    "eg_qv_ballot_size": (C.c_size_t, [C.POINTER(QvParams)]),
+    "eg_verify_qv_batch": (C.c_int32, [C.c_void_p, C.POINTER(QvParams), C.c_size_t, P8, P8, P8]),
+    "eg_verify_shares_batch": (C.c_int32, [C.c_void_p, C.POINTER(KeySet), C.c_size_t, C.c_uint32, C.POINTER(C.c_uint32), P8, P8, P8, P8]),
+    "eg_dlog_table_create": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_void_p)]),
+    "eg_dlog_table_destroy": (None, [C.c_void_p]),
+    "eg_combine_decrypt_batch": (C.c_int32, [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.c_size_t, C.c_uint32, P8, P8, C.c_void_p, P8, P8]),
     "eg_kernel_launch_count": (C.c_uint64, [C.c_void_p]),
     "eg_last_timings": (C.c_int32, [C.c_void_p, C.POINTER(C.c_float * 5)]),
     "eg_ctx_stream": (C.c_void_p, [C.c_void_p]),

@@ -206,6 +206,50 @@ __global__ void k_ciphertexts_sum(const uint8_t *parts, size_t n_parts, size_t n
     if (tid < 2 * n_cts) ciphertexts_sum_body(tid, parts, n_parts, n_cts, out, bad);
 }
 
+// general multi-scalar equations (share proofs, SumOfSquaresProof, Lagrange recombination)
+__global__ void __launch_bounds__(128) k_msm(const msm_params P) {
+    __shared__ uint32_t s_tab[2 * EG_FIXED_TABLE_WORDS];
+    for (int k = threadIdx.x; k < EG_FIXED_TABLE_WORDS; k += blockDim.x) {
+        s_tab[k] = P.table_g[k];
+        s_tab[EG_FIXED_TABLE_WORDS + k] = P.table_k[k];
+    }
+    __syncthreads();
+    size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= P.n * (size_t)P.n_slots) return;
+    msm_body(P, tid % P.n, (int)(tid / P.n), s_tab, s_tab + EG_FIXED_TABLE_WORDS);
+}
+
+__global__ void __launch_bounds__(128) k_sumsq_final(const sumsq_final_params P) {
+    size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid < P.n) sumsq_final_body(P, tid);
+}
+
+__global__ void __launch_bounds__(128) k_share_final(const share_final_params *Pp) {
+    const share_final_params &P = *Pp;
+    size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid < P.n * P.n_shares) share_final_body(P, tid % P.n, (int)(tid / P.n));
+}
+
+__global__ void __launch_bounds__(256) k_qv_verdict(const qv_verdict_params P) {
+    size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid < P.n) qv_verdict_body(P, tid);
+}
+
+__global__ void __launch_bounds__(256) k_share_verdict(const share_verdict_params P, size_t total) {
+    size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid < total) share_verdict_body(P, tid);
+}
+
+__global__ void __launch_bounds__(128) k_dlog_build(const dlog_build_params P, size_t threads) {
+    size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid < threads) dlog_build_body(P, tid);
+}
+
+__global__ void __launch_bounds__(128) k_dlog_lookup(const dlog_lookup_params P) {
+    size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid < P.n) dlog_lookup_body(P, tid);
+}
+
 // on-device self-test of the tuned field arithmetic against the portable formulation (eg_selftest_field)
 __global__ void __launch_bounds__(128) k_selftest_field(size_t n, uint64_t seed, unsigned long long *mismatches) {
     size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -264,7 +308,8 @@ struct eg_ctx {
     size_t commit_ev_used = 0;
     uint64_t call_commit_tasks = 0, call_commit_launches = 0;
     // grow-only scratch
-    dev_buf pts, enc, commit, chal, flags, res[3], in[4], verdicts, partial, running, adm, misc;
+    dev_buf pts, enc, commit, chal, flags, res[3], in[4], verdicts, partial, running, adm, misc, slots, consts, res_big;
+    size_t adm_used = 0;      // cached points in `adm` (32 words each); entries 0,1 = the [O, G] pair
     std::map<std::string, std::vector<uint64_t>> adm_cache_key;
     size_t chunk_items = 0;   // 0 = default
 };
@@ -511,6 +556,55 @@ static void launch_ciphertexts_sum(eg_ctx *ctx, const uint8_t *parts, size_t n_p
     ctx->launches++;
 }
 
+static void launch_msm(eg_ctx *ctx, const msm_params &P) {
+    size_t total = P.n * (size_t)P.n_slots;
+#ifdef EG_HOSTSIM
+    EG_FOR_HOST(total, msm_body(P, tid % P.n, (int)(tid / P.n), P.table_g, P.table_k))
+#else
+    k_msm<<<grid_for(total, 128), 128, 0, ctx->stream>>>(P);
+#endif
+    ctx->launches++;
+}
+
+static void launch_sumsq_final(eg_ctx *ctx, const sumsq_final_params &P) {
+#ifdef EG_HOSTSIM
+    EG_FOR_HOST(P.n, sumsq_final_body(P, tid))
+#else
+    k_sumsq_final<<<grid_for(P.n, 128), 128, 0, ctx->stream>>>(P);
+#endif
+    ctx->launches++;
+}
+
+// `P` lives in host memory; the device copy `d_P` is what the kernel reads (the struct exceeds the 4 KB launch limit)
+static void launch_share_final(eg_ctx *ctx, const share_final_params &P, const share_final_params *d_P) {
+    size_t total = P.n * (size_t)P.n_shares;
+#ifdef EG_HOSTSIM
+    (void)d_P;
+    EG_FOR_HOST(total, share_final_body(P, tid % P.n, (int)(tid / P.n)))
+#else
+    k_share_final<<<grid_for(total, 128), 128, 0, ctx->stream>>>(d_P);
+#endif
+    ctx->launches++;
+}
+
+static void launch_dlog_build(eg_ctx *ctx, const dlog_build_params &P, size_t threads) {
+#ifdef EG_HOSTSIM
+    EG_FOR_HOST(threads, dlog_build_body(P, tid))
+#else
+    k_dlog_build<<<grid_for(threads, 128), 128, 0, ctx->stream>>>(P, threads);
+#endif
+    ctx->launches++;
+}
+
+static void launch_dlog_lookup(eg_ctx *ctx, const dlog_lookup_params &P) {
+#ifdef EG_HOSTSIM
+    EG_FOR_HOST(P.n, dlog_lookup_body(P, tid))
+#else
+    k_dlog_lookup<<<grid_for(P.n, 128), 128, 0, ctx->stream>>>(P);
+#endif
+    ctx->launches++;
+}
+
 extern "C" const char *eg_version(void) { return "eg_b200 0.1.0 sm_100a"; }
 
 extern "C" const char *eg_last_error(const eg_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
@@ -589,7 +683,7 @@ extern "C" void eg_ctx_destroy(eg_ctx *ctx) {
     cudaSetDevice(ctx->device);
     dev_buf *bufs[] = {&ctx->pts, &ctx->enc, &ctx->commit, &ctx->chal, &ctx->flags, &ctx->res[0], &ctx->res[1], &ctx->res[2],
                        &ctx->in[0], &ctx->in[1], &ctx->in[2], &ctx->in[3], &ctx->verdicts, &ctx->partial, &ctx->running,
-                       &ctx->adm, &ctx->misc};
+                       &ctx->adm, &ctx->misc, &ctx->slots, &ctx->consts, &ctx->res_big};
     for (dev_buf *b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->d_table_g) cudaFree(ctx->d_table_g);
     if (ctx->d_table_k) cudaFree(ctx->d_table_k);
@@ -1175,4 +1269,687 @@ extern "C" eg_status eg_ciphertexts_sum(eg_ctx *ctx, size_t n_parts, size_t n_ct
     TRY(finish_call(ctx));
     if (ok) *ok = bad ? 0 : 1;
     return EG_SUCCESS;
+}
+
+// =================================================================== RangeDecomposition (host logic)
+
+namespace {
+
+struct opt_entry { uint64_t len; eg_range d; };
+
+uint64_t lower_len_estimate(uint64_t ub) { return (uint64_t)std::ceil(std::log2((double)ub) * 3.0); }   // range.rs:302-305
+
+// RangeDecomposition::optimize (range.rs:238-300)
+const opt_entry &range_optimize(uint64_t ub, std::map<uint64_t, opt_entry> &memo) {
+    auto it = memo.find(ub);
+    if (it != memo.end()) return it->second;
+    opt_entry opt;
+    memset(&opt.d, 0, sizeof opt.d);
+    opt.len = ub + 2;
+    opt.d.n_rings = 1; opt.d.size[0] = ub; opt.d.step[0] = 1;
+    for (uint64_t first = 2;; first++) {
+        if (first + 2 > opt.len) break;
+        uint64_t remaining = ub - first;
+        for (uint64_t mult = 2; mult <= first; mult++) {
+            if (remaining % mult != 0) continue;
+            uint64_t inner_ub = remaining / mult + 1;
+            if (inner_ub < 2) break;
+            if (first + 2 + lower_len_estimate(inner_ub) > opt.len) continue;
+            const opt_entry inner = range_optimize(inner_ub, memo);
+            uint64_t cand_len = first + 2 + inner.len;
+            uint32_t cand_rings = 1 + inner.d.n_rings;
+            if ((cand_len < opt.len || (cand_len == opt.len && cand_rings < opt.d.n_rings)) && cand_rings <= 64) {
+                opt.len = cand_len;
+                opt.d = inner.d;
+                for (uint32_t i = 0; i < opt.d.n_rings; i++) opt.d.step[i] *= mult;      // combine_mul range.rs:163-171
+                opt.d.size[opt.d.n_rings] = first;
+                opt.d.step[opt.d.n_rings] = 1;
+                opt.d.n_rings++;
+            }
+        }
+    }
+    return memo.emplace(ub, opt).first->second;
+}
+
+uint64_t range_rings_size(const eg_range &r) { uint64_t s = 0; for (uint32_t i = 0; i < r.n_rings; i++) s += r.size[i]; return s; }
+
+bool range_valid(const eg_range *r) {
+    if (!r || r->n_rings == 0 || r->n_rings > 64) return false;
+    for (uint32_t i = 0; i < r->n_rings; i++) if (r->size[i] < 1 || r->size[i] > 4096 || r->step[i] == 0) return false;
+    return range_rings_size(*r) <= 3500;
+}
+
+uint64_t isqrt_u64(uint64_t x) {            // quadratic_voting.rs:127-143
+    uint64_t root = 0, p4 = 1ULL << 62;
+    while (p4 > x) p4 /= 4;
+    while (p4 > 0) {
+        if (x >= root + p4) { x -= root + p4; root = root / 2 + p4; } else root /= 2;
+        p4 /= 4;
+    }
+    return root;
+}
+
+}  // namespace
+
+extern "C" eg_status eg_range_optimal(uint64_t upper_bound, eg_range *out) {
+    if (!out || upper_bound < 2) return EG_ERR_INVALID_ARG;     // range.rs:149 assert
+    std::map<uint64_t, opt_entry> memo;
+    *out = range_optimize(upper_bound, memo).d;
+    return EG_SUCCESS;
+}
+
+extern "C" size_t eg_range_display(const eg_range *r, char *buf, size_t cap) {     // range.rs:110-124
+    if (!r || !buf || cap == 0) return 0;
+    std::string s;
+    for (uint32_t i = 0; i < r->n_rings; i++) {
+        if (r->step[i] > 1) s += std::to_string(r->step[i]) + " * ";
+        s += "0.." + std::to_string(r->size[i]);
+        if (i + 1 < r->n_rings) s += " + ";
+    }
+    size_t n = std::min(cap - 1, s.size());
+    memcpy(buf, s.data(), n);
+    buf[n] = 0;
+    return n;
+}
+
+extern "C" eg_status eg_qv_params_new(uint32_t options, uint64_t credits, eg_qv_params *out) {   // quadratic_voting.rs:63-76
+    if (!out || options == 0 || credits == 0) return EG_ERR_INVALID_ARG;
+    memset(out, 0, sizeof *out);
+    out->options = options;
+    out->credits = credits;
+    eg_status st = eg_range_optimal(isqrt_u64(credits) + 1, &out->vote_range);
+    if (st != EG_SUCCESS) return st;
+    return eg_range_optimal(credits + 1, &out->credit_range);
+}
+
+static size_t range_item_size(const eg_range &r) { return 64 + 64 * (size_t)(r.n_rings - 1) + 32 * (1 + (size_t)range_rings_size(r)); }
+
+extern "C" size_t eg_qv_ballot_size(const eg_qv_params *p) {
+    if (!p) return 0;
+    return p->options * range_item_size(p->vote_range) + range_item_size(p->credit_range) + 32 * (2 * (size_t)p->options + 2);
+}
+
+// =================================================================== RangeProof engine
+
+// admissible values of a range, cached on the device by Display string: adm_base[r] + j = cached([j * step_r] G)
+static eg_status ensure_range_adm(eg_ctx *ctx, const eg_range &range, int32_t adm_base[EG_MAX_RINGS]) {
+    TRY(ensure_bool_adm(ctx));
+    if (ctx->adm_used < 2) ctx->adm_used = 2;
+    char key[4096];
+    eg_range_display(&range, key, sizeof key);
+    auto it = ctx->adm_cache_key.find(key);
+    const size_t total = (size_t)range_rings_size(range);
+    if (it == ctx->adm_cache_key.end()) {
+        if (ctx->adm_used + total > 4096) {      // evict everything but the [O, G] pair
+            CU(cudaStreamSynchronize(ctx->stream));
+            for (auto i2 = ctx->adm_cache_key.begin(); i2 != ctx->adm_cache_key.end();)
+                if (i2->first != "bool") i2 = ctx->adm_cache_key.erase(i2); else ++i2;
+            ctx->adm_used = 2;
+        }
+        std::vector<uint64_t> vals, bases;
+        size_t off = ctx->adm_used;
+        for (uint32_t r = 0; r < range.n_rings; r++) {
+            bases.push_back(off);
+            for (uint64_t j = 0; j < range.size[r]; j++) vals.push_back(j * range.step[r]);     // PreparedRange::new range.rs:341-355
+            off += (size_t)range.size[r];
+        }
+        TRY(ensure(ctx, ctx->consts, std::max<size_t>(vals.size() * 8, 4096)));
+        CU(cudaMemcpyAsync(ctx->consts.p, vals.data(), vals.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        launch_admissible(ctx, (const uint64_t *)ctx->consts.p, (int)vals.size(), (uint32_t *)ctx->adm.p + ctx->adm_used * 32);
+        CU(cudaStreamSynchronize(ctx->stream));
+        ctx->adm_used = off;
+        it = ctx->adm_cache_key.emplace(key, bases).first;
+    }
+    for (uint32_t r = 0; r < range.n_rings; r++) adm_base[r] = (int32_t)it->second[r];
+    return EG_SUCCESS;
+}
+
+struct range_layout { uint8_t ct_buf, partial_buf, ring_buf; uint32_t ct_off, partial_off, ring_off; };
+
+// RangeProof::verify (range.rs:547-577) for n items addressed through `in` / `lay`; results (1 = ok) to d_result,
+// malformed flags to d_flags.  Uses the context scratch from index 0.
+static eg_status verify_range_items(eg_ctx *ctx, size_t n, const eg_range &range, const in_bufs &in, const range_layout &lay,
+                                    const char *label, uint32_t *d_flags, uint32_t *d_result) {
+    const uint32_t R = range.n_rings, T = (uint32_t)range_rings_size(range);
+    const uint32_t np = 2 * R + 2;
+    TRY(ensure(ctx, ctx->pts, n * np * 128));
+    TRY(ensure(ctx, ctx->enc, n * np * 32));
+    TRY(ensure(ctx, ctx->commit, n * 2 * R * 32));
+    TRY(ensure(ctx, ctx->chal, n * R * 32));
+    int32_t adm_base[EG_MAX_RINGS];
+    TRY(ensure_range_adm(ctx, range, adm_base));
+    CU(cudaMemsetAsync(d_flags, 0, n * 4, ctx->stream));
+    // points: partial k -> 2k, 2k+1 ; last ring -> 2(R-1), 2(R-1)+1 (derived) ; main ciphertext -> 2R, 2R+1
+    for (uint32_t k0 = 0; k0 < 2 * R; k0 += EG_MAX_SLOTS) {
+        decode_params dp;
+        memset(&dp, 0, sizeof dp);
+        dp.in = in; dp.n = n;
+        int ns = 0;
+        for (uint32_t k = k0; k < 2 * R && ns < EG_MAX_SLOTS; k++, ns++) {
+            decode_slot &s = dp.slots[ns];
+            if (k < 2) { s.buf = lay.ct_buf; s.offset = lay.ct_off + 32 * k; s.p_index = 2 * R + k; s.want_enc = 0; }
+            else { s.buf = lay.partial_buf; s.offset = lay.partial_off + 32 * (k - 2); s.p_index = k - 2; s.want_enc = 1; s.enc_index = (uint16_t)(k - 2); }
+        }
+        dp.n_slots = ns;
+        dp.pts = (uint32_t *)ctx->pts.p; dp.enc = (uint32_t *)ctx->enc.p; dp.flags = d_flags;
+        launch_decode(ctx, dp);
+    }
+    scalars_params sp;
+    memset(&sp, 0, sizeof sp);
+    sp.in = in; sp.n = n; sp.n_slots = 1; sp.slots[0].buf = lay.ring_buf; sp.slots[0].offset = lay.ring_off; sp.slots[0].count = 1 + T;
+    sp.flags = d_flags;
+    launch_scalars(ctx, sp);
+    range_last_params rl;
+    memset(&rl, 0, sizeof rl);
+    rl.n = n; rl.n_partial = R - 1; rl.ct_p_index = 2 * R; rl.out_p_index = 2 * (R - 1); rl.out_enc_index = 2 * (R - 1);
+    rl.pts = (uint32_t *)ctx->pts.p; rl.enc = (uint32_t *)ctx->enc.p;
+    launch_range_last(ctx, rl);
+
+    ring_job job;
+    job.n_rings = R;
+    for (uint32_t r = 0; r < R; r++) {
+        job.sizes[r] = (uint32_t)range.size[r]; job.ct_p_index[r] = 2 * r; job.ct_enc_index[r] = 2 * r; job.adm_index[r] = adm_base[r];
+    }
+    job.proof_buf = lay.ring_buf; job.proof_offset = lay.ring_off; job.commit_index0 = 0; job.chal_index0 = 0;
+    merlin_new(job.prefix, label, (uint32_t)strlen(label));
+    char display[4096];
+    size_t dlen = eg_range_display(&range, display, sizeof display);
+    merlin_append_message(job.prefix, EG_LBL("dom-sep"), (const uint8_t *)"encryption_range_proof", 22);    // range.rs:561
+    merlin_append_message(job.prefix, EG_LBL("range"), (const uint8_t *)display, (uint32_t)dlen);          // range.rs:562
+    host_ring_initialize(job.prefix, ctx->key);
+    job.d_result = d_result;
+    return run_ring_job(ctx, job, in, n, nullptr, 0, (const uint32_t *)ctx->adm.p);
+}
+
+static eg_status verify_range_chunk(eg_ctx *ctx, const eg_range &range, const char *label, size_t n, const uint8_t *d_cts,
+                                    const uint8_t *d_partial, const uint8_t *d_rings, uint8_t *d_verdicts) {
+    const uint32_t R = range.n_rings, T = (uint32_t)range_rings_size(range);
+    TRY(ensure(ctx, ctx->flags, n * 4));
+    TRY(ensure(ctx, ctx->res[0], n * 4));
+    in_bufs in;
+    memset(&in, 0, sizeof in);
+    in.buf[0] = d_cts; in.stride[0] = 64;
+    in.buf[1] = d_partial; in.stride[1] = 64 * (R - 1);
+    in.buf[2] = d_rings; in.stride[2] = 32 * (1 + T);
+    range_layout lay = {0, 1, 2, 0, 0, 0};
+    TRY(verify_range_items(ctx, n, range, in, lay, label, (uint32_t *)ctx->flags.p, (uint32_t *)ctx->res[0].p));
+    verdict_params vp;
+    memset(&vp, 0, sizeof vp);
+    vp.n = n; vp.flags = (const uint32_t *)ctx->flags.p; vp.n_checks = 1;
+    vp.check[0] = (const uint32_t *)ctx->res[0].p; vp.check_stride[0] = 1; vp.code[0] = EG_V_CHALLENGE_MISMATCH;
+    vp.verdicts = d_verdicts;
+    launch_verdict(ctx, vp);
+    return EG_SUCCESS;
+}
+
+extern "C" eg_status eg_verify_range_batch_dev(eg_ctx *ctx, const eg_range *range, const char *label, size_t n, const uint8_t *d_cts,
+                                               const uint8_t *d_partial, const uint8_t *d_rings, uint8_t *d_verdicts) {
+    TRY(begin_call(ctx));
+    if (!range_valid(range) || !label) return fail(ctx, EG_ERR_INVALID_ARG, "invalid range decomposition or label");
+    if (n == 0) return EG_SUCCESS;
+    if (!d_cts || !d_rings || !d_verdicts || (range->n_rings > 1 && !d_partial)) return fail(ctx, EG_ERR_INVALID_ARG, "null pointer");
+    const uint32_t R = range->n_rings, T = (uint32_t)range_rings_size(*range);
+    const size_t chunk = std::max<size_t>(1024, default_chunk(ctx) * 12 / (2 * T + 2));   // keep the scratch footprint of a choice chunk
+    for (size_t off = 0; off < n; off += chunk) {
+        size_t m = std::min(chunk, n - off);
+        TRY(verify_range_chunk(ctx, *range, label, m, d_cts + 64 * off, d_partial ? d_partial + 64 * (size_t)(R - 1) * off : nullptr,
+                               d_rings + 32 * (size_t)(1 + T) * off, d_verdicts + off));
+    }
+    return finish_call(ctx);
+}
+
+extern "C" eg_status eg_verify_range_batch(eg_ctx *ctx, const eg_range *range, const char *label, size_t n, const uint8_t *cts,
+                                           const uint8_t *partial, const uint8_t *rings, uint8_t *verdicts) {
+    TRY(begin_call(ctx));
+    if (!range_valid(range) || !label) return fail(ctx, EG_ERR_INVALID_ARG, "invalid range decomposition or label");
+    if (n == 0) return EG_SUCCESS;
+    if (!cts || !rings || !verdicts || (range->n_rings > 1 && !partial)) return fail(ctx, EG_ERR_INVALID_ARG, "null pointer");
+    const uint32_t R = range->n_rings, T = (uint32_t)range_rings_size(*range);
+    const size_t chunk = std::max<size_t>(1024, default_chunk(ctx) * 12 / (2 * T + 2));
+    const size_t cm = std::min(chunk, n), pstride = 64 * (size_t)(R - 1), rstride = 32 * (size_t)(1 + T);
+    TRY(ensure(ctx, ctx->in[0], cm * 64));
+    TRY(ensure(ctx, ctx->in[1], std::max<size_t>(cm * pstride, 64)));
+    TRY(ensure(ctx, ctx->in[2], cm * rstride));
+    TRY(ensure(ctx, ctx->verdicts, cm));
+    for (size_t off = 0; off < n; off += chunk) {
+        size_t m = std::min(chunk, n - off);
+        CU(cudaMemcpyAsync(ctx->in[0].p, cts + 64 * off, m * 64, cudaMemcpyHostToDevice, ctx->stream));
+        if (R > 1) CU(cudaMemcpyAsync(ctx->in[1].p, partial + pstride * off, m * pstride, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->in[2].p, rings + rstride * off, m * rstride, cudaMemcpyHostToDevice, ctx->stream));
+        TRY(verify_range_chunk(ctx, *range, label, m, (const uint8_t *)ctx->in[0].p, (const uint8_t *)ctx->in[1].p,
+                               (const uint8_t *)ctx->in[2].p, (uint8_t *)ctx->verdicts.p));
+        CU(cudaMemcpyAsync(verdicts + off, ctx->verdicts.p, m, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    return finish_call(ctx);
+}
+
+// =================================================================== QuadraticVotingBallot::verify + tally
+
+static void launch_qv_verdict(eg_ctx *ctx, const qv_verdict_params &P);
+static void launch_share_verdict(eg_ctx *ctx, const share_verdict_params &P);
+
+static eg_status upload_slots(eg_ctx *ctx, const std::vector<msm_slot> &slots) {
+    TRY(ensure(ctx, ctx->slots, std::max<size_t>(slots.size() * sizeof(msm_slot), 4096)));
+    CU(cudaStreamSynchronize(ctx->stream));      // previous launches may still read the slot table
+    CU(cudaMemcpyAsync(ctx->slots.p, slots.data(), slots.size() * sizeof(msm_slot), cudaMemcpyHostToDevice, ctx->stream));
+    return EG_SUCCESS;
+}
+
+static scalar_src src_in(uint8_t buf, uint32_t offset, bool negate) { scalar_src s; memset(&s, 0, sizeof s); s.kind = 0; s.buf = buf; s.offset = offset; s.negate = negate; return s; }
+static scalar_src src_const(uint32_t index) { scalar_src s; memset(&s, 0, sizeof s); s.kind = 2; s.offset = index; return s; }
+
+static eg_status verify_qv_chunk(eg_ctx *ctx, const eg_qv_params &qp, size_t n, const uint8_t *d_ballots, uint8_t *d_verdicts,
+                                 bool want_tally, bool first_chunk) {
+    const uint32_t m = qp.options;
+    const size_t vsz = range_item_size(qp.vote_range), csz = range_item_size(qp.credit_range), bsz = eg_qv_ballot_size(&qp);
+    const uint32_t Rv = qp.vote_range.n_rings, Rc = qp.credit_range.n_rings;
+    // flags / results: [votes n*m][credit n][sumsq n] each for flags and results
+    const size_t words = n * m + 2 * n;
+    TRY(ensure(ctx, ctx->res_big, 2 * words * 4));
+    uint32_t *f_votes = (uint32_t *)ctx->res_big.p, *f_credit = f_votes + n * m, *f_sumsq = f_credit + n;
+    uint32_t *r_votes = f_sumsq + n, *r_credit = r_votes + n * m, *r_sumsq = r_credit + n;
+
+    CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+    // ---- vote range proofs: items = (ballot, option), quadratic_voting.rs:296-306
+    in_bufs in;
+    memset(&in, 0, sizeof in);
+    in.buf[0] = d_ballots; in.stride[0] = (uint32_t)bsz; in.group[0] = m; in.inner[0] = (uint32_t)vsz;
+    range_layout lay_v = {0, 0, 0, 0, 64, (uint32_t)(64 + 64 * (Rv - 1))};
+    TRY(verify_range_items(ctx, n * m, qp.vote_range, in, lay_v, "quadratic_voting_variant", f_votes, r_votes));
+    // ---- credit range proof, quadratic_voting.rs:308-316
+    memset(&in, 0, sizeof in);
+    in.buf[0] = d_ballots; in.stride[0] = (uint32_t)bsz;
+    range_layout lay_c = {0, 0, 0, (uint32_t)(vsz * m), (uint32_t)(vsz * m + 64), (uint32_t)(vsz * m + 64 + 64 * (Rc - 1))};
+    TRY(verify_range_items(ctx, n, qp.credit_range, in, lay_c, "quadratic_voting_credit_range", f_credit, r_credit));
+    // ---- sum-of-squares proof over (votes, credit), quadratic_voting.rs:318-326 -> mul.rs:190-260
+    const uint32_t np = 2 * m + 2;
+    TRY(ensure(ctx, ctx->pts, n * np * 128));
+    TRY(ensure(ctx, ctx->enc, n * np * 32));
+    TRY(ensure(ctx, ctx->commit, n * np * 32));
+    CU(cudaMemsetAsync(f_sumsq, 0, n * 4, ctx->stream));
+    const uint32_t proof_off = (uint32_t)(vsz * m + csz);
+    for (uint32_t k0 = 0; k0 < np; k0 += EG_MAX_SLOTS) {
+        decode_params dp;
+        memset(&dp, 0, sizeof dp);
+        dp.in = in; dp.n = n;
+        int ns = 0;
+        for (uint32_t k = k0; k < np && ns < EG_MAX_SLOTS; k++, ns++) {
+            decode_slot &s = dp.slots[ns];
+            s.buf = 0; s.want_enc = 1; s.enc_index = (uint16_t)k; s.p_index = k;
+            s.offset = (uint32_t)(vsz * (k / 2) + 32 * (k % 2));      // option k/2 (k/2 == m: the credit ciphertext follows the votes)
+        }
+        dp.n_slots = ns;
+        dp.pts = (uint32_t *)ctx->pts.p; dp.enc = (uint32_t *)ctx->enc.p; dp.flags = f_sumsq;
+        launch_decode(ctx, dp);
+    }
+    scalars_params sp;
+    memset(&sp, 0, sizeof sp);
+    sp.in = in; sp.n = n; sp.n_slots = 1; sp.slots[0].buf = 0; sp.slots[0].offset = proof_off; sp.slots[0].count = 2 * m + 2;
+    sp.flags = f_sumsq;
+    launch_scalars(ctx, sp);
+    // proof = challenge | (r_resp_i, v_resp_i)* | sum_resp
+    std::vector<msm_slot> slots;
+    const uint32_t c_off = proof_off, sum_off = proof_off + 32 * (1 + 2 * m);
+    for (uint32_t i = 0; i < m; i++) {
+        const uint32_t r_off = proof_off + 32 * (1 + 2 * i), v_off = r_off + 32;
+        msm_slot a;                                    // [e_r]G = [-c]R_x + [r_resp]G, mul.rs:215-219
+        memset(&a, 0, sizeof a);
+        a.nv = 1; a.nf = 1; a.out_enc = 1; a.out_index = 2 * i;
+        a.p_index[0] = 2 * i; a.vs[0] = src_in(0, c_off, true);
+        a.fbase[0] = 0; a.fs[0] = src_in(0, r_off, false);
+        slots.push_back(a);
+        msm_slot b;                                    // [v_resp]G + [r_resp]K + [-c]X, mul.rs:221-228
+        memset(&b, 0, sizeof b);
+        b.nv = 1; b.nf = 2; b.out_enc = 1; b.out_index = 2 * i + 1;
+        b.p_index[0] = 2 * i + 1; b.vs[0] = src_in(0, c_off, true);
+        b.fbase[0] = 0; b.fs[0] = src_in(0, v_off, false);
+        b.fbase[1] = 1; b.fs[1] = src_in(0, r_off, false);
+        slots.push_back(b);
+    }
+    for (int side = 0; side < 2; side++) {             // mul.rs:232-247: sum_i [v_resp_i]{R_x, X}_i + [sum_resp]{G, K} + [-c]{R_z, Z}
+        msm_slot z;
+        memset(&z, 0, sizeof z);
+        z.nv = (uint8_t)(m + 1); z.nf = 1; z.out_enc = 1; z.out_index = 2 * m + side;
+        for (uint32_t i = 0; i < m; i++) { z.p_index[i] = 2 * i + side; z.vs[i] = src_in(0, proof_off + 32 * (2 + 2 * i), false); }
+        z.p_index[m] = 2 * m + side; z.vs[m] = src_in(0, c_off, true);
+        z.fbase[0] = (uint8_t)side; z.fs[0] = src_in(0, sum_off, false);
+        slots.push_back(z);
+    }
+    TRY(upload_slots(ctx, slots));
+    msm_params mp;
+    memset(&mp, 0, sizeof mp);
+    mp.in = in; mp.n = n; mp.n_slots = (int)slots.size(); mp.slots = (const msm_slot *)ctx->slots.p;
+    mp.pts = (const uint32_t *)ctx->pts.p; mp.commit = (uint32_t *)ctx->commit.p; mp.pts_out = (uint32_t *)ctx->pts.p;
+    mp.table_g = ctx->d_table_g; mp.table_k = ctx->d_table_k;
+    launch_msm(ctx, mp);
+    sumsq_final_params fp;
+    memset(&fp, 0, sizeof fp);
+    fp.in = in; fp.n = n; fp.n_cts = m;
+    for (uint32_t i = 0; i < m; i++) fp.ct_enc_index[i] = 2 * i;
+    fp.sum_enc_index = 2 * m; fp.commit_index = 0; fp.proof_buf = 0; fp.c_offset = c_off;
+    merlin_new(fp.prefix, EG_LBL("quadratic_voting_credit_equiv"));        // quadratic_voting.rs:324
+    merlin_append_message(fp.prefix, EG_LBL("dom-sep"), (const uint8_t *)"sum_of_squares", 14);   // mul.rs:96-99
+    merlin_append_message(fp.prefix, EG_LBL("K"), ctx->key, 32);
+    fp.enc = (const uint32_t *)ctx->enc.p; fp.commit = (const uint32_t *)ctx->commit.p; fp.result = r_sumsq;
+    launch_sumsq_final(ctx, fp);
+    qv_verdict_params vp;
+    memset(&vp, 0, sizeof vp);
+    vp.n = n; vp.options = m; vp.flags_votes = f_votes; vp.flags_credit = f_credit; vp.flags_sumsq = f_sumsq;
+    vp.res_votes = r_votes; vp.res_credit = r_credit; vp.res_sumsq = r_sumsq; vp.verdicts = d_verdicts;
+    launch_qv_verdict(ctx, vp);
+    CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+    CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+    if (want_tally) {
+        TRY(ensure(ctx, ctx->partial, (size_t)2 * m * EG_TALLY_BLOCKS * 128));
+        TRY(ensure(ctx, ctx->running, (size_t)2 * m * 128));
+        const int blocks = launch_tally_partial(ctx, (const uint32_t *)ctx->pts.p, n, (int)(2 * m), d_verdicts, (uint32_t *)ctx->partial.p);
+        launch_tally_final(ctx, (const uint32_t *)ctx->partial.p, blocks, (int)(2 * m), (uint32_t *)ctx->running.p, first_chunk ? 0 : 1, nullptr);
+    }
+    CU(cudaEventRecord(ctx->ev[3], ctx->stream));
+    return EG_SUCCESS;
+}
+
+static void launch_qv_verdict(eg_ctx *ctx, const qv_verdict_params &P) {
+#ifdef EG_HOSTSIM
+    EG_FOR_HOST(P.n, qv_verdict_body(P, tid))
+#else
+    k_qv_verdict<<<grid_for(P.n, 256), 256, 0, ctx->stream>>>(P);
+#endif
+    ctx->launches++;
+}
+
+static void launch_share_verdict(eg_ctx *ctx, const share_verdict_params &P) {
+    size_t total = P.n * (size_t)P.n_shares;
+#ifdef EG_HOSTSIM
+    EG_FOR_HOST(total, share_verdict_body(P, tid))
+#else
+    k_share_verdict<<<grid_for(total, 256), 256, 0, ctx->stream>>>(P, total);
+#endif
+    ctx->launches++;
+}
+
+extern "C" eg_status eg_verify_qv_batch(eg_ctx *ctx, const eg_qv_params *params, size_t n, const uint8_t *ballots, uint8_t *verdicts,
+                                        uint8_t *tally) {
+    TRY(begin_call(ctx));
+    if (!params || params->options == 0 || params->options >= EG_MSM_MAXV || !range_valid(&params->vote_range) ||
+        !range_valid(&params->credit_range))
+        return fail(ctx, EG_ERR_INVALID_ARG, "invalid quadratic voting parameters (options must be in 1..15)");
+    if (n && (!ballots || !verdicts)) return fail(ctx, EG_ERR_INVALID_ARG, "null pointer");
+    const uint32_t m = params->options;
+    const size_t bsz = eg_qv_ballot_size(params);
+    const size_t chunk = std::max<size_t>(1024, default_chunk(ctx) / 4), cm = std::min(chunk, std::max<size_t>(n, 1));
+    float acc[5] = {0, 0, 0, 0, 0};
+    TRY(ensure(ctx, ctx->in[0], cm * bsz));
+    TRY(ensure(ctx, ctx->verdicts, cm));
+    TRY(ensure(ctx, ctx->misc, 64 * (size_t)m));
+    TRY(ensure(ctx, ctx->partial, (size_t)2 * m * EG_TALLY_BLOCKS * 128));
+    TRY(ensure(ctx, ctx->running, (size_t)2 * m * 128));
+    bool first = true;
+    for (size_t off = 0; off < n; off += chunk) {
+        size_t k = std::min(chunk, n - off);
+        CU(cudaMemcpyAsync(ctx->in[0].p, ballots + bsz * off, k * bsz, cudaMemcpyHostToDevice, ctx->stream));
+        TRY(verify_qv_chunk(ctx, *params, k, (const uint8_t *)ctx->in[0].p, (uint8_t *)ctx->verdicts.p, tally != nullptr, first));
+        first = false;
+        CU(cudaMemcpyAsync(verdicts + off, ctx->verdicts.p, k, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        collect_timings(ctx, acc);
+    }
+    if (tally) {
+        launch_tally_final(ctx, (const uint32_t *)ctx->partial.p, 0, (int)(2 * m), (uint32_t *)ctx->running.p, first ? 0 : 1, (uint8_t *)ctx->misc.p);
+        CU(cudaMemcpyAsync(tally, ctx->misc.p, 64 * (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    { float keep = ctx->timings[2]; memcpy(ctx->timings, acc, sizeof acc); ctx->timings[2] = keep; }
+    return finish_call(ctx);
+}
+
+// =================================================================== threshold decryption shares
+
+extern "C" eg_status eg_verify_shares_batch(eg_ctx *ctx, const eg_keyset *ks, size_t n, uint32_t n_shares, const uint32_t *indexes,
+                                            const uint8_t *cts, const uint8_t *shares, const uint8_t *proofs, uint8_t *verdicts) {
+    if (!ctx) return EG_ERR_INVALID_ARG;
+    CU(cudaSetDevice(ctx->device));
+    ctx->err.clear(); ctx->commit_ev_used = 0; ctx->call_commit_tasks = 0; ctx->call_commit_launches = 0;
+    if (!ks || !indexes || n_shares == 0 || n_shares > 8 || ks->shares == 0 || ks->shares > 64 || ks->threshold == 0 || ks->threshold > ks->shares)
+        return fail(ctx, EG_ERR_INVALID_ARG, "invalid key set / share count (at most 8 shares per call)");
+    for (uint32_t j = 0; j < n_shares; j++)
+        if (indexes[j] >= ks->shares) return fail(ctx, EG_ERR_INVALID_ARG, "participant index out of bounds");      // key_set.rs:216 panics
+    if (n == 0) return EG_SUCCESS;
+    if (!cts || !shares || !proofs || !verdicts) return fail(ctx, EG_ERR_INVALID_ARG, "null pointer");
+    const uint32_t S = n_shares;
+    // participant keys -> constant points (decoded on the device)
+    TRY(ensure(ctx, ctx->consts, 64 * 1024));
+    uint8_t keys[8 * 32];
+    for (uint32_t j = 0; j < S; j++) memcpy(keys + 32 * j, ks->participant_keys[indexes[j]], 32);
+    uint8_t *d_keys = (uint8_t *)ctx->consts.p;                       // [0, 256): key encodings
+    uint32_t *d_const_pts = (uint32_t *)((uint8_t *)ctx->consts.p + 1024);          // 8 points x 128 B
+    uint32_t *d_key_flags = (uint32_t *)((uint8_t *)ctx->consts.p + 4096);
+    share_final_params *d_fp = (share_final_params *)((uint8_t *)ctx->consts.p + 8192);
+    CU(cudaMemcpyAsync(d_keys, keys, 32 * S, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(d_key_flags, 0, 4, ctx->stream));
+    {
+        decode_params dp;
+        memset(&dp, 0, sizeof dp);
+        dp.in.buf[0] = d_keys; dp.in.stride[0] = 32 * S; dp.n = 1; dp.n_slots = (int)S;
+        for (uint32_t j = 0; j < S; j++) { dp.slots[j].buf = 0; dp.slots[j].offset = 32 * j; dp.slots[j].p_index = j; }
+        dp.pts = d_const_pts; dp.enc = nullptr; dp.flags = d_key_flags;
+        launch_decode(ctx, dp);
+        uint32_t kf = 0;
+        CU(cudaMemcpyAsync(&kf, d_key_flags, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (kf) return fail(ctx, EG_ERR_INVALID_ELEMENT, "a participant key does not represent a group element");
+    }
+    const size_t chunk = default_chunk(ctx), cm = std::min(chunk, n);
+    TRY(ensure(ctx, ctx->in[0], cm * 64));
+    TRY(ensure(ctx, ctx->in[1], cm * 32 * S));
+    TRY(ensure(ctx, ctx->in[2], cm * 64 * S));
+    TRY(ensure(ctx, ctx->verdicts, cm * S));
+    TRY(ensure(ctx, ctx->pts, cm * (2 + S) * 128));
+    TRY(ensure(ctx, ctx->enc, cm * (2 + S) * 32));
+    TRY(ensure(ctx, ctx->commit, cm * 2 * S * 32));
+    TRY(ensure(ctx, ctx->flags, cm * (S + 1) * 4));
+    TRY(ensure(ctx, ctx->res[0], cm * S * 4));
+    for (size_t off = 0; off < n; off += chunk) {
+        size_t k = std::min(chunk, n - off);
+        CU(cudaMemcpyAsync(ctx->in[0].p, cts + 64 * off, k * 64, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->in[1].p, shares + 32 * S * off, k * 32 * S, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->in[2].p, proofs + 64 * S * off, k * 64 * S, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemsetAsync(ctx->flags.p, 0, k * (S + 1) * 4, ctx->stream));
+        in_bufs in;
+        memset(&in, 0, sizeof in);
+        in.buf[0] = (const uint8_t *)ctx->in[0].p; in.stride[0] = 64;
+        in.buf[1] = (const uint8_t *)ctx->in[1].p; in.stride[1] = 32 * S;
+        in.buf[2] = (const uint8_t *)ctx->in[2].p; in.stride[2] = 64 * S;
+        // points: 0 = R, 1 = B, 2 + j = share j (CandidateDecryption::from_bytes, decryption.rs:168-177)
+        decode_params dp;
+        memset(&dp, 0, sizeof dp);
+        dp.in = in; dp.n = k; dp.n_slots = (int)(2 + S); dp.flag_stride = S + 1;
+        for (uint32_t q = 0; q < 2 + S; q++) {
+            decode_slot &s = dp.slots[q];
+            s.want_enc = 1; s.enc_index = (uint16_t)q; s.p_index = q;
+            if (q < 2) { s.buf = 0; s.offset = 32 * q; s.flag_offset = 0; }
+            else { s.buf = 1; s.offset = 32 * (q - 2); s.flag_offset = 1 + (q - 2); }
+        }
+        dp.pts = (uint32_t *)ctx->pts.p; dp.enc = (uint32_t *)ctx->enc.p; dp.flags = (uint32_t *)ctx->flags.p;
+        launch_decode(ctx, dp);
+        scalars_params sp;
+        memset(&sp, 0, sizeof sp);
+        sp.in = in; sp.n = k; sp.n_slots = (int)S; sp.flag_stride = S + 1;
+        for (uint32_t j = 0; j < S; j++) { sp.slots[j].buf = 2; sp.slots[j].offset = 64 * j; sp.slots[j].count = 2; sp.slots[j].flag_offset = 1 + j; }
+        sp.flags = (uint32_t *)ctx->flags.p;
+        launch_scalars(ctx, sp);
+        // log_equality.rs:160-164 with log base R: [x]G = [-c]key_j + [s]G ; [x]K = [-c]dh_j + [s]R
+        std::vector<msm_slot> slots;
+        for (uint32_t j = 0; j < S; j++) {
+            msm_slot a;
+            memset(&a, 0, sizeof a);
+            a.nv = 1; a.nf = 1; a.out_enc = 1; a.out_index = 2 * j;
+            a.p_index[0] = 0x80000000u | j; a.vs[0] = src_in(2, 64 * j, true);
+            a.fbase[0] = 0; a.fs[0] = src_in(2, 64 * j + 32, false);
+            slots.push_back(a);
+            msm_slot b;
+            memset(&b, 0, sizeof b);
+            b.nv = 2; b.nf = 0; b.out_enc = 1; b.out_index = 2 * j + 1;
+            b.p_index[0] = 2 + j; b.vs[0] = src_in(2, 64 * j, true);
+            b.p_index[1] = 0; b.vs[1] = src_in(2, 64 * j + 32, false);
+            slots.push_back(b);
+        }
+        TRY(upload_slots(ctx, slots));
+        msm_params mp;
+        memset(&mp, 0, sizeof mp);
+        mp.in = in; mp.n = k; mp.n_slots = (int)slots.size(); mp.slots = (const msm_slot *)ctx->slots.p;
+        mp.pts = (const uint32_t *)ctx->pts.p; mp.const_pts = d_const_pts; mp.commit = (uint32_t *)ctx->commit.p;
+        mp.pts_out = (uint32_t *)ctx->pts.p; mp.table_g = ctx->d_table_g; mp.table_k = ctx->d_table_k;
+        launch_msm(ctx, mp);
+        share_final_params fp;
+        memset(&fp, 0, sizeof fp);
+        fp.in = in; fp.n = k; fp.n_shares = S; fp.r_enc_index = 0; fp.share_enc_index0 = 2; fp.commit_index0 = 0; fp.proof_buf = 2;
+        for (uint32_t j = 0; j < S; j++) {
+            transcript &t = fp.prefix[j];
+            merlin_new(t, EG_LBL("elgamal_decryption_share"));                 // key_set.rs:218
+            merlin_append_u64(t, EG_LBL("n"), ks->shares);                     // commit, key_set.rs:167-171
+            merlin_append_u64(t, EG_LBL("t"), ks->threshold);
+            merlin_append_message(t, EG_LBL("K"), ks->shared_key, 32);
+            merlin_append_u64(t, EG_LBL("i"), indexes[j]);                     // key_set.rs:220
+            for (int w = 0; w < 8; w++)
+                fp.key_words[j][w] = (uint32_t)keys[32 * j + 4 * w] | ((uint32_t)keys[32 * j + 4 * w + 1] << 8) |
+                                     ((uint32_t)keys[32 * j + 4 * w + 2] << 16) | ((uint32_t)keys[32 * j + 4 * w + 3] << 24);
+        }
+        fp.enc = (const uint32_t *)ctx->enc.p; fp.commit = (const uint32_t *)ctx->commit.p; fp.result = (uint32_t *)ctx->res[0].p;
+        CU(cudaMemcpyAsync(d_fp, &fp, sizeof fp, cudaMemcpyHostToDevice, ctx->stream));
+        launch_share_final(ctx, fp, d_fp);
+        share_verdict_params vp;
+        memset(&vp, 0, sizeof vp);
+        vp.n = k; vp.n_shares = S; vp.flags = (const uint32_t *)ctx->flags.p; vp.result = (const uint32_t *)ctx->res[0].p;
+        vp.verdicts = (uint8_t *)ctx->verdicts.p;
+        launch_share_verdict(ctx, vp);
+        CU(cudaMemcpyAsync(verdicts + S * off, ctx->verdicts.p, k * S, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    return finish_call(ctx);
+}
+
+// =================================================================== DiscreteLogTable + combine_shares + decrypt
+
+extern "C" eg_status eg_dlog_table_create(eg_ctx *ctx, uint64_t lo, uint64_t hi, eg_dlog_table **out) {
+    if (!ctx || !out || hi < lo || hi - lo > (1ULL << 28)) return EG_ERR_INVALID_ARG;
+    *out = nullptr;
+    CU(cudaSetDevice(ctx->device));
+    eg_dlog_table *t = new (std::nothrow) eg_dlog_table();
+    if (!t) return EG_ERR_OUT_OF_MEMORY;
+    t->ctx = ctx; t->lo = lo; t->hi = hi;
+    size_t cap = 16;
+    while (cap < 2 * (size_t)(hi - lo) + 2) cap <<= 1;
+    t->cap = cap; t->d_keys = nullptr; t->d_vals = nullptr;
+    if (cudaMalloc(&t->d_keys, cap * 32) != cudaSuccess || cudaMalloc(&t->d_vals, cap * 8) != cudaSuccess) {
+        cudaGetLastError();
+        eg_dlog_table_destroy(t);
+        return fail(ctx, EG_ERR_OUT_OF_MEMORY, "dlog table allocation");
+    }
+    CU(cudaMemsetAsync(t->d_vals, 0, cap * 8, ctx->stream));
+    dlog_build_params bp;
+    bp.lo = lo; bp.hi = hi; bp.per = 32; bp.cap = cap; bp.keys = t->d_keys; bp.vals = (unsigned long long *)t->d_vals;
+    size_t threads = (size_t)((hi - lo + bp.per - 1) / bp.per);
+    if (threads) launch_dlog_build(ctx, bp, threads);
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    *out = t;
+    return EG_SUCCESS;
+}
+
+extern "C" void eg_dlog_table_destroy(eg_dlog_table *t) {
+    if (!t) return;
+    if (t->d_keys) cudaFree(t->d_keys);
+    if (t->d_vals) cudaFree(t->d_vals);
+    delete t;
+}
+
+extern "C" eg_status eg_combine_decrypt_batch(eg_ctx *ctx, uint32_t threshold, const uint32_t *indexes, size_t n, uint32_t share_stride,
+                                              const uint8_t *cts, const uint8_t *shares, const eg_dlog_table *table, uint64_t *values,
+                                              uint8_t *found) {
+    if (!ctx) return EG_ERR_INVALID_ARG;
+    CU(cudaSetDevice(ctx->device));
+    ctx->err.clear(); ctx->commit_ev_used = 0; ctx->call_commit_tasks = 0; ctx->call_commit_launches = 0;
+    if (!indexes || !table || threshold == 0 || threshold > EG_MSM_MAXV || share_stride < threshold)
+        return fail(ctx, EG_ERR_INVALID_ARG, "invalid threshold / share layout");
+    if (n == 0) return EG_SUCCESS;
+    if (!cts || !shares || !values || !found) return fail(ctx, EG_ERR_INVALID_ARG, "null pointer");
+    const uint32_t t = threshold;
+    // lagrange_coefficients (sharing/mod.rs:139-170) on the host: t scalars, folded with the common scale
+    std::vector<uint32_t> coeff(8 * t);
+    {
+        sc scale = sc_from_u64(1);
+        for (uint32_t a = 0; a < t; a++) { sc e = sc_from_u64((uint64_t)indexes[a] + 1); sc_mul(scale, scale, e); }
+        for (uint32_t a = 0; a < t; a++) {
+            bool sign = false;
+            sc mag = sc_from_u64(1);
+            for (uint32_t b = 0; b < t; b++) {
+                sc e;
+                if (indexes[a] > indexes[b]) { sign = !sign; e = sc_from_u64(indexes[a] - indexes[b]); }
+                else if (indexes[a] < indexes[b]) e = sc_from_u64(indexes[b] - indexes[a]);
+                else {
+                    if (a != b) return fail(ctx, EG_ERR_INVALID_ARG, "duplicate participant index");
+                    e = sc_from_u64((uint64_t)indexes[a] + 1);
+                }
+                sc_mul(mag, mag, e);
+            }
+            if (sign) sc_neg(mag, mag);
+            sc inv, c;
+            sc_invert(inv, mag);
+            sc_mul(c, inv, scale);          // (sum lambda_j S_j) * scale == sum (lambda_j * scale) S_j
+            for (int w = 0; w < 8; w++) coeff[8 * a + w] = c.v[w];
+        }
+    }
+    TRY(ensure(ctx, ctx->consts, 64 * 1024));
+    uint32_t *d_coeff = (uint32_t *)((uint8_t *)ctx->consts.p + 16384);
+    CU(cudaMemcpyAsync(d_coeff, coeff.data(), coeff.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    const size_t chunk = default_chunk(ctx), cm = std::min(chunk, n);
+    TRY(ensure(ctx, ctx->in[0], cm * 64));
+    TRY(ensure(ctx, ctx->in[1], cm * 32 * share_stride));
+    TRY(ensure(ctx, ctx->pts, cm * (3 + t) * 128));
+    TRY(ensure(ctx, ctx->flags, cm * 4));
+    TRY(ensure(ctx, ctx->res_big, cm * 8));
+    TRY(ensure(ctx, ctx->verdicts, cm));
+    for (size_t off = 0; off < n; off += chunk) {
+        size_t k = std::min(chunk, n - off);
+        CU(cudaMemcpyAsync(ctx->in[0].p, cts + 64 * off, k * 64, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->in[1].p, shares + 32 * (size_t)share_stride * off, k * 32 * share_stride, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemsetAsync(ctx->flags.p, 0, k * 4, ctx->stream));
+        in_bufs in;
+        memset(&in, 0, sizeof in);
+        in.buf[0] = (const uint8_t *)ctx->in[0].p; in.stride[0] = 64;
+        in.buf[1] = (const uint8_t *)ctx->in[1].p; in.stride[1] = 32 * share_stride;
+        decode_params dp;
+        memset(&dp, 0, sizeof dp);
+        dp.in = in; dp.n = k; dp.n_slots = (int)(2 + t);
+        for (uint32_t q = 0; q < 2 + t; q++) {
+            decode_slot &s = dp.slots[q];
+            s.p_index = q;
+            if (q < 2) { s.buf = 0; s.offset = 32 * q; } else { s.buf = 1; s.offset = 32 * (q - 2); }
+        }
+        dp.pts = (uint32_t *)ctx->pts.p; dp.enc = nullptr; dp.flags = (uint32_t *)ctx->flags.p;
+        launch_decode(ctx, dp);
+        std::vector<msm_slot> slots(1);
+        msm_slot &z = slots[0];
+        memset(&z, 0, sizeof z);
+        z.nv = (uint8_t)t; z.nf = 0; z.out_point = 1; z.out_index = 2 + t;
+        for (uint32_t j = 0; j < t; j++) { z.p_index[j] = 2 + j; z.vs[j] = src_const(j); }
+        TRY(upload_slots(ctx, slots));
+        msm_params mp;
+        memset(&mp, 0, sizeof mp);
+        mp.in = in; mp.n = k; mp.n_slots = 1; mp.slots = (const msm_slot *)ctx->slots.p;
+        mp.pts = (const uint32_t *)ctx->pts.p; mp.const_scalars = d_coeff; mp.pts_out = (uint32_t *)ctx->pts.p;
+        mp.table_g = ctx->d_table_g; mp.table_k = ctx->has_receiver ? ctx->d_table_k : ctx->d_table_g;
+        launch_msm(ctx, mp);
+        dlog_lookup_params lp;
+        memset(&lp, 0, sizeof lp);
+        lp.n = k; lp.b_p_index = 1; lp.d_p_index = 2 + t; lp.pts = (const uint32_t *)ctx->pts.p;
+        lp.cap = table->cap; lp.keys = table->d_keys; lp.vals = (const unsigned long long *)table->d_vals;
+        lp.flags = (const uint32_t *)ctx->flags.p; lp.values = (unsigned long long *)ctx->res_big.p; lp.found = (uint8_t *)ctx->verdicts.p;
+        launch_dlog_lookup(ctx, lp);
+        CU(cudaMemcpyAsync(values + off, ctx->res_big.p, k * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(found + off, ctx->verdicts.p, k, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    return finish_call(ctx);
 }

@@ -257,4 +257,63 @@ EG_HD void ge_msm_chain(ge_ext &out, const ge_ext *P, const sc *a, const uint32_
     out = acc;
 }
 
+
+// Same chain with run-time term counts (nv <= MAXV, nf <= 2), for the equations that are not of the [a]P + [b]F shape:
+// share verification (two per-item bases), SumOfSquaresProof (G, K and one per-item base; (n+2)-term sums) and
+// Lagrange recombination.  Replaces the general vartime_multi_mul (ristretto.rs:139-146).
+template <int MAXV>
+EG_HD void ge_msm_chain_rt(ge_ext &out, int nv, const ge_ext *P, const sc *a, int nf, const uint32_t *const *ftab, const sc *b) {
+    ge_cached tbl[MAXV][8];
+    uint32_t ra[MAXV][8];
+    uint32_t rb[2][8];
+#pragma unroll 1
+    for (int v = 0; v < nv; v++) {
+        ge_ext cur = P[v];
+        ge_cached c1;
+        ge_to_cached(c1, cur);
+        tbl[v][0] = c1;
+#pragma unroll 1
+        for (int k = 1; k < 8; k++) {
+            ge_p1p1 t;
+            ge_add_cached_p1p1(t, cur, c1, false);
+            ge_p1p1_to_ext(cur, t);
+            ge_to_cached(tbl[v][k], cur);
+        }
+        sc_recode4(ra[v], a[v]);
+    }
+#pragma unroll 1
+    for (int f = 0; f < nf; f++) sc_recode8(rb[f], b[f]);
+    ge_ext acc = ge_identity();
+    ge_p1p1 t;
+#pragma unroll 1
+    for (int i = 63; i >= 0; i--) {
+#pragma unroll 1
+        for (int k = 0; k < 3; k++) { ge_dbl_p1p1(t, acc); ge_p1p1_to_proj(acc, t); }
+        ge_dbl_p1p1(t, acc); ge_p1p1_to_ext(acc, t);
+#pragma unroll 1
+        for (int v = 0; v < nv; v++) {
+            int d = sc_digit4(ra[v], i);
+            if (d != 0) {
+                int m = d < 0 ? -d : d;
+                ge_add_cached_p1p1(t, acc, tbl[v][m - 1], d < 0);
+                ge_p1p1_to_ext(acc, t);
+            }
+        }
+        if ((i & 1) == 0) {
+#pragma unroll 1
+            for (int f = 0; f < nf; f++) {
+                int d = sc_digit8(rb[f], i >> 1);
+                if (d != 0) {
+                    int m = d < 0 ? -d : d;
+                    ge_niels n;
+                    ge_niels_load(n, ftab[f], m - 1);
+                    ge_add_niels_p1p1(t, acc, n, d < 0);
+                    ge_p1p1_to_ext(acc, t);
+                }
+            }
+        }
+    }
+    out = acc;
+}
+
 }  // namespace eg

@@ -66,8 +66,15 @@ EG_HD void store32_bytes(uint8_t *p, const uint32_t w[8]) {
 // Input buffers of a batch call (array-of-structures, reference byte layouts)
 struct in_bufs {
     const uint8_t *buf[4];
-    uint32_t stride[4];         // bytes per item in buf[k]
+    uint32_t stride[4];         // bytes per outer item in buf[k]
+    uint32_t group[4];          // items per outer item (0 or 1: flat).  Lets "item = (ballot, option)" address proofs that
+    uint32_t inner[4];          // are embedded in a larger record: addr = buf + (item / group) * stride + (item % group) * inner
 };
+
+EG_HD const uint8_t *in_ptr(const in_bufs &in, int k, size_t item) {
+    if (in.group[k] > 1) return in.buf[k] + (item / in.group[k]) * in.stride[k] + (item % in.group[k]) * in.inner[k];
+    return in.buf[k] + item * in.stride[k];
+}
 
 struct decode_slot {
     uint8_t buf;                // which input buffer
@@ -75,6 +82,7 @@ struct decode_slot {
     uint16_t enc_index;         // planar index in enc (8 words each)
     uint32_t offset;            // byte offset inside the item
     uint32_t p_index;           // planar point index
+    uint32_t flag_offset;       // malformed flag goes to flags[item * flag_stride + flag_offset]
 };
 
 struct decode_params {
@@ -84,27 +92,29 @@ struct decode_params {
     decode_slot slots[EG_MAX_SLOTS];
     uint32_t *pts;              // planar points
     uint32_t *enc;              // planar encodings
-    uint32_t *flags;            // per item: bit 0 = malformed
+    uint32_t *flags;            // bit 0 = malformed
+    uint32_t flag_stride;       // 0 is treated as 1
 };
 
 EG_HD void decode_body(const decode_params &P, size_t item, int slot) {
     const decode_slot &s = P.slots[slot];
     uint32_t w[8];
-    load32_bytes(w, P.in.buf[s.buf] + item * P.in.stride[s.buf] + s.offset);
+    load32_bytes(w, in_ptr(P.in, s.buf, item) + s.offset);
     ge_ext p;
     bool ok = ge_decode(p, w);
     planar_store_point(P.pts, P.n, s.p_index, item, p);
     if (s.want_enc) planar_store_words(P.enc, P.n, s.enc_index, 8, item, w);
     if (!ok) {
+        size_t fi = item * (P.flag_stride ? P.flag_stride : 1) + s.flag_offset;
 #if defined(__CUDA_ARCH__)
-        atomicOr(&P.flags[item], 1u);
+        atomicOr(&P.flags[fi], 1u);
 #else
-        P.flags[item] |= 1u;
+        P.flags[fi] |= 1u;
 #endif
     }
 }
 
-struct scalar_slot { uint8_t buf; uint32_t offset; uint32_t count; };   // `count` consecutive scalars
+struct scalar_slot { uint8_t buf; uint32_t offset; uint32_t count; uint32_t flag_offset; };   // `count` consecutive scalars
 
 struct scalars_params {
     in_bufs in;
@@ -112,24 +122,26 @@ struct scalars_params {
     int n_slots;
     scalar_slot slots[8];
     uint32_t *flags;
+    uint32_t flag_stride;
 };
 
 EG_HD void scalars_body(const scalars_params &P, size_t item) {
-    bool ok = true;
     for (int s = 0; s < P.n_slots; s++) {
-        const uint8_t *base = P.in.buf[P.slots[s].buf] + item * P.in.stride[P.slots[s].buf] + P.slots[s].offset;
+        bool ok = true;
+        const uint8_t *base = in_ptr(P.in, P.slots[s].buf, item) + P.slots[s].offset;
         for (uint32_t k = 0; k < P.slots[s].count; k++) {
             uint32_t w[8];
             load32_bytes(w, base + 32 * k);
             ok = ok && sc_is_canonical_words(w);
         }
-    }
-    if (!ok) {
+        if (!ok) {
+            size_t fi = item * (P.flag_stride ? P.flag_stride : 1) + P.slots[s].flag_offset;
 #if defined(__CUDA_ARCH__)
-        atomicOr(&P.flags[item], 1u);
+            atomicOr(&P.flags[fi], 1u);
 #else
-        P.flags[item] |= 1u;
+            P.flags[fi] |= 1u;
 #endif
+        }
     }
 }
 
@@ -176,9 +188,9 @@ EG_HD void commit_body(const commit_params &P, size_t item, int slot, const uint
     uint32_t w[8];
     sc e, r, ne;
     if (s.e_planar) planar_load_words(w, P.chal, P.n, s.e_offset, 8, item);
-    else load32_bytes(w, P.in.buf[s.e_buf] + item * P.in.stride[s.e_buf] + s.e_offset);
+    else load32_bytes(w, in_ptr(P.in, s.e_buf, item) + s.e_offset);
     bool ok = sc_from_words(e, w);
-    load32_bytes(w, P.in.buf[s.s_buf] + item * P.in.stride[s.s_buf] + s.s_offset);
+    load32_bytes(w, in_ptr(P.in, s.s_buf, item) + s.s_offset);
     ok = sc_from_words(r, w) && ok;
     if (!ok) { e = sc_zero(); r = sc_zero(); }      // malformed items are already flagged; keep the math defined
     sc_neg(ne, e);
@@ -187,6 +199,90 @@ EG_HD void commit_body(const commit_params &P, size_t item, int slot, const uint
     ge_msm_chain<1, 1>(acc, &pt, &ne, ft, &r);
     ge_encode(w, acc);
     planar_store_words(P.commit, P.n, s.out_index, 8, item, w);
+}
+
+
+EG_HD void point_to_words32(uint32_t *o, const ge_ext &p) {
+    for (int k = 0; k < 8; k++) { o[k] = p.X.v[k]; o[8 + k] = p.Y.v[k]; o[16 + k] = p.Z.v[k]; o[24 + k] = p.T.v[k]; }
+}
+EG_HD void point_from_words32(ge_ext &p, const uint32_t *o) {
+    for (int k = 0; k < 8; k++) { p.X.v[k] = o[k]; p.Y.v[k] = o[8 + k]; p.Z.v[k] = o[16 + k]; p.T.v[k] = o[24 + k]; }
+}
+
+// ------------------------------------------------------------------ general multi-scalar equations
+
+#define EG_MSM_MAXV 16
+
+// where a scalar comes from
+struct scalar_src {
+    uint8_t kind;               // 0: input buffer (AoS bytes), 1: planar `chal` buffer, 2: constant table
+    uint8_t buf;                // input buffer (kind 0)
+    uint8_t negate;             // use l - x
+    uint8_t pad;
+    uint32_t offset;            // byte offset in the item (kind 0), planar index (kind 1), table index (kind 2)
+};
+
+struct msm_slot {
+    uint8_t nv, nf;             // per-item / constant bases ; fixed bases (G / K tables)
+    uint8_t out_enc;            // store the 8-word encoding at commit[out_index]
+    uint8_t out_point;          // store the extended point at pts[out_index]
+    uint32_t out_index;
+    uint32_t p_index[EG_MSM_MAXV];   // planar point index, or index into const_pts when bit 31 is set
+    scalar_src vs[EG_MSM_MAXV];
+    uint8_t fbase[2];           // 0: G, 1: K
+    uint8_t pad2[2];
+    scalar_src fs[2];
+};
+
+struct msm_params {
+    in_bufs in;
+    size_t n;
+    int n_slots;
+    const msm_slot *slots;      // device memory
+    const uint32_t *pts;        // planar per-item points
+    const uint32_t *const_pts;  // batch-constant points, 32 words each (X, Y, Z, T)
+    const uint32_t *chal;       // planar scalars
+    const uint32_t *const_scalars;   // batch-constant scalars, 8 words each
+    uint32_t *commit;           // planar encodings out
+    uint32_t *pts_out;          // planar points out
+    const uint32_t *table_g, *table_k;
+};
+
+EG_HD bool load_scalar(sc &out, const msm_params &P, const scalar_src &src, size_t item) {
+    uint32_t w[8];
+    if (src.kind == 0) load32_bytes(w, in_ptr(P.in, src.buf, item) + src.offset);
+    else if (src.kind == 1) planar_load_words(w, P.chal, P.n, src.offset, 8, item);
+    else for (int k = 0; k < 8; k++) w[k] = P.const_scalars[(size_t)src.offset * 8 + k];
+    sc x;
+    bool ok = sc_from_words(x, w);
+    if (!ok) x = sc_zero();
+    if (src.negate) sc_neg(out, x); else out = x;
+    return ok;
+}
+
+EG_HD void msm_body(const msm_params &P, size_t item, int slot, const uint32_t *tab_g, const uint32_t *tab_k) {
+    const msm_slot &s = P.slots[slot];
+    ge_ext pts[EG_MSM_MAXV];
+    sc a[EG_MSM_MAXV], b[2];
+    const uint32_t *ft[2];
+#pragma unroll 1
+    for (int v = 0; v < s.nv; v++) {
+        if (s.p_index[v] & 0x80000000u) point_from_words32(pts[v], P.const_pts + (size_t)(s.p_index[v] & 0x7fffffffu) * 32);
+        else planar_load_point(pts[v], P.pts, P.n, s.p_index[v], item);
+        load_scalar(a[v], P, s.vs[v], item);
+    }
+    for (int f = 0; f < s.nf; f++) {
+        ft[f] = s.fbase[f] ? tab_k : tab_g;
+        load_scalar(b[f], P, s.fs[f], item);
+    }
+    ge_ext acc;
+    ge_msm_chain_rt<EG_MSM_MAXV>(acc, s.nv, pts, a, s.nf, ft, b);
+    if (s.out_point) planar_store_point(P.pts_out, P.n, s.out_index, item, acc);
+    if (s.out_enc) {
+        uint32_t w[8];
+        ge_encode(w, acc);
+        planar_store_words(P.commit, P.n, s.out_index, 8, item, w);
+    }
 }
 
 // ------------------------------------------------------------------ ring transcripts
@@ -254,7 +350,7 @@ EG_HD void ring_final_body(const ring_final_params &P, size_t item) {
     }
     sc c, cc;
     merlin_challenge_scalar(t, EG_LBL("c"), c);
-    load32_bytes(w, P.in.buf[P.proof_buf] + item * P.in.stride[P.proof_buf] + P.cc_offset);
+    load32_bytes(w, in_ptr(P.in, P.proof_buf, item) + P.cc_offset);
     bool ok = sc_from_words(cc, w);
     P.result[item] = (ok && sc_eq(c, cc)) ? 1u : 0u;
 }
@@ -293,7 +389,7 @@ EG_HD void logeq_final_body(const logeq_final_params &P, size_t item) {
     merlin_append_words(t, EG_LBL("[x]K"), w, 8);
     sc c, cc;
     merlin_challenge_scalar(t, EG_LBL("c"), c);
-    load32_bytes(w, P.in.buf[P.proof_buf] + item * P.in.stride[P.proof_buf] + P.c_offset);
+    load32_bytes(w, in_ptr(P.in, P.proof_buf, item) + P.c_offset);
     bool ok = sc_from_words(cc, w);
     P.result[item] = (ok && sc_eq(c, cc)) ? 1u : 0u;
 }
@@ -418,12 +514,6 @@ EG_HD void admissible_body(int tid, const uint64_t *values, uint32_t *adm) {
     for (int k = 0; k < 8; k++) { o[k] = c.YpX.v[k]; o[8 + k] = c.YmX.v[k]; o[16 + k] = c.Z.v[k]; o[24 + k] = c.T2d.v[k]; }
 }
 
-EG_HD void point_to_words32(uint32_t *o, const ge_ext &p) {
-    for (int k = 0; k < 8; k++) { o[k] = p.X.v[k]; o[8 + k] = p.Y.v[k]; o[16 + k] = p.Z.v[k]; o[24 + k] = p.T.v[k]; }
-}
-EG_HD void point_from_words32(ge_ext &p, const uint32_t *o) {
-    for (int k = 0; k < 8; k++) { p.X.v[k] = o[k]; p.Y.v[k] = o[8 + k]; p.Z.v[k] = o[16 + k]; p.T.v[k] = o[24 + k]; }
-}
 
 EG_HD void elements_validate_body(size_t i, const uint8_t *enc, uint8_t *ok) {
     uint32_t w[8];
@@ -486,6 +576,227 @@ EG_HD void ciphertexts_sum_body(size_t tid, const uint8_t *parts, size_t n_parts
     }
     ge_encode(w, acc);
     store32_bytes(out + 32 * tid, w);
+}
+
+}  // namespace eg
+
+// ------------------------------------------------------------------ SumOfSquaresProof / share proofs / dlog table
+
+namespace eg {
+
+// SumOfSquaresProof::verify transcript (mul.rs:205-258).  prefix = Transcript::new(label) + start_proof("sum_of_squares")
+// + "K".  Per item: n ciphertexts (input encodings), commitments (planar, from the msm kernel), the sum ciphertext.
+struct sumsq_final_params {
+    in_bufs in;
+    size_t n;
+    uint32_t n_cts;
+    uint32_t ct_enc_index[EG_MSM_MAXV];   // planar enc of R_x; X at +1
+    uint32_t sum_enc_index;               // planar enc of R_z; Z at +1
+    uint32_t commit_index;                // [e_r]G_i at +2i, [e_x]G+[e_r]K_i at +2i+1, then the two sums at +2n, +2n+1
+    uint8_t proof_buf;
+    uint32_t c_offset;
+    transcript prefix;
+    const uint32_t *enc;
+    const uint32_t *commit;
+    uint32_t *result;
+};
+
+EG_HD void sumsq_final_body(const sumsq_final_params &P, size_t item) {
+    transcript t = P.prefix;
+    uint32_t w[8];
+#pragma unroll 1
+    for (uint32_t i = 0; i < P.n_cts; i++) {
+        planar_load_words(w, P.enc, P.n, P.ct_enc_index[i], 8, item);
+        merlin_append_words(t, EG_LBL("R_x"), w, 8);
+        planar_load_words(w, P.enc, P.n, P.ct_enc_index[i] + 1, 8, item);
+        merlin_append_words(t, EG_LBL("X"), w, 8);
+        planar_load_words(w, P.commit, P.n, P.commit_index + 2 * i, 8, item);
+        merlin_append_words(t, EG_LBL("[e_r]G"), w, 8);
+        planar_load_words(w, P.commit, P.n, P.commit_index + 2 * i + 1, 8, item);
+        merlin_append_words(t, EG_LBL("[e_x]G + [e_r]K"), w, 8);
+    }
+    planar_load_words(w, P.enc, P.n, P.sum_enc_index, 8, item);
+    merlin_append_words(t, EG_LBL("R_z"), w, 8);
+    planar_load_words(w, P.enc, P.n, P.sum_enc_index + 1, 8, item);
+    merlin_append_words(t, EG_LBL("Z"), w, 8);
+    planar_load_words(w, P.commit, P.n, P.commit_index + 2 * P.n_cts, 8, item);
+    merlin_append_words(t, EG_LBL("[e_x]R_x + [e_z]G"), w, 8);
+    planar_load_words(w, P.commit, P.n, P.commit_index + 2 * P.n_cts + 1, 8, item);
+    merlin_append_words(t, EG_LBL("[e_x]X + [e_z]K"), w, 8);
+    sc c, cc;
+    merlin_challenge_scalar(t, EG_LBL("c"), c);
+    load32_bytes(w, in_ptr(P.in, P.proof_buf, item) + P.c_offset);
+    bool ok = sc_from_words(cc, w);
+    P.result[item] = (ok && sc_eq(c, cc)) ? 1u : 0u;
+}
+
+// PublicKeySet::verify_share transcript tail (key_set.rs:216-226 -> log_equality.rs:167-173).
+// prefix[j] = Transcript::new("elgamal_decryption_share") + commit(n, t, shared key) + "i" = indexes[j].
+// The log base is the ciphertext's random element: "K" = enc(R) (PublicKey::from_element, keys/mod.rs:178-185).
+struct share_final_params {
+    in_bufs in;
+    size_t n;                   // tallies
+    uint32_t n_shares;
+    uint32_t r_enc_index;       // planar enc(R)
+    uint32_t share_enc_index0;  // planar enc of share j at +j
+    uint32_t commit_index0;     // [x]G_j at +2j, [x]K_j at +2j+1
+    uint8_t proof_buf;          // proofs: item stride n_shares*64, share j at 64j: c | s
+    transcript prefix[8];
+    uint32_t key_words[8][8];   // participant key encodings (constant per j)
+    const uint32_t *enc;
+    const uint32_t *commit;
+    uint32_t *result;           // n * n_shares
+};
+
+EG_HD void share_final_body(const share_final_params &P, size_t item, int j) {
+    transcript t = P.prefix[j];
+    uint32_t w[8];
+    merlin_append_message(t, EG_LBL("dom-sep"), (const uint8_t *)"log_eq", 6);
+    planar_load_words(w, P.enc, P.n, P.r_enc_index, 8, item);
+    merlin_append_words(t, EG_LBL("K"), w, 8);
+    merlin_append_words(t, EG_LBL("[r]G"), P.key_words[j], 8);
+    planar_load_words(w, P.enc, P.n, P.share_enc_index0 + j, 8, item);
+    merlin_append_words(t, EG_LBL("[r]K"), w, 8);
+    planar_load_words(w, P.commit, P.n, P.commit_index0 + 2 * j, 8, item);
+    merlin_append_words(t, EG_LBL("[x]G"), w, 8);
+    planar_load_words(w, P.commit, P.n, P.commit_index0 + 2 * j + 1, 8, item);
+    merlin_append_words(t, EG_LBL("[x]K"), w, 8);
+    sc c, cc;
+    merlin_challenge_scalar(t, EG_LBL("c"), c);
+    load32_bytes(w, in_ptr(P.in, P.proof_buf, item) + 64 * j);
+    bool ok = sc_from_words(cc, w);
+    P.result[item * P.n_shares + j] = (ok && sc_eq(c, cc)) ? 1u : 0u;
+}
+
+// DiscreteLogTable (encryption.rs:260-298) as an open-addressing table on the device: slot = 8 key words + value.
+EG_HD uint64_t dlog_hash(const uint32_t w[8]) {
+    uint64_t h = ((uint64_t)w[1] << 32) | w[0];
+    h ^= h >> 29; h *= 0xbf58476d1ce4e5b9ULL; h ^= h >> 32;
+    return h;
+}
+
+// thread t inserts the encodings of [lo + t*per .. lo + (t+1)*per) G: one variable-time [k]G, then additions of G
+struct dlog_build_params {
+    uint64_t lo, hi, per;
+    size_t cap;                 // power of two
+    uint32_t *keys;             // cap * 8
+    unsigned long long *vals;   // cap, 0 = empty (value 0 is never stored, encryption.rs:270)
+};
+
+EG_HD void dlog_build_body(const dlog_build_params &P, size_t tid) {
+    uint64_t v0 = P.lo + tid * P.per;
+    if (v0 >= P.hi) return;
+    uint64_t v1 = v0 + P.per < P.hi ? v0 + P.per : P.hi;
+    ge_ext G = ge_generator(), acc = ge_identity();
+    ge_cached cg;
+    ge_to_cached(cg, G);
+#pragma unroll 1
+    for (int bit = 63; bit >= 0; bit--) {
+        ge_dbl(acc, acc);
+        if ((v0 >> bit) & 1) ge_add(acc, acc, G);
+    }
+#pragma unroll 1
+    for (uint64_t v = v0; v < v1; v++) {
+        if (v != 0) {
+            uint32_t w[8];
+            ge_encode(w, acc);
+            size_t slot = (size_t)dlog_hash(w) & (P.cap - 1);
+            for (;;) {
+#if defined(__CUDA_ARCH__)
+                unsigned long long prev = atomicCAS(&P.vals[slot], 0ULL, (unsigned long long)v);
+#else
+                unsigned long long prev = P.vals[slot];
+                if (prev == 0) P.vals[slot] = v;
+#endif
+                if (prev == 0) { for (int k = 0; k < 8; k++) P.keys[slot * 8 + k] = w[k]; break; }
+                slot = (slot + 1) & (P.cap - 1);
+            }
+        }
+        ge_p1p1 t;
+        ge_add_cached_p1p1(t, acc, cg, false);
+        ge_p1p1_to_ext(acc, t);
+    }
+}
+
+// decrypt_to_element (decryption.rs:129-131) + DiscreteLogTable::get (encryption.rs:287-297):
+// M = B - D (D = recombined share, a planar point), identity -> Some(0), else table probe on the encoding
+struct dlog_lookup_params {
+    size_t n;
+    uint32_t b_p_index, d_p_index;
+    const uint32_t *pts;
+    size_t cap;
+    const uint32_t *keys;
+    const unsigned long long *vals;
+    const uint32_t *flags;      // malformed inputs
+    unsigned long long *values;
+    uint8_t *found;             // 1 found, 0 absent, 2 malformed input
+};
+
+EG_HD void dlog_lookup_body(const dlog_lookup_params &P, size_t item) {
+    if (P.flags[item] & 1u) { P.found[item] = 2; P.values[item] = 0; return; }
+    ge_ext B, D, M;
+    planar_load_point(B, P.pts, P.n, P.b_p_index, item);
+    planar_load_point(D, P.pts, P.n, P.d_p_index, item);
+    ge_sub(M, B, D);
+    if (ge_is_identity(M)) { P.found[item] = 1; P.values[item] = 0; return; }
+    uint32_t w[8];
+    ge_encode(w, M);
+    size_t slot = (size_t)dlog_hash(w) & (P.cap - 1);
+    for (;;) {
+        unsigned long long v = P.vals[slot];
+        if (v == 0) { P.found[item] = 0; P.values[item] = 0; return; }
+        bool eq = true;
+        for (int k = 0; k < 8; k++) eq = eq && (P.keys[slot * 8 + k] == w[k]);
+        if (eq) { P.found[item] = 1; P.values[item] = v; return; }
+        slot = (slot + 1) & (P.cap - 1);
+    }
+}
+
+
+// QuadraticVotingBallot::verify precedence (quadratic_voting.rs:291-329): malformed anywhere, then the first failing
+// vote range proof (Variant{i}), then the credit range proof, then the sum-of-squares proof.
+struct qv_verdict_params {
+    size_t n;
+    uint32_t options;
+    const uint32_t *flags_votes;    // n * options
+    const uint32_t *flags_credit;   // n
+    const uint32_t *flags_sumsq;    // n
+    const uint32_t *res_votes;      // n * options
+    const uint32_t *res_credit;     // n
+    const uint32_t *res_sumsq;      // n
+    uint8_t *verdicts;
+};
+
+EG_HD void qv_verdict_body(const qv_verdict_params &P, size_t item) {
+    bool bad = (P.flags_credit[item] | P.flags_sumsq[item]) & 1u;
+    for (uint32_t i = 0; i < P.options; i++) bad = bad || (P.flags_votes[item * P.options + i] & 1u);
+    uint8_t v = 0;
+    if (bad) v = 1;
+    else {
+        for (uint32_t i = 0; i < P.options && v == 0; i++)
+            if (!P.res_votes[item * P.options + i]) v = (uint8_t)(16 + i);
+        if (v == 0 && !P.res_credit[item]) v = 5;
+        if (v == 0 && !P.res_sumsq[item]) v = 6;
+    }
+    P.verdicts[item] = v;
+}
+
+// per (tally, share): malformed ciphertext / share / proof scalars, else the log-equality check
+struct share_verdict_params {
+    size_t n;
+    uint32_t n_shares;
+    const uint32_t *flags;          // n * (n_shares + 1): [0] ciphertext, [1 + j] share j
+    const uint32_t *result;         // n * n_shares
+    uint8_t *verdicts;              // n * n_shares
+};
+
+EG_HD void share_verdict_body(const share_verdict_params &P, size_t tid) {
+    size_t item = tid / P.n_shares, j = tid % P.n_shares;
+    const uint32_t *f = P.flags + item * (P.n_shares + 1);
+    uint8_t v = 0;
+    if ((f[0] | f[1 + j]) & 1u) v = 1;
+    else if (!P.result[tid]) v = 2;
+    P.verdicts[tid] = v;
 }
 
 }  // namespace eg

@@ -147,6 +147,70 @@ class Engine:
                                                     _addr(sums) if single else None, _addr(v), _addr(t)))
         return v, t
 
+    # ---- RangeDecomposition / RangeProof
+    def range_optimal(self, upper_bound):
+        r = _ffi.Range()
+        self._check(self.lib.eg_range_optimal(upper_bound, C.byref(r)))
+        return r
+
+    def range_display(self, r):
+        b = C.create_string_buffer(4096)
+        n = self.lib.eg_range_display(C.byref(r), b, 4096)
+        return b.raw[:n].decode()
+
+    def verify_range(self, rng, label, cts, partials, rings):
+        cts = _u8(cts, (-1, 64))
+        n = cts.shape[0]
+        partials = _u8(partials, (n, max(0, rng.n_rings - 1), 64))
+        rings = _u8(rings, (n, 1 + rng.rings_size, 32))
+        v = np.empty(n, np.uint8)
+        self._check(self.lib.eg_verify_range_batch(self.h, C.byref(rng), label.encode(), n, _addr(cts),
+                                                   _addr(partials) if rng.n_rings > 1 else None, _addr(rings), _addr(v)))
+        return v
+
+    # ---- QuadraticVotingBallot
+    def qv_params(self, options, credits):
+        p = _ffi.QvParams()
+        self._check(self.lib.eg_qv_params_new(options, credits, C.byref(p)))
+        return p
+
+    def qv_ballot_size(self, p):
+        return self.lib.eg_qv_ballot_size(C.byref(p))
+
+    def verify_qv(self, p, ballots, tally=True):
+        bsz = self.qv_ballot_size(p)
+        ballots = _u8(ballots, (-1, bsz))
+        n = ballots.shape[0]
+        v = np.empty(n, np.uint8)
+        t = np.empty((p.options, 64), np.uint8) if tally else None
+        self._check(self.lib.eg_verify_qv_batch(self.h, C.byref(p), n, _addr(ballots), _addr(v), _addr(t)))
+        return v, t
+
+    # ---- threshold decryption
+    def verify_shares(self, keyset, indexes, cts, shares, proofs):
+        s = len(indexes)
+        cts = _u8(cts, (-1, 64))
+        n = cts.shape[0]
+        shares, proofs = _u8(shares, (n, s, 32)), _u8(proofs, (n, s, 64))
+        idx = (C.c_uint32 * s)(*indexes)
+        v = np.empty((n, s), np.uint8)
+        self._check(self.lib.eg_verify_shares_batch(self.h, C.byref(keyset), n, s, idx, _addr(cts), _addr(shares), _addr(proofs), _addr(v)))
+        return v
+
+    def dlog_table(self, lo, hi):
+        return DlogTable(self, lo, hi)
+
+    def combine_decrypt(self, indexes, cts, shares, table):
+        t = len(indexes)
+        cts = _u8(cts, (-1, 64))
+        n = cts.shape[0]
+        shares = _u8(shares, (n, -1, 32))
+        idx = (C.c_uint32 * t)(*indexes)
+        values, found = np.zeros(n, np.uint64), np.zeros(n, np.uint8)
+        self._check(self.lib.eg_combine_decrypt_batch(self.h, t, idx, n, shares.shape[1], _addr(cts), _addr(shares), table.h,
+                                                      _addr(values), _addr(found)))
+        return values, found
+
     # ---- device-pointer variants (ints are raw device addresses, e.g. torch.Tensor.data_ptr())
     def verify_bool_dev(self, n, d_cts, d_proofs, d_verdicts):
         self._check(self.lib.eg_verify_bool_batch_dev(self.h, n, d_cts, d_proofs, d_verdicts))
@@ -154,3 +218,20 @@ class Engine:
     def verify_choice_dev(self, n, options, single, d_choices, d_rings, d_sums, d_verdicts, d_tally):
         self._check(self.lib.eg_verify_choice_batch_dev(self.h, n, options, int(single), d_choices, d_rings, d_sums,
                                                         d_verdicts, d_tally))
+
+
+class DlogTable:
+    """DiscreteLogTable::new(lo..hi) resident on the engine's GPU."""
+
+    def __init__(self, engine, lo, hi):
+        self.engine = engine
+        h = C.c_void_p()
+        engine._check(engine.lib.eg_dlog_table_create(engine.h, lo, hi, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None) and self.engine.h:
+            self.engine.lib.eg_dlog_table_destroy(self.h)
+        self.h = None
+
+    __del__ = close

@@ -140,3 +140,163 @@ def check_empty_and_tiny(e, pk):
     assert v.shape == (0,) and not t.any()          # empty tally = identity ciphertexts (all-zero encodings)
     for n in (1, 2, 31, 33):
         check_verify_choice(e, pk, options=2, n=n, frac=0)
+
+
+def to_engine_range(e, spec):
+    """oracle Range -> engine Range (same rings); also checks RangeDecomposition::optimal parity."""
+    r = e.range_optimal(int(O.lib().eo_range_upper_bound(O.C.byref(spec))))
+    assert r.rings == spec.rings and e.range_display(r) == O.range_display(spec)
+    return r
+
+
+def check_range_decomposition(e):
+    for ub in (2, 5, 16, 17, 21, 42, 60, 100, 101, 256, 1000, 12345, 65536, 777777):
+        to_engine_range(e, O.range_optimal(ub))
+
+
+def tamper_range(cts, partials, rings, rnd, frac):
+    n = cts.shape[0]
+    idx = sorted(rnd.sample(range(n), max(1, int(n * frac)))) if n else []
+    for k, i in enumerate(idx):
+        kind = k % 5
+        if kind == 0:
+            cts[i, 32:] = np.frombuffer(O.point_add(bytes(cts[i, 32:]), W.G_ENC), np.uint8)
+        elif kind == 1 and partials.shape[1] > 0:
+            partials[i, 0, 32:] = np.frombuffer(O.point_add(bytes(partials[i, 0, 32:]), W.G_ENC), np.uint8)
+        elif kind == 2:
+            rings[i, -1] = np.frombuffer(W.BAD_SCALAR, np.uint8)
+        elif kind == 3:
+            cts[i, :32] = np.frombuffer(W.BAD_POINT2, np.uint8)
+        else:
+            a, b = rings[i, 1].copy(), rings[i, 2].copy()
+            rings[i, 1], rings[i, 2] = b, a
+    return idx
+
+
+def check_verify_range(e, pk, upper_bound, n=40, label="ciphertext_range", frac=0.25, seed=3):
+    spec = O.range_optimal(upper_bound)
+    rng = to_engine_range(e, spec)
+    rnd = random.Random(seed)
+    values = [0, upper_bound - 1] + [rnd.randrange(upper_bound) for _ in range(n - 2)]
+    cts, partials, rings = O.gen_range_batch(pk, spec, label, W.SEED_QV, np.array(values[:n], np.uint64))
+    cts, partials, rings = cts.copy(), partials.copy(), rings.copy()
+    tampered = tamper_range(cts, partials, rings, rnd, frac) if frac else []
+    expected = O.verify_range_batch(pk, spec, label, cts, partials, rings)
+    got = e.verify_range(rng, label, cts, partials, rings)
+    assert got.tolist() == expected.tolist()
+    if frac:
+        assert (expected[tampered] != 0).all() and (np.delete(expected, tampered) == 0).all()
+    # a proof is bound to its transcript label (range.rs:732-794)
+    other = e.verify_range(rng, "another_label", cts[:4], partials[:4], rings[:4])
+    assert (other != 0).all()
+
+
+def as_engine_keyset(ks):
+    from elastic_elgamal_b200 import _ffi
+    out = _ffi.KeySet()
+    O.C.memmove(O.C.byref(out), O.C.byref(ks), O.C.sizeof(_ffi.KeySet))
+    return out
+
+
+def as_engine_qv(p):
+    from elastic_elgamal_b200 import _ffi
+    out = _ffi.QvParams()
+    out.options, out.credits = p.options, p.credits
+    for dst, src in ((out.vote_range, p.vote_range), (out.credit_range, p.credit_range)):
+        dst.n_rings = src.n_rings
+        for i in range(src.n_rings):
+            dst.size[i], dst.step[i] = src.size[i], src.step[i]
+    return out
+
+
+QV_VOTES = [[4, 0, 0, 1, 1], [1, 3, 0, 3, 1], [0, 0, 0, 0, 0], [2, 2, 2, 2, 2]]      # quadratic_voting.rs:188 and friends
+
+
+def check_verify_qv(e, pk, sk=None, n=12, options=5, credits=20, seed=4):
+    p = O.qv_params(options, credits)
+    ep = e.qv_params(options, credits)
+    assert ep.vote_range.rings == p.vote_range.rings and ep.credit_range.rings == p.credit_range.rings
+    bsz = O.qv_ballot_size(p)
+    assert e.qv_ballot_size(ep) == bsz
+    rnd = random.Random(seed)
+    if options == 5 and credits == 20:
+        votes = [QV_VOTES[i % 4] for i in range(n)]
+    else:
+        mv = int(O.lib().eo_isqrt(credits))
+        votes = []
+        for _ in range(n):
+            while True:
+                v = [rnd.randrange(mv + 1) for _ in range(options)]
+                if sum(x * x for x in v) <= credits:
+                    break
+            votes.append(v)
+    ballots = O.gen_qv_batch(pk, p, W.SEED_QV, np.array(votes, np.uint64)).copy()
+    vsz = 64 + 64 * (p.vote_range.n_rings - 1) + 32 * (1 + p.vote_range.rings_size)
+    csz = 64 + 64 * (p.credit_range.n_rings - 1) + 32 * (1 + p.credit_range.rings_size)
+    if n >= 8:
+        # the reference's tamper patterns (quadratic_voting.rs:433-464) at fixed positions
+        o = 2 % options
+        ballots[1, vsz * o + 32:vsz * o + 64] = np.frombuffer(O.point_add(bytes(ballots[1, vsz * o + 32:vsz * o + 64]), W.G_ENC), np.uint8)
+        ballots[2, vsz * options:vsz * options + 64] = ballots[3, vsz * options:vsz * options + 64]
+        ballots[4, -32 * (2 * options + 2):] = ballots[5, -32 * (2 * options + 2):]
+        ballots[6, -1] = 0xff
+        ballots[7, 0:32] = np.frombuffer(W.BAD_POINT, np.uint8)
+    expected, exp_tally = O.verify_qv_batch(pk, p, ballots)
+    got, tally = e.verify_qv(ep, ballots)
+    assert got.tolist() == expected.tolist(), (got, expected)
+    assert (tally == exp_tally).all()
+    if n >= 8:
+        assert expected[1] == O.QV_VARIANT_BASE + o and expected[2] == O.QV_CREDIT_RANGE and expected[6] == O.MALFORMED
+        assert expected[7] == O.MALFORMED and expected[0] == O.OK
+    if sk is not None:
+        table = O.DlogTable(0, 4 * n + 1)
+        ok = [i for i in range(n) if expected[i] == 0]
+        for k in range(options):
+            assert table.get(O.decrypt_to_element(sk, bytes(tally[k]))) == sum(votes[i][k] for i in ok)
+
+
+def check_shares_and_decrypt(e, n=10, shares=5, threshold=3, used=(0, 2, 4), table_hi=64, seed=6):
+    rng = O.rng_from_seed(bytes([9] * 32))
+    ks, secrets = O.dealer_new(shares, threshold, rng)
+    eks = as_engine_keyset(ks)
+    shared = bytes(ks.shared_key)
+    rnd = random.Random(seed)
+    values = [0, table_hi - 1, table_hi + 5] + [rnd.randrange(table_hi) for _ in range(n - 3)]
+    cts = [O.encrypt(shared, v, rng) for v in values[:n]]
+    sh, pr = [], []
+    for ct in cts:
+        row = [O.decrypt_share(ks, i, secrets[i], ct, rng) for i in used]
+        sh.append([r[0] for r in row]); pr.append([r[1] for r in row])
+    cts_a = np.frombuffer(b"".join(cts), np.uint8).reshape(n, 64).copy()
+    sh_a = np.frombuffer(b"".join(b"".join(r) for r in sh), np.uint8).reshape(n, len(used), 32).copy()
+    pr_a = np.frombuffer(b"".join(b"".join(r) for r in pr), np.uint8).reshape(n, len(used), 64).copy()
+    # tamper: proof of another tally, share of another participant, malformed share, malformed scalar, malformed ciphertext
+    if n >= 8:
+        pr_a[1, 0] = pr_a[2, 0]
+        sh_a[3, 1] = sh_a[3, 2]
+        sh_a[4, 2] = np.frombuffer(W.BAD_POINT, np.uint8)
+        pr_a[5, 1, 32:] = np.frombuffer(W.BAD_SCALAR, np.uint8)
+        cts_a[6, :32] = np.frombuffer(W.BAD_POINT2, np.uint8)
+    expected = np.array([[O.verify_share(ks, used[j], bytes(cts_a[i]), bytes(sh_a[i, j]), bytes(pr_a[i, j])) for j in range(len(used))]
+                         for i in range(n)], np.uint8)
+    got = e.verify_shares(eks, list(used), cts_a, sh_a, pr_a)
+    assert got.tolist() == expected.tolist(), (got, expected)
+    if n >= 8:
+        assert expected[1, 0] == O.CHALLENGE_MISMATCH and expected[4, 2] == O.MALFORMED and (expected[6] == O.MALFORMED).all()
+        assert (expected[0] == 0).all()
+    # combine + decrypt + table lookup (sharing/mod.rs:302-325, decryption.rs:138-144, encryption.rs:287-297)
+    table = e.dlog_table(0, table_hi)
+    otable = O.DlogTable(0, table_hi)
+    vals, found = e.combine_decrypt(list(used[:threshold]), cts_a, sh_a, table)
+    for i in range(n):
+        rc, elem = O.combine_decrypt(list(used[:threshold]), [bytes(sh_a[i, j]) for j in range(threshold)], bytes(cts_a[i]))
+        if rc != 0:
+            assert found[i] == 2
+            continue
+        ov = otable.get(elem)
+        if ov is None:
+            assert found[i] == 0
+        else:
+            assert found[i] == 1 and int(vals[i]) == ov
+    assert found[0] == 1 and vals[0] == 0 and found[1] == 1 and vals[1] == table_hi - 1 and found[2] == 0
+    table.close()

@@ -99,3 +99,44 @@ def test_large_batch_properties(env):
     for k in range(5):
         expect = reps * int(np.count_nonzero(accepted[k::5]))
         assert table.get(O.decrypt_to_element(sk, bytes(t[k]))) == expect
+
+
+def test_range_decomposition(env):
+    PC.check_range_decomposition(env[0])
+
+
+@pytest.mark.parametrize("ub", [2, 5, 16, 21, 100, 1000, 65536])      # 65536 = BASELINE config 4 (8 rings x 4)
+def test_verify_range(env, ub):
+    PC.check_verify_range(env[0], env[2], ub, n=120 if ub < 65536 else 64, frac=0.2)
+
+
+def test_verify_qv_config3_shape(env):
+    PC.check_verify_qv(env[0], env[2], env[1], n=96)                   # 5 options / 20 credits
+
+
+def test_verify_qv_other_shapes(env):
+    PC.check_verify_qv(env[0], env[2], env[1], n=16, options=3, credits=15)
+    PC.check_verify_qv(env[0], env[2], env[1], n=16, options=8, credits=30)
+
+
+def test_shares_config5_shape(env):
+    PC.check_shares_and_decrypt(env[0], n=200, shares=5, threshold=3, used=(0, 2, 4), table_hi=1 << 12)
+
+
+def test_shares_other_params(env):
+    PC.check_shares_and_decrypt(env[0], n=16, shares=10, threshold=7, used=(1, 2, 3, 5, 6, 8, 9), table_hi=100)
+    PC.check_shares_and_decrypt(env[0], n=16, shares=2, threshold=1, used=(1,), table_hi=100)
+
+
+def test_dlog_table_large(env):
+    e, sk, pk = env
+    table = e.dlog_table(0, 1 << 20)
+    rng = O.rng_from_seed(bytes([9] * 32))
+    ks, secrets = O.dealer_new(3, 2, rng)
+    shared = bytes(ks.shared_key)
+    values = [0, 1, (1 << 20) - 1, 1 << 20, 777777, 123456]
+    cts = [O.encrypt(shared, v, rng) for v in values]
+    sh = [[O.decrypt_share(ks, i, secrets[i], ct, rng)[0] for i in (0, 2)] for ct in cts]
+    vals, found = e.combine_decrypt([0, 2], np.frombuffer(b"".join(cts), np.uint8), np.frombuffer(b"".join(b"".join(r) for r in sh), np.uint8), table)
+    assert found.tolist() == [1, 1, 1, 0, 1, 1] and [int(v) for v in vals[[0, 1, 2, 4, 5]]] == [0, 1, (1 << 20) - 1, 777777, 123456]
+    table.close()

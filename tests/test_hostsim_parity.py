@@ -67,3 +67,24 @@ def test_receiver_validation(env):
         e.verify_bool(np.zeros((1, 64), np.uint8), np.zeros((1, 96), np.uint8))
     assert ei.value.status == _ffi.ERR_NO_RECEIVER
     e.set_receiver(pk)
+
+
+def test_range_decomposition(env):
+    PC.check_range_decomposition(env[0])
+
+
+@pytest.mark.parametrize("ub", [2, 5, 21, 100])
+def test_verify_range(env, ub):
+    PC.check_verify_range(env[0], env[2], ub, n=8, frac=0.5)
+
+
+def test_verify_qv(env):
+    PC.check_verify_qv(env[0], env[2], env[1], n=8)
+
+
+def test_verify_qv_other_shape(env):
+    PC.check_verify_qv(env[0], env[2], env[1], n=3, options=3, credits=15)
+
+
+def test_shares_and_decrypt(env):
+    PC.check_shares_and_decrypt(env[0], n=8)
