@@ -271,7 +271,8 @@ def check_shares_and_decrypt(e, n=10, shares=5, threshold=3, used=(0, 2, 4), tab
     sh_a = np.frombuffer(b"".join(b"".join(r) for r in sh), np.uint8).reshape(n, len(used), 32).copy()
     pr_a = np.frombuffer(b"".join(b"".join(r) for r in pr), np.uint8).reshape(n, len(used), 64).copy()
     # tamper: proof of another tally, share of another participant, malformed share, malformed scalar, malformed ciphertext
-    if n >= 8:
+    tamper = n >= 8 and len(used) >= 3
+    if tamper:
         pr_a[1, 0] = pr_a[2, 0]
         sh_a[3, 1] = sh_a[3, 2]
         sh_a[4, 2] = np.frombuffer(W.BAD_POINT, np.uint8)
@@ -281,7 +282,7 @@ def check_shares_and_decrypt(e, n=10, shares=5, threshold=3, used=(0, 2, 4), tab
                          for i in range(n)], np.uint8)
     got = e.verify_shares(eks, list(used), cts_a, sh_a, pr_a)
     assert got.tolist() == expected.tolist(), (got, expected)
-    if n >= 8:
+    if tamper:
         assert expected[1, 0] == O.CHALLENGE_MISMATCH and expected[4, 2] == O.MALFORMED and (expected[6] == O.MALFORMED).all()
         assert (expected[0] == 0).all()
     # combine + decrypt + table lookup (sharing/mod.rs:302-325, decryption.rs:138-144, encryption.rs:287-297)
