@@ -15,6 +15,16 @@
 
 #define U 8
 
+__device__ __forceinline__ long long gtime_ns() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+
+// SM clock actually in effect: clock64 ticks per globaltimer nanosecond over a ~1 ms spin (thread 0 of block 0)
+__global__ void k_clock_probe(double *mhz) {
+    long long g0 = gtime_ns(), c0 = clock64();
+    while (gtime_ns() - g0 < 1000000) { }
+    long long g1 = gtime_ns(), c1 = clock64();
+    *mhz = (double)(c1 - c0) * 1e3 / (double)(g1 - g0);
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(256) k_pipe(int iters, uint32_t a, uint32_t b, uint32_t *sink, long long *cycles) {
     uint32_t x[U];
@@ -140,12 +150,27 @@ int main(int argc, char **argv) {
     FIELD(0, "fe_mul_ptx_w32", 8);
     FIELD(1, "fe_sq_ptx_w32", 8);
 
+    // SM clock in effect while the integer pipe is loaded: probe kernel on a second stream next to a long IMAD launch
+    double *d_mhz, h_mhz = 0;
+    cudaMalloc(&d_mhz, sizeof(double));
+    cudaStream_t s2;
+    cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking);
+    k_pipe<0><<<sms * 2, 256>>>(1 << 17, 0x9e3779b1u, 12345u, sink, cycles);
+    k_clock_probe<<<1, 1, 0, s2>>>(d_mhz);
+    cudaDeviceSynchronize();
+    cudaMemcpy(&h_mhz, d_mhz, sizeof(double), cudaMemcpyDeviceToHost);
+
     int clock_khz = 0;
     cudaDeviceGetAttribute(&clock_khz, cudaDevAttrClockRate, dev);
-    printf("{\"device\": \"%s\", \"sms\": %d, \"max_clock_mhz\": %.0f, \"iters\": %d, \"tests\": {", prop.name, sms, clock_khz / 1000.0, iters);
+    // `per_s` (CUDA events around the launch) is the rate the roofline uses; `per_clk_per_sm` = per_s / (SMs x the probed
+    // SM clock); `per_clk_per_sm_clock64` is the in-kernel clock64 estimate (kept for comparison only: it assumes that
+    // all CTAs of an SM are co-resident for the whole launch).
+    printf("{\"device\": \"%s\", \"sms\": %d, \"max_clock_mhz\": %.0f, \"sm_clock_mhz_probed\": %.1f, \"iters\": %d, \"tests\": {",
+           prop.name, sms, clock_khz / 1000.0, h_mhz, iters);
     for (size_t i = 0; i < results.size(); i++)
-        printf("%s\"%s\": {\"per_clk_per_sm\": %.2f, \"per_s\": %.4e, \"ms\": %.3f}", i ? ", " : "", results[i].name.c_str(),
-               results[i].ops_per_clk_sm, results[i].ops_per_s, results[i].ms);
+        printf("%s\"%s\": {\"per_s\": %.4e, \"per_clk_per_sm\": %.2f, \"per_clk_per_sm_clock64\": %.2f, \"ms\": %.3f}", i ? ", " : "",
+               results[i].name.c_str(), results[i].ops_per_s, h_mhz > 0 ? results[i].ops_per_s / (sms * h_mhz * 1e6) : 0.0,
+               results[i].ops_per_clk_sm, results[i].ms);
     printf("}}\n");
     cudaError_t ce = cudaGetLastError();
     if (ce != cudaSuccess) { fprintf(stderr, "CUDA error: %s\n", cudaGetErrorString(ce)); return 1; }
