@@ -53,6 +53,8 @@ def parse_args():
     ap.add_argument("--unique", type=int, default=4096, help="distinct oracle-generated ballots that are tiled")
     ap.add_argument("--cpu-sample", type=int, default=0, help="ballots in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ring-mode", type=int, default=2, choices=[1, 2], help="2: k_ring (default); 1: per-equation k_commit launches")
+    ap.add_argument("--chunk", type=int, default=0, help="ballots per internal chunk (0 = library default)")
     return ap.parse_args()
 
 
@@ -199,6 +201,9 @@ def main():
     threads = O.hw_threads()
     sk, pk, cts, rings, sums = make_workload(args.unique, max(1, threads // max(1, min(world, 8))))
     e.set_receiver(pk)
+    e.set_ring_mode(args.ring_mode)
+    if args.chunk:
+        e.set_chunk_items(args.chunk)
     ov, ot = O.verify_choice_batch(pk, OPTIONS, True, cts, rings, sums, threads=max(1, threads // max(1, min(world, 8))))
 
     B = args.ballots
@@ -215,6 +220,7 @@ def main():
     d_verdicts = torch.empty(B, dtype=torch.uint8, device=dev)
     d_tally = torch.empty((OPTIONS, 64), dtype=torch.uint8, device=dev)
     gathered = torch.empty((world, OPTIONS, 64), dtype=torch.uint8, device=dev) if world > 1 else None
+    d_total = torch.empty((OPTIONS, 64), dtype=torch.uint8, device=dev) if world > 1 else None
     stream = torch.cuda.ExternalStream(e.stream, device=dev)
 
     def step_device():
@@ -224,6 +230,7 @@ def main():
             # the only exchange step: per-rank partial tallies (options x 64 B); NCCL has no EC-add reduction, so
             # all_gather + a local point-add kernel
             dist.all_gather_into_tensor(gathered, d_tally)
+            e.ciphertexts_sum_dev(world, OPTIONS, gathered.data_ptr(), d_total.data_ptr())
 
     def barrier():
         torch.cuda.synchronize()
@@ -261,8 +268,9 @@ def main():
     v = d_verdicts.cpu().numpy()
     assert (v == expected_v).all(), "verdict mismatch against the oracle"
     if world > 1:
-        total, ok = e.ciphertexts_sum(gathered.cpu().numpy())
-        assert ok
+        total = d_total.cpu().numpy()
+        check, ok = e.ciphertexts_sum(gathered.cpu().numpy())
+        assert ok and (check == total).all()
     else:
         total = d_tally.cpu().numpy()
     if rank == 0:
@@ -315,10 +323,13 @@ def main():
     peak = int32_peak()
     imad = peak.get("tests", {}).get("imad", {})
     clk = sampler.summary()
-    # peak = measured IMAD lane-ops per clock per SM x SMs x the SM clock observed during the timed region
+    # peak = IMAD lane-ops/s measured with CUDA events by the microbenchmark, rescaled by (SM clock sampled during the
+    # timed region) / (SM clock probed in the microbenchmark: clock64 ticks per globaltimer ns) when the two differ
     peak_ops = None
-    if imad.get("per_clk_per_sm") and clk.get("sm_mhz"):
-        peak_ops = imad["per_clk_per_sm"] * peak.get("sms", 148) * clk["sm_mhz"] * 1e6
+    if imad.get("per_s"):
+        peak_ops = imad["per_s"]
+        if clk.get("sm_mhz") and peak.get("sm_clock_mhz_probed"):
+            peak_ops *= clk["sm_mhz"] / peak["sm_clock_mhz_probed"]
     achieved_ops = commit_tasks * FIELD_OPS_PER_COMMIT * IMAD_PER_FIELD_OP / (commit_ms * 1e-3) if commit_ms > 0 else None
     traffic = None
     tfile = ROOT / "profiles" / "k_commit_traffic.json"
@@ -328,12 +339,12 @@ def main():
         except Exception:
             traffic = None
     roofline = {
-        "kernel": "k_commit", "bound": "int32",
+        "kernel": "k_ring" if args.ring_mode == 2 else "k_commit", "bound": "int32",
         "achieved": achieved_ops / 1e12 if achieved_ops else None, "peak": peak_ops / 1e12 if peak_ops else None,
         "unit": "T int32 multiply-add lane-ops/s",
         "frac": (achieved_ops / peak_ops) if achieved_ops and peak_ops else None,
-        "peak_source": "measured live: tools/microbench/int_pipe_bench `imad` lane-ops/clk/SM x SMs x SM clock sampled during the timed "
-                       "region (MEASURED_PEAKS.json has no integer peak)",
+        "peak_source": "measured live: tools/microbench/int_pipe_bench `imad` lane-ops/s (CUDA events; = 63 of the nominal 64 "
+                       "lanes/clk/SM) at the SM clock sampled during the timed region (MEASURED_PEAKS.json has no integer peak)",
         "traffic": traffic,
         "launches": commit_launches, "avg_launch_ms": commit_ms / max(1, commit_launches),
         "share_of_step": commit_ms / dev_ms if dev_ms else None,

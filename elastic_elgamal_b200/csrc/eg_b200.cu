@@ -65,6 +65,29 @@ __global__ void __launch_bounds__(EG_COMMIT_THREADS, EG_COMMIT_MINBLOCKS) k_comm
     commit_body(P, tid % P.n, (int)(tid / P.n), s_tab, s_tab + EG_FIXED_TABLE_WORDS);
 }
 
+// v2 ring engine: persistent grid (one CTA slot per resident CTA), each thread walks (item, ring) pairs with a fixed
+// 8 KB scratch region for the window tables of its current ring.  Both 48 KB chunked fixed-base tables live in shared
+// memory (dynamic, 96 KB per CTA).
+#ifndef EG_RING_THREADS
+#define EG_RING_THREADS 256
+#endif
+#ifndef EG_RING_MINBLOCKS
+#define EG_RING_MINBLOCKS 2
+#endif
+__global__ void __launch_bounds__(EG_RING_THREADS, EG_RING_MINBLOCKS) k_ring(const ring_params P) {
+    extern __shared__ __align__(16) uint32_t s_rtab[];
+    for (int k = threadIdx.x; k < EG_FCHUNK_TABLE_WORDS; k += blockDim.x) {
+        s_rtab[k] = P.table_g[k];
+        s_rtab[EG_FCHUNK_TABLE_WORDS + k] = P.table_k[k];
+    }
+    __syncthreads();
+    const size_t total = P.n * (size_t)P.n_rings, stride = (size_t)gridDim.x * blockDim.x;
+    const size_t slot = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t *scratch = P.scratch + slot * (2 * EG_VTAB_WORDS);
+    for (size_t tid = slot; tid < total; tid += stride)
+        ring_body(P, tid % P.n, (uint32_t)(tid / P.n), scratch, s_rtab, s_rtab + EG_FCHUNK_TABLE_WORDS);
+}
+
 __global__ void __launch_bounds__(128) k_ring_hash(const ring_hash_params P) {
     size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= P.n * (size_t)P.n_slots) return;
@@ -102,7 +125,7 @@ __global__ void __launch_bounds__(256) k_verdict(const verdict_params P) {
 }
 
 __global__ void k_build_table(const uint32_t *enc_words, int use_generator, uint32_t *table, uint32_t *status) {
-    build_table_body(threadIdx.x, enc_words, use_generator, table, status);
+    build_table_body(blockIdx.x * blockDim.x + threadIdx.x, enc_words, use_generator, table, status);
 }
 
 __global__ void k_admissible(const uint64_t *values, int count, uint32_t *adm) {
@@ -312,6 +335,9 @@ struct eg_ctx {
     size_t adm_used = 0;      // cached points in `adm` (32 words each); entries 0,1 = the [O, G] pair
     std::map<std::string, std::vector<uint64_t>> adm_cache_key;
     size_t chunk_items = 0;   // 0 = default
+    int ring_mode = 2;        // 2: k_ring (one thread per ring, chunked tables); 1: k_commit / k_ring_hash launches per equation
+    int ring_grid = 0;        // resident CTAs of k_ring (queried once)
+    dev_buf ring_scratch;
 };
 
 struct eg_dlog_table {
@@ -402,6 +428,49 @@ static void launch_commit(eg_ctx *ctx, const commit_params &P) {
     ctx->call_commit_launches++;
 }
 
+// One launch evaluates every equation of every ring of the chunk.  Accounted like k_commit: tasks = equation sides.
+static eg_status launch_ring(eg_ctx *ctx, ring_params &P) {
+    size_t sides = 0;
+    for (uint32_t r = 0; r < P.n_rings; r++) sides += 2 * (size_t)P.sizes[r];
+    sides *= P.n;
+    if (ctx->commit_ev_used + 2 > ctx->commit_ev.size()) {
+        cudaEvent_t a = nullptr, b = nullptr;
+        cudaEventCreate(&a); cudaEventCreate(&b);
+        ctx->commit_ev.push_back(a); ctx->commit_ev.push_back(b);
+    }
+    cudaEvent_t e_start = ctx->commit_ev[ctx->commit_ev_used], e_stop = ctx->commit_ev[ctx->commit_ev_used + 1];
+    ctx->commit_ev_used += 2;
+    const size_t total = P.n * (size_t)P.n_rings;
+#ifdef EG_HOSTSIM
+    TRY(ensure(ctx, ctx->ring_scratch, 2 * EG_VTAB_WORDS * 4));
+    P.scratch = (uint32_t *)ctx->ring_scratch.p;
+    cudaEventRecord(e_start, ctx->stream);
+    EG_FOR_HOST(total, ring_body(P, tid % P.n, (uint32_t)(tid / P.n), P.scratch, P.table_g, P.table_k))
+#else
+    const size_t smem = 2 * EG_FCHUNK_TABLE_WORDS * 4;
+    if (ctx->ring_grid == 0) {
+        CU(cudaFuncSetAttribute(k_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0, sms = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ring, EG_RING_THREADS, smem));
+        CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+        if (per_sm < 1) return fail(ctx, EG_ERR_CUDA, "k_ring does not fit on an SM");
+        ctx->ring_grid = per_sm * sms;
+    }
+    const unsigned grid = (unsigned)std::min<size_t>((size_t)ctx->ring_grid, (total + EG_RING_THREADS - 1) / EG_RING_THREADS);
+    TRY(ensure(ctx, ctx->ring_scratch, (size_t)ctx->ring_grid * EG_RING_THREADS * 2 * EG_VTAB_WORDS * 4));
+    P.scratch = (uint32_t *)ctx->ring_scratch.p;
+    cudaEventRecord(e_start, ctx->stream);
+    k_ring<<<grid, EG_RING_THREADS, smem, ctx->stream>>>(P);
+#endif
+    cudaEventRecord(e_stop, ctx->stream);
+    ctx->launches++;
+    ctx->commit_launches++;
+    ctx->commit_tasks += sides;
+    ctx->call_commit_tasks += sides;
+    ctx->call_commit_launches++;
+    return EG_SUCCESS;
+}
+
 static void launch_ring_hash(eg_ctx *ctx, const ring_hash_params &P) {
     size_t total = P.n * (size_t)P.n_slots;
 #ifdef EG_HOSTSIM
@@ -459,9 +528,9 @@ static void launch_verdict(eg_ctx *ctx, const verdict_params &P) {
 
 static void launch_build_table(eg_ctx *ctx, const uint32_t *enc_words, int use_generator, uint32_t *table, uint32_t *status) {
 #ifdef EG_HOSTSIM
-    EG_FOR_HOST(EG_FIXED_TABLE_ENTRIES, build_table_body((int)tid, enc_words, use_generator, table, status))
+    EG_FOR_HOST(EG_VCHUNKS * EG_FIXED_TABLE_ENTRIES, build_table_body((int)tid, enc_words, use_generator, table, status))
 #else
-    k_build_table<<<1, EG_FIXED_TABLE_ENTRIES, 0, ctx->stream>>>(enc_words, use_generator, table, status);
+    k_build_table<<<EG_VCHUNKS, EG_FIXED_TABLE_ENTRIES, 0, ctx->stream>>>(enc_words, use_generator, table, status);
 #endif
     ctx->launches++;
 }
@@ -654,6 +723,12 @@ extern "C" eg_status eg_ctx_set_chunk_items(eg_ctx *ctx, size_t items) {
     return EG_SUCCESS;
 }
 
+extern "C" eg_status eg_ctx_set_ring_mode(eg_ctx *ctx, int mode) {
+    if (!ctx || (mode != 1 && mode != 2)) return EG_ERR_INVALID_ARG;
+    ctx->ring_mode = mode;
+    return EG_SUCCESS;
+}
+
 extern "C" eg_status eg_ctx_create(int device_id, eg_ctx **out) {
     if (!out) return EG_ERR_INVALID_ARG;
     *out = nullptr;
@@ -669,8 +744,8 @@ extern "C" eg_status eg_ctx_create(int device_id, eg_ctx **out) {
     if (cudaSetDevice(device_id) != cudaSuccess) return bail(EG_ERR_NO_DEVICE);
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(EG_ERR_CUDA);
     for (auto &e : ctx->ev) if (cudaEventCreate(&e) != cudaSuccess) return bail(EG_ERR_CUDA);
-    if (cudaMalloc(&ctx->d_table_g, EG_FIXED_TABLE_WORDS * 4) != cudaSuccess) return bail(EG_ERR_OUT_OF_MEMORY);
-    if (cudaMalloc(&ctx->d_table_k, EG_FIXED_TABLE_WORDS * 4) != cudaSuccess) return bail(EG_ERR_OUT_OF_MEMORY);
+    if (cudaMalloc(&ctx->d_table_g, EG_FCHUNK_TABLE_WORDS * 4) != cudaSuccess) return bail(EG_ERR_OUT_OF_MEMORY);
+    if (cudaMalloc(&ctx->d_table_k, EG_FCHUNK_TABLE_WORDS * 4) != cudaSuccess) return bail(EG_ERR_OUT_OF_MEMORY);
     if (cudaMalloc(&ctx->d_status, 1024) != cudaSuccess) return bail(EG_ERR_OUT_OF_MEMORY);
     launch_build_table(ctx, nullptr, 1, ctx->d_table_g, ctx->d_status);
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) return bail(EG_ERR_CUDA);
@@ -683,7 +758,7 @@ extern "C" void eg_ctx_destroy(eg_ctx *ctx) {
     cudaSetDevice(ctx->device);
     dev_buf *bufs[] = {&ctx->pts, &ctx->enc, &ctx->commit, &ctx->chal, &ctx->flags, &ctx->res[0], &ctx->res[1], &ctx->res[2],
                        &ctx->in[0], &ctx->in[1], &ctx->in[2], &ctx->in[3], &ctx->verdicts, &ctx->partial, &ctx->running,
-                       &ctx->adm, &ctx->misc, &ctx->slots, &ctx->consts, &ctx->res_big};
+                       &ctx->adm, &ctx->misc, &ctx->slots, &ctx->consts, &ctx->res_big, &ctx->ring_scratch};
     for (dev_buf *b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->d_table_g) cudaFree(ctx->d_table_g);
     if (ctx->d_table_k) cudaFree(ctx->d_table_k);
@@ -720,6 +795,7 @@ struct ring_job {
     uint32_t ct_p_index[EG_MAX_RINGS];      // ring r ciphertext: R at ct_p_index[r], B at +1
     uint32_t ct_enc_index[EG_MAX_RINGS];    // enc(R) at ct_enc_index[r], enc(B) at +1
     int32_t adm_index[EG_MAX_RINGS];        // admissible value j of ring r (j >= 1) at adm_index[r] + j; -1: [O, G] pair
+    uint64_t adm_step[EG_MAX_RINGS];        // admissible value j of ring r = [j * adm_step[r]] G
     uint8_t proof_buf = 0;                  // input buffer of the ring proof (e0 | responses)
     uint32_t proof_offset = 0;              // byte offset of the proof inside the item
     uint32_t commit_index0 = 0;             // planar commitments: ring r -> commit_index0 + 2r (+1)
@@ -739,6 +815,31 @@ static eg_status run_ring_job(eg_ctx *ctx, const ring_job &job, const in_bufs &i
                               const uint32_t *d_adm) {
     uint32_t max_size = 0, starts[EG_MAX_RINGS], start = 0;
     for (uint32_t r = 0; r < job.n_rings; r++) { starts[r] = start; start += job.sizes[r]; max_size = std::max(max_size, job.sizes[r]); }
+    if (ctx->ring_mode == 2) {
+        if (n_extra > 0) {          // e.g. the sum proof of an EncryptedChoice: single-use points, plain chain
+            commit_params cp;
+            memset(&cp, 0, sizeof cp);
+            cp.in = in; cp.n = n;
+            cp.pts = (const uint32_t *)ctx->pts.p; cp.chal = (const uint32_t *)ctx->chal.p; cp.commit = (uint32_t *)ctx->commit.p;
+            cp.adm = d_adm; cp.table_g = ctx->d_table_g; cp.table_k = ctx->d_table_k;
+            for (int k = 0; k < n_extra; k++) cp.slots[k] = extra[k];
+            cp.n_slots = n_extra;
+            launch_commit(ctx, cp);
+        }
+        ring_params rp;
+        memset(&rp, 0, sizeof rp);
+        rp.in = in; rp.n = n; rp.n_rings = job.n_rings;
+        for (uint32_t r = 0; r < job.n_rings; r++) {
+            rp.sizes[r] = (uint16_t)job.sizes[r]; rp.starts[r] = (uint16_t)starts[r];
+            rp.ct_p_index[r] = job.ct_p_index[r]; rp.ct_enc_index[r] = job.ct_enc_index[r]; rp.adm_step[r] = job.adm_step[r];
+        }
+        rp.proof_buf = job.proof_buf; rp.proof_offset = job.proof_offset; rp.commit_index0 = job.commit_index0;
+        rp.prefix = job.prefix;
+        rp.pts = (const uint32_t *)ctx->pts.p; rp.enc = (const uint32_t *)ctx->enc.p; rp.commit = (uint32_t *)ctx->commit.p;
+        rp.table_g = ctx->d_table_g; rp.table_k = ctx->d_table_k;
+        TRY(launch_ring(ctx, rp));
+        max_size = 0;               // skip the per-equation launches below
+    }
     for (uint32_t j = 0; j < max_size; j++) {
         // ---- commitments of equation j for every ring that has one (ring.rs:342-350)
         uint32_t r0 = 0;
@@ -875,7 +976,7 @@ static eg_status verify_bool_chunk(eg_ctx *ctx, size_t n, const uint8_t *d_cts, 
     launch_scalars(ctx, sp);
 
     ring_job job;
-    job.n_rings = 1; job.sizes[0] = 2; job.ct_p_index[0] = 0; job.ct_enc_index[0] = 0; job.adm_index[0] = 0;
+    job.n_rings = 1; job.sizes[0] = 2; job.ct_p_index[0] = 0; job.ct_enc_index[0] = 0; job.adm_index[0] = 0; job.adm_step[0] = 1;
     job.proof_buf = 1; job.proof_offset = 0; job.commit_index0 = 0; job.chal_index0 = 0;
     merlin_new(job.prefix, EG_LBL("bool_encryption"));            // keys/impls.rs:111
     host_ring_initialize(job.prefix, ctx->key);
@@ -1063,7 +1164,7 @@ static eg_status verify_choice_chunk(eg_ctx *ctx, size_t n, uint32_t m, int sing
 
     ring_job job;
     job.n_rings = m;
-    for (uint32_t r = 0; r < m; r++) { job.sizes[r] = 2; job.ct_p_index[r] = 2 * r; job.ct_enc_index[r] = 2 * r; job.adm_index[r] = 0; }
+    for (uint32_t r = 0; r < m; r++) { job.sizes[r] = 2; job.ct_p_index[r] = 2 * r; job.ct_enc_index[r] = 2 * r; job.adm_index[r] = 0; job.adm_step[r] = 1; }
     job.proof_buf = 1; job.proof_offset = 0; job.commit_index0 = 0; job.chal_index0 = 0;
     merlin_new(job.prefix, EG_LBL("encrypted_choice_ranges"));       // choice.rs:376
     host_ring_initialize(job.prefix, ctx->key);
@@ -1271,6 +1372,20 @@ extern "C" eg_status eg_ciphertexts_sum(eg_ctx *ctx, size_t n_parts, size_t n_ct
     return EG_SUCCESS;
 }
 
+// device-pointer variant: the combine step after the all_gather of per-GPU partial tallies (asynchronous on the
+// context's stream; undecodable parts are reported through *d_bad_flag when it is non-null)
+extern "C" eg_status eg_ciphertexts_sum_dev(eg_ctx *ctx, size_t n_parts, size_t n_cts, const uint8_t *d_parts, uint8_t *d_out,
+                                            uint32_t *d_bad_flag) {
+    if (!ctx || !d_out || (n_parts && !d_parts)) return EG_ERR_INVALID_ARG;
+    CU(cudaSetDevice(ctx->device));
+    if (n_cts == 0) return EG_SUCCESS;
+    uint32_t *d_bad = d_bad_flag ? d_bad_flag : ctx->d_status + 4;
+    CU(cudaMemsetAsync(d_bad, 0, 4, ctx->stream));
+    launch_ciphertexts_sum(ctx, d_parts, n_parts, n_cts, d_out, d_bad);
+    CU(cudaGetLastError());
+    return EG_SUCCESS;
+}
+
 // =================================================================== RangeDecomposition (host logic)
 
 namespace {
@@ -1448,7 +1563,7 @@ static eg_status verify_range_items(eg_ctx *ctx, size_t n, const eg_range &range
     ring_job job;
     job.n_rings = R;
     for (uint32_t r = 0; r < R; r++) {
-        job.sizes[r] = (uint32_t)range.size[r]; job.ct_p_index[r] = 2 * r; job.ct_enc_index[r] = 2 * r; job.adm_index[r] = adm_base[r];
+        job.sizes[r] = (uint32_t)range.size[r]; job.ct_p_index[r] = 2 * r; job.ct_enc_index[r] = 2 * r; job.adm_index[r] = adm_base[r]; job.adm_step[r] = range.step[r];
     }
     job.proof_buf = lay.ring_buf; job.proof_offset = lay.ring_off; job.commit_index0 = 0; job.chal_index0 = 0;
     merlin_new(job.prefix, label, (uint32_t)strlen(label));

@@ -258,6 +258,213 @@ EG_HD void ge_msm_chain(ge_ext &out, const ge_ext *P, const sc *a, const uint32_
 }
 
 
+// ------------------------------------------------------------------ chunked tables: 64 doublings per equation
+//
+// A ring proof evaluates several equations on the SAME ciphertext points (one per admissible value, ring.rs:333-361)
+// with different challenges.  Splitting a 253-bit scalar into four 64-bit chunks, a = sum_c 2^(64c) a_c, turns
+// [a]P into sum_c [a_c] P_c with P_c = [2^(64c)] P: the 192 doublings that produce P_1..P_3 (and the four window
+// tables [1..8] P_c) are paid once per point, every equation then needs only 64 shared doublings.  The fixed bases
+// G and K get the same treatment once per context (4 x 128 affine entries each).
+
+#define EG_VCHUNKS 4
+#define EG_VTAB_ENTRY_WORDS 32                                  // one cached point
+#define EG_VTAB_WORDS (EG_VCHUNKS * 8 * EG_VTAB_ENTRY_WORDS)    // 4 KB per point
+#define EG_FCHUNK_TABLE_WORDS (EG_VCHUNKS * EG_FIXED_TABLE_WORDS)   // 48 KB per fixed base
+
+EG_HD void ge_cached_store(uint32_t *e, const ge_cached &c) {
+#if defined(__CUDA_ARCH__)
+    uint4 *q = reinterpret_cast<uint4 *>(e);
+    q[0] = make_uint4(c.YpX.v[0], c.YpX.v[1], c.YpX.v[2], c.YpX.v[3]); q[1] = make_uint4(c.YpX.v[4], c.YpX.v[5], c.YpX.v[6], c.YpX.v[7]);
+    q[2] = make_uint4(c.YmX.v[0], c.YmX.v[1], c.YmX.v[2], c.YmX.v[3]); q[3] = make_uint4(c.YmX.v[4], c.YmX.v[5], c.YmX.v[6], c.YmX.v[7]);
+    q[4] = make_uint4(c.Z.v[0], c.Z.v[1], c.Z.v[2], c.Z.v[3]);         q[5] = make_uint4(c.Z.v[4], c.Z.v[5], c.Z.v[6], c.Z.v[7]);
+    q[6] = make_uint4(c.T2d.v[0], c.T2d.v[1], c.T2d.v[2], c.T2d.v[3]); q[7] = make_uint4(c.T2d.v[4], c.T2d.v[5], c.T2d.v[6], c.T2d.v[7]);
+#else
+    for (int k = 0; k < 8; k++) { e[k] = c.YpX.v[k]; e[8 + k] = c.YmX.v[k]; e[16 + k] = c.Z.v[k]; e[24 + k] = c.T2d.v[k]; }
+#endif
+}
+
+EG_HD void ge_cached_load(ge_cached &c, const uint32_t *e) {
+#if defined(__CUDA_ARCH__)
+    const uint4 *q = reinterpret_cast<const uint4 *>(e);
+    uint4 a;
+    a = q[0]; c.YpX.v[0] = a.x; c.YpX.v[1] = a.y; c.YpX.v[2] = a.z; c.YpX.v[3] = a.w;
+    a = q[1]; c.YpX.v[4] = a.x; c.YpX.v[5] = a.y; c.YpX.v[6] = a.z; c.YpX.v[7] = a.w;
+    a = q[2]; c.YmX.v[0] = a.x; c.YmX.v[1] = a.y; c.YmX.v[2] = a.z; c.YmX.v[3] = a.w;
+    a = q[3]; c.YmX.v[4] = a.x; c.YmX.v[5] = a.y; c.YmX.v[6] = a.z; c.YmX.v[7] = a.w;
+    a = q[4]; c.Z.v[0] = a.x; c.Z.v[1] = a.y; c.Z.v[2] = a.z; c.Z.v[3] = a.w;
+    a = q[5]; c.Z.v[4] = a.x; c.Z.v[5] = a.y; c.Z.v[6] = a.z; c.Z.v[7] = a.w;
+    a = q[6]; c.T2d.v[0] = a.x; c.T2d.v[1] = a.y; c.T2d.v[2] = a.z; c.T2d.v[3] = a.w;
+    a = q[7]; c.T2d.v[4] = a.x; c.T2d.v[5] = a.y; c.T2d.v[6] = a.z; c.T2d.v[7] = a.w;
+#else
+    for (int k = 0; k < 8; k++) { c.YpX.v[k] = e[k]; c.YmX.v[k] = e[8 + k]; c.Z.v[k] = e[16 + k]; c.T2d.v[k] = e[24 + k]; }
+#endif
+}
+
+// tab[(c * 8 + k) * 32 ..] = cached((k + 1) * 2^(64 c) * P), c < 4, k < 8.  `tab` is 16-byte aligned scratch.
+static EG_HD_NOINLINE void ge_vtab_build(uint32_t *tab, const ge_ext &P) {
+    ge_ext base = P;
+#pragma unroll 1
+    for (int c = 0; c < EG_VCHUNKS; c++) {
+        ge_cached c1;
+        ge_to_cached(c1, base);
+        ge_cached_store(tab + (c * 8) * EG_VTAB_ENTRY_WORDS, c1);
+        ge_ext cur = base;
+#pragma unroll 1
+        for (int k = 1; k < 8; k++) {
+            ge_p1p1 t;
+            ge_add_cached_p1p1(t, cur, c1, false);
+            ge_p1p1_to_ext(cur, t);
+            ge_cached ck;
+            ge_to_cached(ck, cur);
+            ge_cached_store(tab + (c * 8 + k) * EG_VTAB_ENTRY_WORDS, ck);
+        }
+        if (c + 1 < EG_VCHUNKS) {
+            ge_p1p1 t;
+#pragma unroll 1
+            for (int k = 0; k < 63; k++) { ge_dbl_p1p1(t, base); ge_p1p1_to_proj(base, t); }
+            ge_dbl_p1p1(t, base); ge_p1p1_to_ext(base, t);
+        }
+    }
+}
+
+// out = [a] P + [b0] F0 (+ [b1] F1 when nf == 2): vtab from ge_vtab_build(P) (or null with a ignored), ftab* = 4-chunk
+// fixed tables.  64 doublings, <= 64 + 32 nf additions.
+static EG_HD_NOINLINE void ge_eval64(ge_ext &out, const uint32_t *vtab, const sc &a, int nf, const uint32_t *ftab0, const sc &b0,
+                     const uint32_t *ftab1, const sc &b1) {
+    uint32_t ra[8], rb0[8], rb1[8];
+    sc_recode4(ra, a);
+    sc_recode8(rb0, b0);
+    sc_recode8(rb1, b1);
+    ge_ext acc = ge_identity();
+    ge_p1p1 t;
+#pragma unroll 1
+    for (int i = 15; i >= 0; i--) {
+        if (i != 15) {
+#pragma unroll 1
+            for (int k = 0; k < 3; k++) { ge_dbl_p1p1(t, acc); ge_p1p1_to_proj(acc, t); }
+            ge_dbl_p1p1(t, acc); ge_p1p1_to_ext(acc, t);
+        }
+        if (vtab) {
+#pragma unroll 1
+            for (int c = 0; c < EG_VCHUNKS; c++) {
+                int d = sc_digit4(ra, 16 * c + i);
+                if (d != 0) {
+                    int m = d < 0 ? -d : d;
+                    ge_cached q;
+                    ge_cached_load(q, vtab + (c * 8 + m - 1) * EG_VTAB_ENTRY_WORDS);
+                    ge_add_cached_p1p1(t, acc, q, d < 0);
+                    ge_p1p1_to_ext(acc, t);
+                }
+            }
+        }
+        if ((i & 1) == 0) {
+#pragma unroll 1
+            for (int f = 0; f < nf; f++) {
+                const uint32_t *ft = f ? ftab1 : ftab0;
+                const uint32_t *rb = f ? rb1 : rb0;
+#pragma unroll 1
+                for (int c = 0; c < EG_VCHUNKS; c++) {
+                    int d = sc_digit8(rb, 8 * c + (i >> 1));
+                    if (d != 0) {
+                        int m = d < 0 ? -d : d;
+                        ge_niels n;
+                        ge_niels_load(n, ft + c * EG_FIXED_TABLE_WORDS, m - 1);
+                        ge_add_niels_p1p1(t, acc, n, d < 0);
+                        ge_p1p1_to_ext(acc, t);
+                    }
+                }
+            }
+        }
+    }
+    out = acc;
+}
+
+// x / 2 mod l
+EG_HD void sc_half(sc &r, const sc &x) {
+    uint32_t t[8];
+    uint64_t c = 0;
+    const bool odd = (x.v[0] & 1u) != 0;
+    for (int i = 0; i < 8; i++) { c += (uint64_t)x.v[i] + (odd ? sc_L(i) : 0u); t[i] = (uint32_t)c; c >>= 32; }
+    for (int i = 0; i < 7; i++) r.v[i] = (t[i] >> 1) | (t[i + 1] << 31);
+    r.v[7] = t[7] >> 1;          // x + l < 2^254: no carry out of limb 7
+}
+
+// ------------------------------------------------------------------ double-and-compress
+//
+// encode(2Q) for several Q with ONE field inversion and no square root (the doubling makes the quantity under the
+// RFC 9496 square root a known square).  A verifier that needs encode(C), C = sum [x_i] P_i, evaluates
+// Q = sum [x_i / 2 mod l] P_i instead: 2Q = C + (a 4-torsion point), and all representatives of a ristretto255
+// element encode identically.  Same bytes as serialize_element (ristretto.rs:88-90) on C.
+
+struct ge_dc_state { fe e, f, g, h, eg, fh; };
+
+EG_HD void ge_dc_prepare(ge_dc_state &s, fe &efgh, const ge_ext &P) {
+    fe xx, yy, zz, dtt, t;
+    fe_sq(xx, P.X); fe_sq(yy, P.Y); fe_sq(zz, P.Z);
+    fe_sq(t, P.T); fe_mul(dtt, t, fe_const_d());
+    fe_add(t, P.Y, P.Y); fe_mul(s.e, P.X, t);       // 2XY
+    fe_add(s.f, zz, dtt);
+    fe_add(s.g, yy, xx);
+    fe_sub(s.h, zz, dtt);
+    fe_mul(s.eg, s.e, s.g);
+    fe_mul(s.fh, s.f, s.h);
+    fe_mul(efgh, s.eg, s.fh);
+}
+
+// inv = 1 / (eg * fh), or 0 when that product is 0 (2Q in the identity coset: the encoding is all zeros)
+EG_HD void ge_dc_finish(uint32_t w[8], const ge_dc_state &s, const fe &inv) {
+    fe zinv, tinv, t, e, g, h, magic, s_out;
+    fe_mul(zinv, s.eg, inv);
+    fe_mul(tinv, s.fh, inv);
+    fe_mul(t, s.eg, zinv);
+    const bool rot = fe_isneg(t);
+    fe ne, fi;
+    fe_neg(ne, s.e);
+    fe_mul(fi, s.f, fe_const_sqrtm1());
+    fe_select(e, s.e, s.g, rot);
+    fe_select(g, s.g, ne, rot);
+    fe_select(h, s.h, fi, rot);
+    fe_select(magic, fe_const_invsqrt_a_minus_d(), fe_const_sqrtm1(), rot);
+    fe_mul(t, h, e); fe_mul(t, t, zinv);
+    fe_cneg(g, g, fe_isneg(t));
+    fe_mul(t, g, tinv); fe_mul(t, magic, t);
+    fe hg;
+    fe_sub(hg, h, g);
+    fe_mul(s_out, hg, t);
+    fe_abs(s_out, s_out);
+    fe_towords(w, s_out);
+}
+
+// w0 = encode(2 Q0), w1 = encode(2 Q1)
+static EG_HD_NOINLINE void ge_double_compress2(uint32_t w0[8], uint32_t w1[8], const ge_ext &Q0, const ge_ext &Q1) {
+    ge_dc_state s0, s1;
+    fe t0, t1, u0, u1, p, ip, i0, i1;
+    ge_dc_prepare(s0, t0, Q0);
+    ge_dc_prepare(s1, t1, Q1);
+    const bool z0 = fe_iszero(t0), z1 = fe_iszero(t1);
+    fe_select(u0, t0, fe_one(), z0);
+    fe_select(u1, t1, fe_one(), z1);
+    fe_mul(p, u0, u1);
+    fe_invert(ip, p);
+    fe_mul(i0, ip, u1);
+    fe_mul(i1, ip, u0);
+    fe_select(i0, i0, fe_zero(), z0);
+    fe_select(i1, i1, fe_zero(), z1);
+    ge_dc_finish(w0, s0, i0);
+    ge_dc_finish(w1, s1, i1);
+}
+
+EG_HD void ge_double_compress1(uint32_t w[8], const ge_ext &Q) {
+    ge_dc_state s;
+    fe t, u, i;
+    ge_dc_prepare(s, t, Q);
+    const bool z = fe_iszero(t);
+    fe_select(u, t, fe_one(), z);
+    fe_invert(i, u);
+    fe_select(i, i, fe_zero(), z);
+    ge_dc_finish(w, s, i);
+}
+
 // Same chain with run-time term counts (nv <= MAXV, nf <= 2), for the equations that are not of the [a]P + [b]F shape:
 // share verification (two per-item bases), SumOfSquaresProof (G, K and one per-item base; (n+2)-term sums) and
 // Lagrange recombination.  Replaces the general vartime_multi_mul (ristretto.rs:139-146).

@@ -325,6 +325,97 @@ EG_HD void ring_hash_body(const ring_hash_params &P, size_t item, int slot) {
     planar_store_words(P.chal, P.n, s.chal_index, 8, item, c.v);
 }
 
+// ---- v2 ring engine: one thread = one ring of one item, all of its equations (ring.rs:322-366) --------------------
+//
+// R_G(j) = [s_j] G - [e_j] R ; R_K(j) = [s_j] K - [e_j] (B - [a_j] G) = [s_j] K - [e_j] B + [e_j a_j] G with a_j = j * step
+// the admissible value of equation j (PreparedRange::new range.rs:341-355; [O, G] for bool / choice rings).  The window
+// tables of R and B are built once per ring (ge_vtab_build) in a per-thread scratch region and serve every j; the two
+// commitments of an equation are encoded together with one inversion (ge_double_compress2 on the half-scalar points).
+struct ring_params {
+    in_bufs in;
+    size_t n;
+    uint32_t n_rings;
+    uint16_t sizes[EG_MAX_RINGS];           // equations per ring
+    uint16_t starts[EG_MAX_RINGS];          // index of the ring's first response in the proof
+    uint32_t ct_p_index[EG_MAX_RINGS];      // planar point index of R; B at +1
+    uint32_t ct_enc_index[EG_MAX_RINGS];    // planar encoding index of R; B at +1
+    uint64_t adm_step[EG_MAX_RINGS];
+    uint8_t proof_buf;
+    uint32_t proof_offset;                  // e0 | responses
+    uint32_t commit_index0;                 // terminal commitments of ring r -> commit_index0 + 2r, +1
+    transcript prefix;                      // after initialize_transcript (ring.rs:290-293)
+    const uint32_t *pts;
+    const uint32_t *enc;
+    uint32_t *commit;
+    uint32_t *scratch;                      // 2 * EG_VTAB_WORDS words per resident thread
+    const uint32_t *table_g, *table_k;      // 4-chunk fixed tables
+};
+
+// the ring's own transcript: prefix + start_proof("ring_enc") + "enc" + "i"   (ring.rs:325-331)
+static EG_HD_NOINLINE void ring_transcript_start(transcript &rt, const transcript &prefix, const uint32_t enc_ct[16], uint32_t r) {
+    rt = prefix;
+    merlin_append_message(rt, EG_LBL("dom-sep"), (const uint8_t *)"ring_enc", 8);
+    merlin_append_words(rt, EG_LBL("enc"), enc_ct, 16);
+    merlin_append_u64(rt, EG_LBL("i"), r);
+}
+
+// e_{j+1} = H(ring transcript, j, R_G, R_K)   (ring.rs:354-360)
+static EG_HD_NOINLINE void ring_next_challenge(sc &e, const transcript &rt, uint32_t j, const uint32_t cg[8], const uint32_t ck[8]) {
+    transcript t = rt;
+    merlin_append_u64(t, EG_LBL("j"), j);
+    merlin_append_words(t, EG_LBL("R_G"), cg, 8);
+    merlin_append_words(t, EG_LBL("R_K"), ck, 8);
+    merlin_challenge_scalar(t, EG_LBL("c"), e);
+}
+
+EG_HD void ring_body(const ring_params &P, size_t item, uint32_t r, uint32_t *scratch, const uint32_t *tab_g, const uint32_t *tab_k) {
+    uint32_t *tab_r = scratch, *tab_b = scratch + EG_VTAB_WORDS;
+    {
+        ge_ext pt;
+        planar_load_point(pt, P.pts, P.n, P.ct_p_index[r], item);
+        ge_vtab_build(tab_r, pt);
+        planar_load_point(pt, P.pts, P.n, P.ct_p_index[r] + 1, item);
+        ge_vtab_build(tab_b, pt);
+    }
+    const uint8_t *proof = in_ptr(P.in, P.proof_buf, item) + P.proof_offset;
+    uint32_t w[16];
+    sc e;
+    load32_bytes(w, proof);
+    bool ok = sc_from_words(e, w);
+    if (!ok) e = sc_zero();                 // malformed items are flagged by k_scalars; keep the math defined
+    planar_load_words(w, P.enc, P.n, P.ct_enc_index[r], 8, item);
+    planar_load_words(w + 8, P.enc, P.n, P.ct_enc_index[r] + 1, 8, item);
+    const uint32_t *enc_ct = w;
+    const uint32_t size = P.sizes[r];
+    transcript rt;                          // cloned per equation
+    ring_transcript_start(rt, P.prefix, enc_ct, r);
+    uint32_t cg[8], ck[8];
+#pragma unroll 1
+    for (uint32_t j = 0; j < size; j++) {
+        sc s, ne, hs, hne, hea;
+        load32_bytes(w, proof + 32 * (1 + P.starts[r] + j));
+        if (!sc_from_words(s, w)) s = sc_zero();
+        sc_neg(ne, e);
+        sc_half(hs, s);
+        sc_half(hne, ne);
+        ge_ext qg, qk;
+        ge_eval64(qg, tab_r, hne, 1, tab_g, hs, tab_g, hs);
+        const uint64_t a = P.adm_step[r] * (uint64_t)j;
+        if (a != 0) {
+            sc ea;
+            sc_mul(ea, e, sc_from_u64(a));
+            sc_half(hea, ea);
+            ge_eval64(qk, tab_b, hne, 2, tab_k, hs, tab_g, hea);
+        } else {
+            ge_eval64(qk, tab_b, hne, 1, tab_k, hs, tab_k, hs);
+        }
+        ge_double_compress2(cg, ck, qg, qk);
+        if (j + 1 < size) ring_next_challenge(e, rt, j, cg, ck);
+    }
+    planar_store_words(P.commit, P.n, P.commit_index0 + 2 * r, 8, item, cg);
+    planar_store_words(P.commit, P.n, P.commit_index0 + 2 * r + 1, 8, item, ck);
+}
+
 // Outer transcript: absorb every ring's terminal commitments, compare with the common challenge (ring.rs:364-373)
 struct ring_final_params {
     in_bufs in;
@@ -477,7 +568,7 @@ EG_HD void verdict_body(const verdict_params &P, size_t item) {
 
 namespace eg {
 
-// table[k] = (k+1) F in affine Niels form, F given as an encoding; status: 0 ok, 1 undecodable, 2 identity
+// table[c * 128 + k] = (k+1) 2^(64c) F in affine Niels form (c < 4), F given as an encoding; status: 0 ok, 1 undecodable, 2 identity
 EG_HD void build_table_body(int tidx, const uint32_t *enc_words, int use_generator, uint32_t *table, uint32_t *status) {
     ge_ext F;
     bool ok = true;
@@ -489,7 +580,11 @@ EG_HD void build_table_body(int tidx, const uint32_t *enc_words, int use_generat
     }
     if (tidx == 0) *status = !ok ? 1u : (ge_is_identity(F) ? 2u : 0u);
     if (!ok) return;
-    int m = tidx + 1;               // 1..128
+    // entry tidx = (chunk c, multiple m): m * 2^(64 c) * F; the first 128 entries are the plain [1..128] F table
+    const int chunk = tidx / EG_FIXED_TABLE_ENTRIES;
+    int m = tidx % EG_FIXED_TABLE_ENTRIES + 1;               // 1..128
+#pragma unroll 1
+    for (int k = 0; k < 64 * chunk; k++) ge_dbl(F, F);
     ge_ext acc = ge_identity();
 #pragma unroll 1
     for (int bit = 7; bit >= 0; bit--) {

@@ -21,7 +21,7 @@ struct transcript {
 
 EG_HD uint64_t rotl64(uint64_t x, int n) { return (x << n) | (x >> (64 - n)); }
 
-EG_HD void keccak_f1600(uint64_t a[25]) {
+static EG_HD_NOINLINE void keccak_f1600(uint64_t a[25]) {
     const uint64_t RC[24] = {
         0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL,
         0x000000000000808bULL, 0x0000000080000001ULL, 0x8000000080008081ULL, 0x8000000000008009ULL,
@@ -69,7 +69,7 @@ EG_HD void st_xor_byte(transcript &t, uint32_t pos, uint8_t b) { t.st[pos >> 3] 
 EG_HD uint8_t st_get_byte(const transcript &t, uint32_t pos) { return (uint8_t)(t.st[pos >> 3] >> ((pos & 7) * 8)); }
 EG_HD void st_clear_byte(transcript &t, uint32_t pos) { t.st[pos >> 3] &= ~((uint64_t)0xff << ((pos & 7) * 8)); }
 
-EG_HD void strobe_run_f(transcript &t) {
+static EG_HD_NOINLINE void strobe_run_f(transcript &t) {
     st_xor_byte(t, t.pos, (uint8_t)t.pos_begin);
     st_xor_byte(t, t.pos + 1, 0x04);
     st_xor_byte(t, EG_STROBE_R + 1, 0x80);
@@ -77,7 +77,7 @@ EG_HD void strobe_run_f(transcript &t) {
     t.pos = 0; t.pos_begin = 0;
 }
 
-EG_HD void strobe_absorb(transcript &t, const uint8_t *d, uint32_t n) {
+static EG_HD_NOINLINE void strobe_absorb(transcript &t, const uint8_t *d, uint32_t n) {
 #pragma unroll 1
     for (uint32_t i = 0; i < n; i++) {
         st_xor_byte(t, t.pos, d[i]);
@@ -86,7 +86,7 @@ EG_HD void strobe_absorb(transcript &t, const uint8_t *d, uint32_t n) {
 }
 
 // absorb little-endian words (n_bytes multiple of 4): the hot path appends 32-byte elements and u64s
-EG_HD void strobe_absorb_words(transcript &t, const uint32_t *w, uint32_t n_words) {
+static EG_HD_NOINLINE void strobe_absorb_words(transcript &t, const uint32_t *w, uint32_t n_words) {
 #pragma unroll 1
     for (uint32_t i = 0; i < n_words; i++) {
         uint32_t x = w[i];
@@ -98,7 +98,7 @@ EG_HD void strobe_absorb_words(transcript &t, const uint32_t *w, uint32_t n_word
     }
 }
 
-EG_HD void strobe_begin_op(transcript &t, uint8_t flags) {
+static EG_HD_NOINLINE void strobe_begin_op(transcript &t, uint8_t flags) {
     uint8_t hdr[2] = {(uint8_t)t.pos_begin, flags};
     t.pos_begin = t.pos + 1;
     strobe_absorb(t, hdr, 2);
@@ -134,7 +134,7 @@ EG_HD void merlin_append_u64(transcript &t, const char *label, uint32_t label_le
 }
 
 // proofs/mod.rs:54-56 -> ristretto.rs:34-38: 64 challenge bytes, wide-reduced
-EG_HD void merlin_challenge_scalar(transcript &t, const char *label, uint32_t label_len, sc &out) {
+static EG_HD_NOINLINE void merlin_challenge_scalar(transcript &t, const char *label, uint32_t label_len, sc &out) {
     merlin_header(t, label, label_len, 64);
     strobe_begin_op(t, EG_FLAG_PRF);
     uint32_t w[16];

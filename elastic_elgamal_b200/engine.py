@@ -72,6 +72,9 @@ class Engine:
     def set_chunk_items(self, items):
         self._check(self.lib.eg_ctx_set_chunk_items(self.h, items))
 
+    def set_ring_mode(self, mode):
+        self._check(self.lib.eg_ctx_set_ring_mode(self.h, mode))
+
     # ---- PublicKey::from_bytes
     def set_receiver(self, key):
         key = _u8(np.frombuffer(bytes(key), dtype=np.uint8), (32,))
@@ -214,6 +217,9 @@ class Engine:
     # ---- device-pointer variants (ints are raw device addresses, e.g. torch.Tensor.data_ptr())
     def verify_bool_dev(self, n, d_cts, d_proofs, d_verdicts):
         self._check(self.lib.eg_verify_bool_batch_dev(self.h, n, d_cts, d_proofs, d_verdicts))
+
+    def ciphertexts_sum_dev(self, n_parts, n_cts, d_parts, d_out, d_bad=None):
+        self._check(self.lib.eg_ciphertexts_sum_dev(self.h, n_parts, n_cts, d_parts, d_out, d_bad))
 
     def verify_choice_dev(self, n, options, single, d_choices, d_rings, d_sums, d_verdicts, d_tally):
         self._check(self.lib.eg_verify_choice_batch_dev(self.h, n, options, int(single), d_choices, d_rings, d_sums,

@@ -197,6 +197,10 @@ eg_status eg_verify_choice_batch_dev(eg_ctx *ctx, size_t n, uint32_t options, in
 eg_status eg_verify_range_batch_dev(eg_ctx *ctx, const eg_range *range, const char *transcript_label, size_t n,
                                     const uint8_t *d_cts, const uint8_t *d_partial_cts, const uint8_t *d_ring_proofs,
                                     uint8_t *d_verdicts);
+/* eg_ciphertexts_sum on device buffers, asynchronous on the context's stream: the local combine after the all_gather
+ * of per-GPU partial tallies.  *d_bad_flag (optional, device) becomes non-zero when a part does not decode. */
+eg_status eg_ciphertexts_sum_dev(eg_ctx *ctx, size_t n_parts, size_t n_cts, const uint8_t *d_parts, uint8_t *d_out,
+                                 uint32_t *d_bad_flag);
 
 /* ---- instrumentation --------------------------------------------------------------------------- */
 /* Number of kernels this context has launched since creation (bench.py's `gpu_launches`). */
@@ -213,6 +217,10 @@ eg_status eg_last_commit_stats(const eg_ctx *ctx, uint64_t *launches, uint64_t *
 eg_status eg_selftest_field(eg_ctx *ctx, size_t n, uint64_t seed, uint64_t *mismatches);
 /* Tuning knob: items processed per internal chunk (0 = default 262144).  Results do not depend on it. */
 eg_status eg_ctx_set_chunk_items(eg_ctx *ctx, size_t items);
+/* Tuning / A-B knob for RingProof verification: 2 (default) = one thread per ring with per-point chunked window tables
+ * (k_ring, 64 doublings per equation); 1 = one launch per equation index (k_commit + k_ring_hash, 252 doublings).
+ * Results do not depend on it. */
+eg_status eg_ctx_set_ring_mode(eg_ctx *ctx, int mode);
 /* Raw CUDA stream handle (cudaStream_t) so callers can order their own work / time with events on it. */
 void     *eg_ctx_stream(const eg_ctx *ctx);
 

@@ -1,0 +1,41 @@
+"""`-m "not gpu"`: the CUDA C-ABI library builds, loads without a GPU and exports every symbol include/eg_b200.h declares;
+compute entry points fail loudly (EG_ERR_NO_DEVICE) instead of falling back to a CPU path."""
+import ctypes as C
+import pathlib
+import re
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+
+
+def _lib():
+    from elastic_elgamal_b200 import _ffi, build
+    return _ffi, _ffi.load(build.build())
+
+
+def test_exports_every_declared_symbol():
+    _ffi, lib = _lib()
+    header = (ROOT / "include" / "eg_b200.h").read_text()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)          # drop comments
+    names = set(re.findall(r"\b(eg_[a-z0-9_]+)\s*\(", header))
+    assert len(names) > 30
+    missing = [n for n in sorted(names) if not hasattr(lib, n)]
+    assert not missing, missing
+    # the ctypes mirror covers the same set
+    assert names <= set(_ffi.PROTOTYPES), sorted(names - set(_ffi.PROTOTYPES))
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        return
+    _ffi, lib = _lib()
+    h = C.c_void_p()
+    assert lib.eg_ctx_create(0, C.byref(h)) == _ffi.ERR_NO_DEVICE and not h.value
+    assert lib.eg_version().startswith(b"eg_b200")
+
+
+def test_package_never_imports_the_oracle():
+    for f in (ROOT / "elastic_elgamal_b200").rglob("*"):
+        if f.suffix in (".py", ".cu", ".cuh", ".h", ".hpp") and f.is_file():
+            text = f.read_text()
+            assert "import oracle" not in text and "liboracle" not in text and "eg_oracle.h" not in text, f

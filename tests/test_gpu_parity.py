@@ -140,3 +140,15 @@ def test_dlog_table_large(env):
     vals, found = e.combine_decrypt([0, 2], np.frombuffer(b"".join(cts), np.uint8), np.frombuffer(b"".join(b"".join(r) for r in sh), np.uint8), table)
     assert found.tolist() == [1, 1, 1, 0, 1, 1] and [int(v) for v in vals[[0, 1, 2, 4, 5]]] == [0, 1, (1 << 20) - 1, 777777, 123456]
     table.close()
+
+
+def test_ring_mode_1_still_matches(env):
+    """The per-equation launch pipeline (ring mode 1) stays available as an A/B knob and must agree with the oracle."""
+    e, sk, pk = env
+    e.set_ring_mode(1)
+    try:
+        PC.check_verify_bool(e, pk, n=200, seed=5)
+        PC.check_verify_choice(e, pk, options=5, n=200, single=True, frac=0.2)
+        PC.check_verify_range(e, pk, 100, n=60, frac=0.2)
+    finally:
+        e.set_ring_mode(2)
