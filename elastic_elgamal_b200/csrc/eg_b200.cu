@@ -88,6 +88,26 @@ __global__ void __launch_bounds__(EG_RING_THREADS, EG_RING_MINBLOCKS) k_ring(con
         ring_body(P, tid % P.n, (uint32_t)(tid / P.n), scratch, s_rtab, s_rtab + EG_FCHUNK_TABLE_WORDS);
 }
 
+// proving side (encrypt_bool / EncryptedChoice::new): same persistent shape and shared-memory tables as k_ring.
+// PHASE 0: ciphertexts + ring construction, 1: common challenge + sum proof (one thread per item), 2: finalize
+template <int PHASE>
+__global__ void __launch_bounds__(EG_RING_THREADS, EG_RING_MINBLOCKS) k_prove(const prove_params P, uint32_t *scratch_base) {
+    extern __shared__ __align__(16) uint32_t s_rtab[];
+    for (int k = threadIdx.x; k < EG_FCHUNK_TABLE_WORDS; k += blockDim.x) {
+        s_rtab[k] = P.table_g[k];
+        s_rtab[EG_FCHUNK_TABLE_WORDS + k] = P.table_k[k];
+    }
+    __syncthreads();
+    const size_t total = PHASE == 1 ? P.n : P.n * (size_t)P.options, stride = (size_t)gridDim.x * blockDim.x;
+    const size_t slot = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t *scratch = scratch_base + slot * (2 * EG_VTAB_WORDS);
+    for (size_t tid = slot; tid < total; tid += stride) {
+        if (PHASE == 0) prove_ring1_body(P, tid % P.n, (uint32_t)(tid / P.n), scratch, s_rtab, s_rtab + EG_FCHUNK_TABLE_WORDS);
+        if (PHASE == 1) prove_common_body(P, tid, s_rtab, s_rtab + EG_FCHUNK_TABLE_WORDS);
+        if (PHASE == 2) prove_ring2_body(P, tid % P.n, (uint32_t)(tid / P.n), scratch, s_rtab, s_rtab + EG_FCHUNK_TABLE_WORDS);
+    }
+}
+
 __global__ void __launch_bounds__(128) k_ring_hash(const ring_hash_params P) {
     size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= P.n * (size_t)P.n_slots) return;
@@ -337,6 +357,7 @@ struct eg_ctx {
     size_t chunk_items = 0;   // 0 = default
     int ring_mode = 2;        // 2: k_ring (one thread per ring, chunked tables); 1: k_commit / k_ring_hash launches per equation
     int ring_grid = 0;        // resident CTAs of k_ring (queried once)
+    int prove_grid[3] = {0, 0, 0};
     dev_buf ring_scratch;
 };
 
@@ -468,6 +489,43 @@ static eg_status launch_ring(eg_ctx *ctx, ring_params &P) {
     ctx->commit_tasks += sides;
     ctx->call_commit_tasks += sides;
     ctx->call_commit_launches++;
+    return EG_SUCCESS;
+}
+
+#ifndef EG_HOSTSIM
+template <int PHASE>
+static eg_status launch_prove_phase(eg_ctx *ctx, const prove_params &P, int &grid_cache) {
+    const size_t smem = 2 * EG_FCHUNK_TABLE_WORDS * 4;
+    if (grid_cache == 0) {
+        CU(cudaFuncSetAttribute(k_prove<PHASE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0, sms = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_prove<PHASE>, EG_RING_THREADS, smem));
+        CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+        if (per_sm < 1) return fail(ctx, EG_ERR_CUDA, "k_prove does not fit on an SM");
+        grid_cache = per_sm * sms;
+    }
+    const size_t total = PHASE == 1 ? P.n : P.n * (size_t)P.options;
+    const unsigned grid = (unsigned)std::min<size_t>((size_t)grid_cache, (total + EG_RING_THREADS - 1) / EG_RING_THREADS);
+    TRY(ensure(ctx, ctx->ring_scratch, (size_t)grid_cache * EG_RING_THREADS * 2 * EG_VTAB_WORDS * 4));
+    k_prove<PHASE><<<grid, EG_RING_THREADS, smem, ctx->stream>>>(P, (uint32_t *)ctx->ring_scratch.p);
+    ctx->launches++;
+    return EG_SUCCESS;
+}
+#endif
+
+static eg_status launch_prove(eg_ctx *ctx, const prove_params &P) {
+#ifdef EG_HOSTSIM
+    TRY(ensure(ctx, ctx->ring_scratch, 2 * EG_VTAB_WORDS * 4));
+    uint32_t *scratch = (uint32_t *)ctx->ring_scratch.p;
+    EG_FOR_HOST(P.n * (size_t)P.options, prove_ring1_body(P, tid % P.n, (uint32_t)(tid / P.n), scratch, P.table_g, P.table_k))
+    EG_FOR_HOST(P.n, prove_common_body(P, tid, P.table_g, P.table_k))
+    EG_FOR_HOST(P.n * (size_t)P.options, prove_ring2_body(P, tid % P.n, (uint32_t)(tid / P.n), scratch, P.table_g, P.table_k))
+    ctx->launches += 3;
+#else
+    TRY(launch_prove_phase<0>(ctx, P, ctx->prove_grid[0]));
+    TRY(launch_prove_phase<1>(ctx, P, ctx->prove_grid[1]));
+    TRY(launch_prove_phase<2>(ctx, P, ctx->prove_grid[2]));
+#endif
     return EG_SUCCESS;
 }
 
@@ -1284,6 +1342,69 @@ extern "C" eg_status eg_verify_choice_batch(eg_ctx *ctx, size_t n, uint32_t opti
     }
     { float keep = ctx->timings[2]; memcpy(ctx->timings, acc, sizeof acc); ctx->timings[2] = keep; }
     return finish_call(ctx);
+}
+
+// =================================================================== encrypt_bool / EncryptedChoice::new
+
+static eg_status prove_chunk(eg_ctx *ctx, size_t n, uint32_t m, int single, const char *label, uint32_t label_len, const uint8_t *d_values,
+                             const uint8_t *d_wide, uint8_t *d_cts, uint8_t *d_ring, uint8_t *d_sum) {
+    TRY(ensure(ctx, ctx->pts, n * 2 * m * 128));
+    TRY(ensure(ctx, ctx->enc, n * 2 * m * 32));
+    TRY(ensure(ctx, ctx->commit, n * 2 * m * 32));
+    TRY(ensure(ctx, ctx->res_big, n * 2 * m * 32));
+    TRY(ensure(ctx, ctx->chal, n * 32));
+    prove_params P;
+    memset(&P, 0, sizeof P);
+    P.n = n; P.options = m; P.draws = 3 * m + (single ? 1 : 0); P.single = single ? 1 : 0;
+    P.values = d_values; P.wide = d_wide; P.cts = d_cts; P.ring = d_ring; P.sum = d_sum;
+    merlin_new(P.ring_prefix, label, label_len);
+    host_ring_initialize(P.ring_prefix, ctx->key);
+    merlin_new(P.sum_prefix, EG_LBL("choice_encryption_sum"));            // choice.rs:72
+    merlin_append_message(P.sum_prefix, EG_LBL("dom-sep"), (const uint8_t *)"log_eq", 6);
+    merlin_append_message(P.sum_prefix, EG_LBL("K"), ctx->key, 32);
+    P.pts = (uint32_t *)ctx->pts.p; P.enc = (uint32_t *)ctx->enc.p; P.sec = (uint32_t *)ctx->res_big.p;
+    P.commit = (uint32_t *)ctx->commit.p; P.chal = (uint32_t *)ctx->chal.p;
+    P.table_g = ctx->d_table_g; P.table_k = ctx->d_table_k;
+    return launch_prove(ctx, P);
+}
+
+static eg_status prove_batch(eg_ctx *ctx, size_t n, uint32_t m, int single, const char *label, uint32_t label_len, const uint8_t *values,
+                             const uint8_t *wide, uint8_t *cts, uint8_t *ring, uint8_t *sum) {
+    TRY(begin_call(ctx));
+    if (m == 0 || m > EG_MAX_RINGS) return fail(ctx, EG_ERR_INVALID_ARG, "options must be in 1..64");
+    if (n == 0) return EG_SUCCESS;
+    if (!values || !wide || !cts || !ring || (single && !sum)) return fail(ctx, EG_ERR_INVALID_ARG, "null pointer");
+    const size_t draws = 3 * (size_t)m + (single ? 1 : 0), ring_stride = 32 * (1 + 2 * (size_t)m);
+    const size_t chunk = std::max<size_t>(1024, default_chunk(ctx) * 5 / m), cm = std::min(chunk, n);
+    // device staging: values | wide in in[0], in[1]; outputs in in[2], in[3], misc
+    TRY(ensure(ctx, ctx->in[0], cm * m));
+    TRY(ensure(ctx, ctx->in[1], cm * draws * 64));
+    TRY(ensure(ctx, ctx->in[2], cm * m * 64));
+    TRY(ensure(ctx, ctx->in[3], cm * ring_stride));
+    TRY(ensure(ctx, ctx->misc, std::max<size_t>(cm * 64, 4096)));
+    for (size_t off = 0; off < n; off += chunk) {
+        const size_t k = std::min(chunk, n - off);
+        CU(cudaMemcpyAsync(ctx->in[0].p, values + off * m, k * m, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->in[1].p, wide + off * draws * 64, k * draws * 64, cudaMemcpyHostToDevice, ctx->stream));
+        TRY(prove_chunk(ctx, k, m, single, label, label_len, (const uint8_t *)ctx->in[0].p, (const uint8_t *)ctx->in[1].p,
+                        (uint8_t *)ctx->in[2].p, (uint8_t *)ctx->in[3].p, (uint8_t *)ctx->misc.p));
+        CU(cudaMemcpyAsync(cts + off * m * 64, ctx->in[2].p, k * m * 64, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(ring + off * ring_stride, ctx->in[3].p, k * ring_stride, cudaMemcpyDeviceToHost, ctx->stream));
+        if (single) CU(cudaMemcpyAsync(sum + off * 64, ctx->misc.p, k * 64, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    return finish_call(ctx);
+}
+
+extern "C" eg_status eg_encrypt_bool_batch(eg_ctx *ctx, size_t n, const uint8_t *values, const uint8_t *wide_rand, uint8_t *cts,
+                                           uint8_t *proofs) {
+    return prove_batch(ctx, n, 1, 0, EG_LBL("bool_encryption"), values, wide_rand, cts, proofs, nullptr);      // keys/impls.rs:82
+}
+
+extern "C" eg_status eg_encrypt_choice_batch(eg_ctx *ctx, size_t n, uint32_t options, int single, const uint8_t *values,
+                                             const uint8_t *wide_rand, uint8_t *choices, uint8_t *ring_proofs, uint8_t *sum_proofs) {
+    return prove_batch(ctx, n, options, single, EG_LBL("encrypted_choice_ranges"), values, wide_rand, choices, ring_proofs,  // choice.rs:323
+                       sum_proofs);
 }
 
 // =================================================================== group-level helpers

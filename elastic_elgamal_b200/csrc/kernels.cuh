@@ -416,6 +416,203 @@ EG_HD void ring_body(const ring_params &P, size_t item, uint32_t r, uint32_t *sc
     planar_store_words(P.commit, P.n, P.commit_index0 + 2 * r + 1, 8, item, ck);
 }
 
+// ------------------------------------------------------------------ proving side: encrypt_bool / EncryptedChoice::new
+//
+// PublicKey::encrypt_bool (keys/impls.rs:77-89) and EncryptedChoice::new / ::single (choice.rs:288-349) for rings over
+// the admissible pair [O, G].  Randomness is caller-supplied: item i consumes `draws` 64-byte blocks in the reference's
+// draw order, each reduced as in Ristretto::generate_scalar (ristretto.rs:28-32).  Ring k draws r_k, x_k
+// and -- when its value is 0 -- the forged response s_1 while the rings are added (ring.rs:97-116); after the common
+// challenge, rings whose value is 1 draw the forged s_0 in ring order (ring.rs:170-175); the sum proof nonce comes last.
+// All fixed-base work goes through the 4-chunk tables; every encoding is produced by double-and-compress on the
+// half-scalar point.
+struct prove_params {
+    size_t n;
+    uint32_t options;
+    uint32_t draws;              // 3 * options + single
+    uint8_t single;
+    const uint8_t *values;       // n * options, zero / non-zero
+    const uint8_t *wide;         // n * draws * 64
+    uint8_t *cts;                // n * options * 64
+    uint8_t *ring;               // n * (1 + 2 * options) * 32 : e0 | responses
+    uint8_t *sum;                // n * 64 : c | s
+    transcript ring_prefix;      // Transcript::new(label) + initialize_transcript (ring.rs:290-293)
+    transcript sum_prefix;       // Transcript::new("choice_encryption_sum") + start_proof("log_eq") + "K"
+    uint32_t *pts;               // planar points: R_k at 2k, B_k at 2k+1
+    uint32_t *enc;               // planar encodings of the same
+    uint32_t *sec;               // planar scalars: r_k at 2k, x_k at 2k+1
+    uint32_t *commit;            // planar encodings: terminal commitments of ring k at 2k, 2k+1
+    uint32_t *chal;              // planar scalars: common challenge at 0
+    const uint32_t *table_g, *table_k;
+};
+
+EG_HD void prove_draw(sc &out, const prove_params &P, size_t item, uint32_t pos) {
+    uint32_t w[16];
+    const uint8_t *b = P.wide + (item * P.draws + pos) * 64;
+    load32_bytes(w, b);
+    load32_bytes(w + 8, b + 32);
+    sc_from_wide_words(out, w);
+}
+
+// out0 = encode([k] G), out1 = encode([k] K)
+EG_HD void prove_commit_pair(uint32_t out0[8], uint32_t out1[8], const sc &k, const uint32_t *tab_g, const uint32_t *tab_k) {
+    sc h;
+    sc_half(h, k);
+    ge_ext q0, q1;
+    ge_eval64(q0, nullptr, h, 1, tab_g, h, tab_g, h);
+    ge_eval64(q1, nullptr, h, 1, tab_k, h, tab_k, h);
+    ge_double_compress2(out0, out1, q0, q1);
+}
+
+// forged equation j (value a_j in {0, 1}) of a ring with challenge e and response s:
+// ([s]G - [e]R, [s]K - [e](B - [a]G)), encoded
+EG_HD void prove_forge_pair(uint32_t cg[8], uint32_t ck[8], const ge_ext &R, const ge_ext &B, const sc &e, const sc &s, uint32_t a,
+                            uint32_t *scratch, const uint32_t *tab_g, const uint32_t *tab_k) {
+    uint32_t *tab_r = scratch, *tab_b = scratch + EG_VTAB_WORDS;
+    ge_vtab_build(tab_r, R);
+    ge_vtab_build(tab_b, B);
+    sc ne, hne, hs, hea;
+    sc_neg(ne, e);
+    sc_half(hne, ne);
+    sc_half(hs, s);
+    ge_ext qg, qk;
+    ge_eval64(qg, tab_r, hne, 1, tab_g, hs, tab_g, hs);
+    if (a) {
+        sc ea;
+        sc_mul(ea, e, sc_from_u64(a));
+        sc_half(hea, ea);
+        ge_eval64(qk, tab_b, hne, 2, tab_k, hs, tab_g, hea);
+    } else {
+        ge_eval64(qk, tab_b, hne, 1, tab_k, hs, tab_k, hs);
+    }
+    ge_double_compress2(cg, ck, qg, qk);
+}
+
+// phase 1, one thread per (item, ring k): ciphertext, nonce commitments, forged equation 1 when the value is 0
+EG_HD void prove_ring1_body(const prove_params &P, size_t item, uint32_t k, uint32_t *scratch, const uint32_t *tab_g, const uint32_t *tab_k) {
+    const uint8_t *vals = P.values + item * P.options;
+    uint32_t pos = 0;
+    for (uint32_t i = 0; i < k; i++) pos += 2 + (vals[i] ? 0 : 1);
+    const bool v = vals[k] != 0;
+    sc r, x, hr;
+    prove_draw(r, P, item, pos);
+    prove_draw(x, P, item, pos + 1);
+    sc_half(hr, r);
+    // ExtendedCiphertext::new (encryption.rs:310-327): R = [r]G, B = [v]G + [r]K
+    ge_ext qr, qb, R, B;
+    sc hone;
+    sc_half(hone, sc_from_u64(1));
+    ge_eval64(qr, nullptr, hr, 1, tab_g, hr, tab_g, hr);
+    ge_eval64(qb, nullptr, hr, v ? 2 : 1, tab_k, hr, tab_g, hone);
+    uint32_t enc_ct[16];
+    ge_double_compress2(enc_ct, enc_ct + 8, qr, qb);
+    ge_dbl(R, qr);
+    ge_dbl(B, qb);
+    uint8_t *ct_out = P.cts + (item * P.options + k) * 64;
+    store32_bytes(ct_out, enc_ct);
+    store32_bytes(ct_out + 32, enc_ct + 8);
+    planar_store_words(P.enc, P.n, 2 * k, 8, item, enc_ct);
+    planar_store_words(P.enc, P.n, 2 * k + 1, 8, item, enc_ct + 8);
+    planar_store_point(P.pts, P.n, 2 * k, item, R);
+    planar_store_point(P.pts, P.n, 2 * k + 1, item, B);
+    planar_store_words(P.sec, P.n, 2 * k, 8, item, r.v);
+    planar_store_words(P.sec, P.n, 2 * k + 1, 8, item, x.v);
+    // Ring::new (ring.rs:54-131): commitments of the real equation, then the forged ones above it
+    uint32_t cg[8], ck[8];
+    prove_commit_pair(cg, ck, x, tab_g, tab_k);
+    if (!v) {
+        transcript rt;
+        ring_transcript_start(rt, P.ring_prefix, enc_ct, k);
+        sc e1, s1;
+        ring_next_challenge(e1, rt, 0, cg, ck);
+        prove_draw(s1, P, item, pos + 2);
+        store32_bytes(P.ring + (item * (1 + 2 * (size_t)P.options) + 1 + 2 * k + 1) * 32, s1.v);
+        prove_forge_pair(cg, ck, R, B, e1, s1, 1, scratch, tab_g, tab_k);
+    }
+    planar_store_words(P.commit, P.n, 2 * k, 8, item, cg);
+    planar_store_words(P.commit, P.n, 2 * k + 1, 8, item, ck);
+}
+
+// middle, one thread per item: common challenge (Ring::aggregate ring.rs:138-160) and the sum proof (choice.rs:58-75)
+EG_HD void prove_common_body(const prove_params &P, size_t item, const uint32_t *tab_g, const uint32_t *tab_k) {
+    transcript t = P.ring_prefix;
+    uint32_t w[8], w2[8];
+#pragma unroll 1
+    for (uint32_t k = 0; k < P.options; k++) {
+        planar_load_words(w, P.commit, P.n, 2 * k, 8, item);
+        merlin_append_words(t, EG_LBL("R_G"), w, 8);
+        planar_load_words(w, P.commit, P.n, 2 * k + 1, 8, item);
+        merlin_append_words(t, EG_LBL("R_K"), w, 8);
+    }
+    sc e0;
+    merlin_challenge_scalar(t, EG_LBL("c"), e0);
+    planar_store_words(P.chal, P.n, 0, 8, item, e0.v);
+    store32_bytes(P.ring + item * (1 + 2 * (size_t)P.options) * 32, e0.v);
+    if (!P.single) return;
+    // sum ciphertext = ([sum r]G, [sum v]G + [sum r]K); powers (sum R, sum B - G)
+    const uint8_t *vals = P.values + item * P.options;
+    sc sum_r = sc_zero(), r, vm1;
+    uint64_t nv = 0;
+#pragma unroll 1
+    for (uint32_t k = 0; k < P.options; k++) {
+        planar_load_words(r.v, P.sec, P.n, 2 * k, 8, item);
+        sc_add(sum_r, sum_r, r);
+        nv += vals[k] ? 1 : 0;
+    }
+    sc_sub(vm1, sc_from_u64(nv), sc_from_u64(1));
+    sc hr, hv, x;
+    sc_half(hr, sum_r);
+    sc_half(hv, vm1);
+    ge_ext q0, q1;
+    ge_eval64(q0, nullptr, hr, 1, tab_g, hr, tab_g, hr);
+    ge_eval64(q1, nullptr, hr, 2, tab_k, hr, tab_g, hv);
+    ge_double_compress2(w, w2, q0, q1);
+    transcript st = P.sum_prefix;
+    merlin_append_words(st, EG_LBL("[r]G"), w, 8);
+    merlin_append_words(st, EG_LBL("[r]K"), w2, 8);
+    prove_draw(x, P, item, 3 * P.options);
+    prove_commit_pair(w, w2, x, tab_g, tab_k);
+    merlin_append_words(st, EG_LBL("[x]G"), w, 8);
+    merlin_append_words(st, EG_LBL("[x]K"), w2, 8);
+    sc c, s;
+    merlin_challenge_scalar(st, EG_LBL("c"), c);
+    sc_muladd(s, c, sum_r, x);
+    store32_bytes(P.sum + item * 64, c.v);
+    store32_bytes(P.sum + item * 64 + 32, s.v);
+}
+
+// phase 2, one thread per (item, ring k): Ring::finalize (ring.rs:162-195)
+EG_HD void prove_ring2_body(const prove_params &P, size_t item, uint32_t k, uint32_t *scratch, const uint32_t *tab_g, const uint32_t *tab_k) {
+    const uint8_t *vals = P.values + item * P.options;
+    const bool v = vals[k] != 0;
+    sc e0, r, x, s;
+    planar_load_words(e0.v, P.chal, P.n, 0, 8, item);
+    planar_load_words(r.v, P.sec, P.n, 2 * k, 8, item);
+    planar_load_words(x.v, P.sec, P.n, 2 * k + 1, 8, item);
+    uint8_t *resp = P.ring + (item * (1 + 2 * (size_t)P.options) + 1 + 2 * k) * 32;
+    if (!v) {
+        sc_muladd(s, e0, r, x);
+        store32_bytes(resp, s.v);
+        return;
+    }
+    uint32_t pos = 0, before = 0;
+    for (uint32_t i = 0; i < P.options; i++) { pos += 2 + (vals[i] ? 0 : 1); if (i < k && vals[i]) before++; }
+    sc s0, e1;
+    prove_draw(s0, P, item, pos + before);
+    store32_bytes(resp, s0.v);
+    ge_ext R, B;
+    planar_load_point(R, P.pts, P.n, 2 * k, item);
+    planar_load_point(B, P.pts, P.n, 2 * k + 1, item);
+    uint32_t cg[8], ck[8], enc_ct[16];
+    prove_forge_pair(cg, ck, R, B, e0, s0, 0, scratch, tab_g, tab_k);
+    planar_load_words(enc_ct, P.enc, P.n, 2 * k, 8, item);
+    planar_load_words(enc_ct + 8, P.enc, P.n, 2 * k + 1, 8, item);
+    transcript rt;
+    ring_transcript_start(rt, P.ring_prefix, enc_ct, k);
+    ring_next_challenge(e1, rt, 0, cg, ck);
+    sc_muladd(s, e1, r, x);
+    store32_bytes(resp + 32, s.v);
+}
+
 // Outer transcript: absorb every ring's terminal commitments, compare with the common challenge (ring.rs:364-373)
 struct ring_final_params {
     in_bufs in;

@@ -150,6 +150,26 @@ class Engine:
                                                     _addr(sums) if single else None, _addr(v), _addr(t)))
         return v, t
 
+    # ---- encryption side (randomness supplied by the caller as 64-byte blocks in the reference's draw order)
+    def encrypt_bool(self, values, wide_rand):
+        values = _u8(values, (-1,))
+        n = values.shape[0]
+        wide_rand = _u8(wide_rand, (n, 3, 64))
+        cts, proofs = np.empty((n, 64), np.uint8), np.empty((n, 96), np.uint8)
+        self._check(self.lib.eg_encrypt_bool_batch(self.h, n, _addr(values), _addr(wide_rand), _addr(cts), _addr(proofs)))
+        return cts, proofs
+
+    def encrypt_choice(self, options, values, wide_rand, single=True):
+        values = _u8(values, (-1, options))
+        n = values.shape[0]
+        draws = 3 * options + (1 if single else 0)
+        wide_rand = _u8(wide_rand, (n, draws, 64))
+        cts, rings = np.empty((n, options, 64), np.uint8), np.empty((n, 1 + 2 * options, 32), np.uint8)
+        sums = np.empty((n, 64), np.uint8) if single else None
+        self._check(self.lib.eg_encrypt_choice_batch(self.h, n, options, int(single), _addr(values), _addr(wide_rand), _addr(cts),
+                                                     _addr(rings), _addr(sums)))
+        return cts, rings, sums
+
     # ---- RangeDecomposition / RangeProof
     def range_optimal(self, upper_bound):
         r = _ffi.Range()

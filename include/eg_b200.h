@@ -177,17 +177,21 @@ eg_status eg_combine_decrypt_batch(eg_ctx *ctx, uint32_t threshold, const uint32
                                    const uint8_t *cts /* n_tallies*64 */, const uint8_t *shares,
                                    const eg_dlog_table *table, uint64_t *values /* n */, uint8_t *found /* n */);
 
-/* ---- encryption side (synthetic workload generation and encrypt_* drop-ins) -------------------- */
+/* ---- encryption side (encrypt_* drop-ins with caller-supplied randomness) ----------------------- */
 
-/* PublicKey::encrypt_bool (src/keys/impls.rs:77-89) with caller-supplied randomness: item i consumes
- * three 64-byte blocks in the reference's draw order: r, x, s_forged. */
+/* PublicKey::encrypt_bool (src/keys/impls.rs:77-89).  The reference draws from a CryptoRng; here the caller supplies the
+ * randomness: item i consumes three 64-byte blocks in the reference's draw order (r, x, forged
+ * response), each reduced mod l as Ristretto::generate_scalar does (src/group/ristretto.rs:28-32).  With blocks taken
+ * from the same ChaCha20 stream the outputs are byte-identical to the reference's.  values[i] != 0 encrypts `true`. */
 eg_status eg_encrypt_bool_batch(eg_ctx *ctx, size_t n, const uint8_t *values /* n */, const uint8_t *wide_rand /* n*3*64 */,
                                 uint8_t *cts /* n*64 */, uint8_t *proofs /* n*96 */);
-/* EncryptedChoice::single (src/app/choice.rs:288-303): item i consumes 3*options + 1 blocks (r, x, forged s per
- * option in option order; then the sum-proof nonce). */
-eg_status eg_encrypt_choice_batch(eg_ctx *ctx, size_t n, uint32_t options, const uint32_t *choice /* n */,
-                                  const uint8_t *wide_rand /* n*(3*options+1)*64 */, uint8_t *choices,
-                                  uint8_t *ring_proofs, uint8_t *sum_proofs);
+/* EncryptedChoice::new / ::single (src/app/choice.rs:288-349): values[i*options + k] != 0 marks option k of ballot i
+ * (exactly one for `single`); item i consumes 3*options (+1 for the sum proof when `single`) blocks: r, x and -- for a
+ * zero option -- the forged response per option in option order, then the forged responses of the chosen options,
+ * then the sum-proof nonce.  sum_proofs may be NULL when single == 0. */
+eg_status eg_encrypt_choice_batch(eg_ctx *ctx, size_t n, uint32_t options, int single, const uint8_t *values /* n*options */,
+                                  const uint8_t *wide_rand /* n*(3*options+single)*64 */, uint8_t *choices /* n*options*64 */,
+                                  uint8_t *ring_proofs /* n*(1+2*options)*32 */, uint8_t *sum_proofs /* n*64 */);
 
 /* ---- device-pointer variants (inputs already resident in HBM; same semantics) ------------------- */
 eg_status eg_verify_bool_batch_dev(eg_ctx *ctx, size_t n, const uint8_t *d_cts, const uint8_t *d_proofs, uint8_t *d_verdicts);

@@ -301,3 +301,93 @@ def check_shares_and_decrypt(e, n=10, shares=5, threshold=3, used=(0, 2, 4), tab
             assert found[i] == 1 and int(vals[i]) == ov
     assert found[0] == 1 and vals[0] == 0 and found[1] == 1 and vals[1] == table_hi - 1 and found[2] == 0
     table.close()
+
+
+def item_blocks(seed, index, count):
+    """`count` 64-byte keystream blocks of item `index`'s ChaCha20 stream (block counter = index << 20)."""
+    rng = O.rng_from_seed(seed, first_block=index << 20)
+    return b"".join(O.rng_block(rng) for _ in range(count))
+
+
+def check_encrypt_bool(e, pk, n=16, seed=W.SEED_CHOICE):
+    """eg_encrypt_bool_batch fed with the oracle's per-item ChaCha20 blocks reproduces encrypt_bool byte for byte."""
+    ocs, ops = O.gen_bool_batch(pk, seed, n)
+    values = np.array([i & 1 for i in range(n)], np.uint8)
+    wide = np.frombuffer(b"".join(item_blocks(seed, i, 3) for i in range(n)), np.uint8)
+    cts, proofs = e.encrypt_bool(values, wide)
+    assert (cts == ocs).all() and (proofs == ops).all()
+    assert (e.verify_bool(cts, proofs) == 0).all()
+
+
+def check_encrypt_choice(e, pk, options=5, n=12, seed=W.SEED_CHOICE):
+    ocs, ors, oss = O.gen_choice_batch(pk, options, seed, n)
+    values = np.zeros((n, options), np.uint8)
+    for i in range(n):
+        values[i, i % options] = 1
+    wide = np.frombuffer(b"".join(item_blocks(seed, i, 3 * options + 1) for i in range(n)), np.uint8)
+    cts, rings, sums = e.encrypt_choice(options, values, wide, single=True)
+    assert (cts == ocs).all() and (rings == ors).all() and (sums == oss).all()
+    v, _ = e.verify_choice(options, cts, rings, sums)
+    assert (v == 0).all()
+
+
+def check_encrypt_multi_choice(e, pk, options=4, n=10, seed=b"\x09" * 32):
+    """EncryptedChoice::new with MultiChoice (choice.rs:313-349): any 0/1 pattern, no sum proof."""
+    rnd = random.Random(17)
+    values = np.array([[rnd.randrange(2) for _ in range(options)] for _ in range(n)], np.uint8)
+    values[0, :] = 0
+    values[1, :] = 1
+    exp_c, exp_r = [], []
+    for i in range(n):
+        rng = O.rng_from_seed(seed, first_block=i << 20)
+        c, r, _ = O.choice_new(pk, [bool(x) for x in values[i]], False, rng)
+        exp_c.append(c); exp_r.append(r)
+    wide = np.frombuffer(b"".join(item_blocks(seed, i, 3 * options) for i in range(n)), np.uint8)
+    cts, rings, sums = e.encrypt_choice(options, values, wide, single=False)
+    assert sums is None
+    assert cts.tobytes() == b"".join(exp_c) and rings.tobytes() == b"".join(exp_r)
+    v, _ = e.verify_choice(options, cts, rings, None, single=False)
+    assert (v == 0).all()
+
+
+def check_encrypt_against_reference_snapshots(e):
+    """The engine's prover, fed with the ChaCha20 blocks of `ChaChaRng::seed_from_u64(12345)`, regenerates the
+    reference's own golden snapshots (tests/snapshots.rs:73-130: bool-encryption, encrypted-choice,
+    encrypted-multi-choice) byte for byte, and the engine's verifier accepts them."""
+    import json
+    import pathlib
+    gold = json.loads((pathlib.Path(__file__).parent / "golden" / "ristretto_snapshots.json").read_text())
+    H = bytes.fromhex
+
+    def fresh(blocks):
+        rng = O.rng_from_u64(12345)
+        sk, pk = O.keypair(rng)                      # snapshots.rs:32-33: the first draw is the secret key
+        return pk, np.frombuffer(b"".join(O.rng_block(rng) for _ in range(blocks)), np.uint8)
+
+    def ctb(d):
+        return H(d["random_element"]) + H(d["blinded_element"])
+
+    try:
+        pk, wide = fresh(3)
+        e.set_receiver(pk)
+        cts, proofs = e.encrypt_bool(np.array([1], np.uint8), wide)
+        g = gold["bool-encryption"]
+        assert cts.tobytes() == ctb(g["ciphertext"]) and proofs.tobytes() == H(gold["bool-encryption-bin"])
+        assert e.verify_bool(cts, proofs).tolist() == [0]
+
+        pk, wide = fresh(16)
+        cts, rings, sums = e.encrypt_choice(5, np.array([[0, 0, 0, 1, 0]], np.uint8), wide, single=True)
+        g = gold["encrypted-choice"]
+        assert cts.tobytes() == b"".join(ctb(c) for c in g["choices"])
+        assert rings.tobytes() == H(g["range_proof"]["common_challenge"]) + b"".join(H(x) for x in g["range_proof"]["ring_responses"])
+        assert sums.tobytes() == H(g["sum_proof"]["challenge"]) + H(g["sum_proof"]["response"])
+        assert e.verify_choice(5, cts, rings, sums)[0].tolist() == [0]
+
+        pk, wide = fresh(15)
+        cts, rings, sums = e.encrypt_choice(5, np.array([[0, 1, 1, 0, 1]], np.uint8), wide, single=False)
+        g = gold["encrypted-multi-choice"]
+        assert cts.tobytes() == b"".join(ctb(c) for c in g["choices"])
+        assert rings.tobytes() == H(g["range_proof"]["common_challenge"]) + b"".join(H(x) for x in g["range_proof"]["ring_responses"])
+        assert e.verify_choice(5, cts, rings, None, single=False)[0].tolist() == [0]
+    finally:
+        e.set_receiver(W.receiver()[1])

@@ -152,3 +152,33 @@ def test_ring_mode_1_still_matches(env):
         PC.check_verify_range(e, pk, 100, n=60, frac=0.2)
     finally:
         e.set_ring_mode(2)
+
+
+def test_encrypt_bool_config1_shape(env):
+    PC.check_encrypt_bool(env[0], env[2], n=500)
+
+
+def test_encrypt_choice(env):
+    PC.check_encrypt_choice(env[0], env[2], options=5, n=300)
+    PC.check_encrypt_choice(env[0], env[2], options=2, n=50)
+    PC.check_encrypt_multi_choice(env[0], env[2], options=6, n=100)
+
+
+def test_encrypt_reference_snapshots(env):
+    PC.check_encrypt_against_reference_snapshots(env[0])
+
+
+def test_encrypt_verify_round_trip_large(env):
+    """Size-independent property at a size the oracle does not check item by item: everything the GPU prover emits from
+    arbitrary randomness is accepted by the GPU verifier, and the tally decrypts to the per-option counts."""
+    e, sk, pk = env
+    n, m = 20000, 5
+    rs = np.random.RandomState(3)
+    values = np.zeros((n, m), np.uint8)
+    values[np.arange(n), rs.randint(0, m, n)] = 1
+    wide = rs.randint(0, 256, (n, 3 * m + 1, 64)).astype(np.uint8)
+    cts, rings, sums = e.encrypt_choice(m, values, wide, single=True)
+    v, t = e.verify_choice(m, cts, rings, sums)
+    assert (v == 0).all()
+    table = O.DlogTable(0, n + 1)
+    assert [table.get(O.decrypt_to_element(sk, bytes(t[k]))) for k in range(m)] == values.sum(axis=0).tolist()

@@ -88,3 +88,16 @@ def test_verify_qv_other_shape(env):
 
 def test_shares_and_decrypt(env):
     PC.check_shares_and_decrypt(env[0], n=8)
+
+
+def test_encrypt_bool(env):
+    PC.check_encrypt_bool(env[0], env[2], n=6)
+
+
+def test_encrypt_choice(env):
+    PC.check_encrypt_choice(env[0], env[2], options=3, n=5)
+    PC.check_encrypt_multi_choice(env[0], env[2], options=3, n=4)
+
+
+def test_encrypt_reference_snapshots(env):
+    PC.check_encrypt_against_reference_snapshots(env[0])
