@@ -1,5 +1,6 @@
 """ctypes declarations for include/eg_b200.h (the C ABI of libeg_b200.so)."""
 import ctypes as C
+import os
 import pathlib
 
 PKG = pathlib.Path(__file__).resolve().parent
@@ -81,7 +82,8 @@ PROTOTYPES = {
 
 def load(path=None):
     """Loads the C-ABI library.  Fails loudly when it has not been built: there is no fallback."""
-    path = pathlib.Path(path) if path else DEFAULT_LIB
+    # EG_B200_LIB selects another build of the same CUDA library (A/B tuning runs); there is still no CPU fallback
+    path = pathlib.Path(path) if path else pathlib.Path(os.environ.get("EG_B200_LIB", DEFAULT_LIB))
     if not path.exists():
         raise RuntimeError(f"{path} is missing: build it with `python -m elastic_elgamal_b200.build` "
                            "(the engine has no CPU fallback)")

@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(256) k_scalars(const scalars_params P) {
 
 // The hot kernel.  Both 12 KB fixed-base tables are staged in shared memory once per CTA.
 __global__ void __launch_bounds__(EG_COMMIT_THREADS, EG_COMMIT_MINBLOCKS) k_commit(const commit_params P) {
-    __shared__ uint32_t s_tab[2 * EG_FIXED_TABLE_WORDS];
+    __shared__ __align__(16) uint32_t s_tab[2 * EG_FIXED_TABLE_WORDS];
     for (int k = threadIdx.x; k < EG_FIXED_TABLE_WORDS; k += blockDim.x) {
         s_tab[k] = P.table_g[k];
         s_tab[EG_FIXED_TABLE_WORDS + k] = P.table_k[k];
@@ -251,7 +251,7 @@ __global__ void k_ciphertexts_sum(const uint8_t *parts, size_t n_parts, size_t n
 
 // general multi-scalar equations (share proofs, SumOfSquaresProof, Lagrange recombination)
 __global__ void __launch_bounds__(128) k_msm(const msm_params P) {
-    __shared__ uint32_t s_tab[2 * EG_FIXED_TABLE_WORDS];
+    __shared__ __align__(16) uint32_t s_tab[2 * EG_FIXED_TABLE_WORDS];
     for (int k = threadIdx.x; k < EG_FIXED_TABLE_WORDS; k += blockDim.x) {
         s_tab[k] = P.table_g[k];
         s_tab[EG_FIXED_TABLE_WORDS + k] = P.table_k[k];

@@ -30,21 +30,50 @@ EG_HD ge_ext ge_generator() {
     return r;
 }
 
+// Field multiply / square policies for the point formulas below.  `fe_ops_call` goes through the non-inlined
+// fe_mul / fe_sq (compact code: setup, encodings, cold paths); `fe_ops_inline` expands the tuned PTX sequence in place and
+// is used only inside the three hot point operations (ge_hot_*), which are themselves non-inlined: the hot code stays
+// ~50 KB (instruction cache) and the by-value call ABI's register moves -- which ptxas issues as IMAD.MOV on the same
+// pipe as the multiplier -- disappear from the inner loops.
+struct fe_ops_call {
+    static EG_HD void mul(fe &r, const fe &a, const fe &b) { fe_mul(r, a, b); }
+    static EG_HD void sq(fe &r, const fe &a) { fe_sq(r, a); }
+};
+struct fe_ops_inline {
+    static EG_HD void mul(fe &r, const fe &a, const fe &b) {
+#if defined(__CUDA_ARCH__) && !defined(EG_PORTABLE_FE)
+        fe_mul_ptx(r, a, b);
+#else
+        fe_mul_portable(r, a, b);
+#endif
+    }
+    static EG_HD void sq(fe &r, const fe &a) {
+#if defined(__CUDA_ARCH__) && !defined(EG_PORTABLE_FE)
+        fe_sq_ptx(r, a);
+#else
+        fe_sq_portable(r, a);
+#endif
+    }
+};
+
+template <class O = fe_ops_call>
 EG_HD void ge_p1p1_to_ext(ge_ext &r, const ge_p1p1 &p) {
-    fe_mul(r.X, p.E, p.F); fe_mul(r.Y, p.G, p.H); fe_mul(r.Z, p.F, p.G); fe_mul(r.T, p.E, p.H);
+    O::mul(r.X, p.E, p.F); O::mul(r.Y, p.G, p.H); O::mul(r.Z, p.F, p.G); O::mul(r.T, p.E, p.H);
 }
 
 // projective only (T left stale): enough when a doubling follows
+template <class O = fe_ops_call>
 EG_HD void ge_p1p1_to_proj(ge_ext &r, const ge_p1p1 &p) {
-    fe_mul(r.X, p.E, p.F); fe_mul(r.Y, p.G, p.H); fe_mul(r.Z, p.F, p.G);
+    O::mul(r.X, p.E, p.F); O::mul(r.Y, p.G, p.H); O::mul(r.Z, p.F, p.G);
 }
 
 // dbl-2008-hwcd; reads X, Y, Z only
+template <class O = fe_ops_call>
 EG_HD void ge_dbl_p1p1(ge_p1p1 &r, const ge_ext &p) {
     fe a, b, c, t;
-    fe_sq(a, p.X); fe_sq(b, p.Y);
-    fe_sq(c, p.Z); fe_add(c, c, c);
-    fe_add(t, p.X, p.Y); fe_sq(t, t);
+    O::sq(a, p.X); O::sq(b, p.Y);
+    O::sq(c, p.Z); fe_add(c, c, c);
+    fe_add(t, p.X, p.Y); O::sq(t, t);
     fe_add(r.H, a, b);              // A + B
     fe_sub(r.E, t, r.H);            // E = (X+Y)^2 - A - B
     fe_sub(r.G, b, a);              // G = B - A
@@ -57,13 +86,14 @@ EG_HD void ge_to_cached(ge_cached &c, const ge_ext &p) {
 }
 
 // add-2008-hwcd-3 with a cached second operand; neg subtracts it
+template <class O = fe_ops_call>
 EG_HD void ge_add_cached_p1p1(ge_p1p1 &r, const ge_ext &p, const ge_cached &q, bool neg) {
     fe a, b, c, d, pm, pp;
     fe_sub(a, p.Y, p.X); fe_add(b, p.Y, p.X);
     fe_select(pm, q.YmX, q.YpX, neg); fe_select(pp, q.YpX, q.YmX, neg);
-    fe_mul(a, a, pm); fe_mul(b, b, pp);
-    fe_mul(c, p.T, q.T2d);
-    fe_mul(d, p.Z, q.Z); fe_add(d, d, d);
+    O::mul(a, a, pm); O::mul(b, b, pp);
+    O::mul(c, p.T, q.T2d);
+    O::mul(d, p.Z, q.Z); fe_add(d, d, d);
     fe_sub(r.E, b, a); fe_add(r.H, b, a);
     fe nf, ng;
     fe_sub(nf, d, c); fe_add(ng, d, c);
@@ -71,12 +101,13 @@ EG_HD void ge_add_cached_p1p1(ge_p1p1 &r, const ge_ext &p, const ge_cached &q, b
 }
 
 // mixed addition with an affine Niels operand (Z2 = 1)
+template <class O = fe_ops_call>
 EG_HD void ge_add_niels_p1p1(ge_p1p1 &r, const ge_ext &p, const ge_niels &q, bool neg) {
     fe a, b, c, d, pm, pp;
     fe_sub(a, p.Y, p.X); fe_add(b, p.Y, p.X);
     fe_select(pm, q.ymx, q.ypx, neg); fe_select(pp, q.ypx, q.ymx, neg);
-    fe_mul(a, a, pm); fe_mul(b, b, pp);
-    fe_mul(c, p.T, q.xy2d);
+    O::mul(a, a, pm); O::mul(b, b, pp);
+    O::mul(c, p.T, q.xy2d);
     fe_add(d, p.Z, p.Z);
     fe_sub(r.E, b, a); fe_add(r.H, b, a);
     fe nf, ng;
@@ -180,96 +211,20 @@ EG_HD void ge_niels_from_ext(uint32_t out[24], const ge_ext &p) {
     fe_mul(t, x, y); fe_mul(t, t, fe_const_2d()); fe_towords(out + 16, t);
 }
 
-// ------------------------------------------------------------------ scalar recoding
-
-// 4-bit signed windows: a + 0x888...8 so that digit_i = nibble_i - 8 in [-8, 7]  (a < 2^253)
-EG_HD void sc_recode4(uint32_t out[8], const sc &a) {
-    uint64_t c = 0;
-    for (int i = 0; i < 8; i++) { c += (uint64_t)a.v[i] + 0x88888888u; out[i] = (uint32_t)c; c >>= 32; }
+EG_HD void ge_niels_load4(ge_niels &n, const uint32_t *tbl, int idx) {
+#if defined(__CUDA_ARCH__)
+    const uint4 *q = reinterpret_cast<const uint4 *>(tbl + idx * 24);
+    uint4 a;
+    a = q[0]; n.ypx.v[0] = a.x; n.ypx.v[1] = a.y; n.ypx.v[2] = a.z; n.ypx.v[3] = a.w;
+    a = q[1]; n.ypx.v[4] = a.x; n.ypx.v[5] = a.y; n.ypx.v[6] = a.z; n.ypx.v[7] = a.w;
+    a = q[2]; n.ymx.v[0] = a.x; n.ymx.v[1] = a.y; n.ymx.v[2] = a.z; n.ymx.v[3] = a.w;
+    a = q[3]; n.ymx.v[4] = a.x; n.ymx.v[5] = a.y; n.ymx.v[6] = a.z; n.ymx.v[7] = a.w;
+    a = q[4]; n.xy2d.v[0] = a.x; n.xy2d.v[1] = a.y; n.xy2d.v[2] = a.z; n.xy2d.v[3] = a.w;
+    a = q[5]; n.xy2d.v[4] = a.x; n.xy2d.v[5] = a.y; n.xy2d.v[6] = a.z; n.xy2d.v[7] = a.w;
+#else
+    ge_niels_load(n, tbl, idx);
+#endif
 }
-// 8-bit signed windows: a + 0x8080...80, digit_i = byte_i - 128 in [-128, 127]
-EG_HD void sc_recode8(uint32_t out[8], const sc &a) {
-    uint64_t c = 0;
-    for (int i = 0; i < 8; i++) { c += (uint64_t)a.v[i] + 0x80808080u; out[i] = (uint32_t)c; c >>= 32; }
-}
-EG_HD int sc_digit4(const uint32_t r[8], int i) { return (int)((r[i >> 3] >> ((i & 7) * 4)) & 15u) - 8; }
-EG_HD int sc_digit8(const uint32_t r[8], int i) { return (int)((r[i >> 2] >> ((i & 3) * 8)) & 255u) - 128; }
-
-// ------------------------------------------------------------------ the multi-scalar chain
-
-// acc = sum_{v<NV} a_v P_v + sum_{f<NF} b_f F_f
-//   P_v : per-item points (extended), windows of 4 bits over a per-thread table of [1..8]P_v
-//   F_f : fixed bases with 128-entry affine tables (shared or global memory), windows of 8 bits
-// One shared doubling chain of 252 doublings (Straus).  NV, NF are compile-time.
-template <int NV, int NF>
-EG_HD void ge_msm_chain(ge_ext &out, const ge_ext *P, const sc *a, const uint32_t *const *ftab, const sc *b) {
-    ge_cached tbl[NV > 0 ? NV : 1][8];
-    uint32_t ra[NV > 0 ? NV : 1][8];
-    uint32_t rb[NF > 0 ? NF : 1][8];
-#pragma unroll 1
-    for (int v = 0; v < NV; v++) {
-        ge_ext cur = P[v];
-        ge_cached c1;
-        ge_to_cached(c1, cur);
-        tbl[v][0] = c1;
-#pragma unroll 1
-        for (int k = 1; k < 8; k++) {
-            ge_p1p1 t;
-            ge_add_cached_p1p1(t, cur, c1, false);
-            ge_p1p1_to_ext(cur, t);
-            ge_to_cached(tbl[v][k], cur);
-        }
-        sc_recode4(ra[v], a[v]);
-    }
-    for (int f = 0; f < NF; f++) sc_recode8(rb[f], b[f]);
-
-    ge_ext acc = ge_identity();
-    ge_p1p1 t;
-#pragma unroll 1
-    for (int i = 63; i >= 0; i--) {
-        // acc = 16 acc ; the last doubling also produces T for the additions below
-#pragma unroll 1
-        for (int k = 0; k < 3; k++) { ge_dbl_p1p1(t, acc); ge_p1p1_to_proj(acc, t); }
-        ge_dbl_p1p1(t, acc); ge_p1p1_to_ext(acc, t);
-#pragma unroll 1
-        for (int v = 0; v < NV; v++) {
-            int d = sc_digit4(ra[v], i);
-            if (d != 0) {
-                int m = d < 0 ? -d : d;
-                ge_add_cached_p1p1(t, acc, tbl[v][m - 1], d < 0);
-                ge_p1p1_to_ext(acc, t);
-            }
-        }
-        if ((i & 1) == 0) {
-#pragma unroll 1
-            for (int f = 0; f < NF; f++) {
-                int d = sc_digit8(rb[f], i >> 1);
-                if (d != 0) {
-                    int m = d < 0 ? -d : d;
-                    ge_niels n;
-                    ge_niels_load(n, ftab[f], m - 1);
-                    ge_add_niels_p1p1(t, acc, n, d < 0);
-                    ge_p1p1_to_ext(acc, t);
-                }
-            }
-        }
-    }
-    out = acc;
-}
-
-
-// ------------------------------------------------------------------ chunked tables: 64 doublings per equation
-//
-// A ring proof evaluates several equations on the SAME ciphertext points (one per admissible value, ring.rs:333-361)
-// with different challenges.  Splitting a 253-bit scalar into four 64-bit chunks, a = sum_c 2^(64c) a_c, turns
-// [a]P into sum_c [a_c] P_c with P_c = [2^(64c)] P: the 192 doublings that produce P_1..P_3 (and the four window
-// tables [1..8] P_c) are paid once per point, every equation then needs only 64 shared doublings.  The fixed bases
-// G and K get the same treatment once per context (4 x 128 affine entries each).
-
-#define EG_VCHUNKS 4
-#define EG_VTAB_ENTRY_WORDS 32                                  // one cached point
-#define EG_VTAB_WORDS (EG_VCHUNKS * 8 * EG_VTAB_ENTRY_WORDS)    // 4 KB per point
-#define EG_FCHUNK_TABLE_WORDS (EG_VCHUNKS * EG_FIXED_TABLE_WORDS)   // 48 KB per fixed base
 
 EG_HD void ge_cached_store(uint32_t *e, const ge_cached &c) {
 #if defined(__CUDA_ARCH__)
@@ -300,30 +255,187 @@ EG_HD void ge_cached_load(ge_cached &c, const uint32_t *e) {
 #endif
 }
 
+// ------------------------------------------------------------------ the three hot point operations
+//
+// Every inner loop of the multi-scalar kernels is a sequence of these three calls on an accumulator that lives in the
+// caller's frame.  EG_HOT_OPS selects the field policy inside them: with fe_ops_inline the three bodies are ~58 KB of
+// SASS and, because the warps of a persistent kernel sit in different functions at the same time, overflow the 32 KB
+// L1.5 instruction cache (ncu: `no_instruction` becomes the top stall, profiles/r1_k_ring_hot_inline.txt); fe_ops_call
+// keeps the resident hot set near 20 KB.
+#ifndef EG_HOT_OPS
+#define EG_HOT_OPS fe_ops_call
+#endif
+#ifndef EG_HOT_DBL_OPS
+#define EG_HOT_DBL_OPS EG_HOT_OPS
+#endif
+
+// acc = 2^n acc (n >= 1); intermediate doublings stay projective, T is produced by the last one
+static EG_HD_NOINLINE void ge_hot_dbl(ge_ext &acc, int n) {
+    ge_ext a = acc;
+    ge_p1p1 t;
+#pragma unroll 1
+    for (int k = 0; k < n; k++) {
+        ge_dbl_p1p1<EG_HOT_DBL_OPS>(t, a);
+        ge_p1p1_to_proj<EG_HOT_DBL_OPS>(a, t);
+        if (k == n - 1) EG_HOT_DBL_OPS::mul(a.T, t.E, t.H);
+    }
+    acc = a;
+}
+
+// acc += (neg ? -Q : Q), Q a cached point at `entry` (32 words, 16-byte aligned)
+static EG_HD_NOINLINE void ge_hot_add_cached(ge_ext &acc, const uint32_t *entry, bool neg) {
+    ge_cached q;
+    ge_cached_load(q, entry);
+    ge_p1p1 t;
+    ge_add_cached_p1p1<EG_HOT_OPS>(t, acc, q, neg);
+    ge_p1p1_to_ext<EG_HOT_OPS>(acc, t);
+}
+
+// acc += (neg ? -Q : Q), Q = entry `idx` of an affine Niels table (24 words per entry, 16-byte aligned)
+static EG_HD_NOINLINE void ge_hot_add_niels(ge_ext &acc, const uint32_t *table, int idx, bool neg) {
+    ge_niels q;
+    ge_niels_load4(q, table, idx);
+    ge_p1p1 t;
+    ge_add_niels_p1p1<EG_HOT_OPS>(t, acc, q, neg);
+    ge_p1p1_to_ext<EG_HOT_OPS>(acc, t);
+}
+
+// ------------------------------------------------------------------ scalar recoding
+
+// 4-bit signed windows: a + 0x888...8 so that digit_i = nibble_i - 8 in [-8, 7]  (a < 2^253)
+EG_HD void sc_recode4(uint32_t out[8], const sc &a) {
+    uint64_t c = 0;
+    for (int i = 0; i < 8; i++) { c += (uint64_t)a.v[i] + 0x88888888u; out[i] = (uint32_t)c; c >>= 32; }
+}
+// 8-bit signed windows: a + 0x8080...80, digit_i = byte_i - 128 in [-128, 127]
+EG_HD void sc_recode8(uint32_t out[8], const sc &a) {
+    uint64_t c = 0;
+    for (int i = 0; i < 8; i++) { c += (uint64_t)a.v[i] + 0x80808080u; out[i] = (uint32_t)c; c >>= 32; }
+}
+EG_HD int sc_digit4(const uint32_t r[8], int i) { return (int)((r[i >> 3] >> ((i & 7) * 4)) & 15u) - 8; }
+EG_HD int sc_digit8(const uint32_t r[8], int i) { return (int)((r[i >> 2] >> ((i & 3) * 8)) & 255u) - 128; }
+
+// ------------------------------------------------------------------ the multi-scalar chain
+
+// acc = sum_{v<NV} a_v P_v + sum_{f<NF} b_f F_f
+//   P_v : per-item points (extended), windows of 4 bits over a per-thread table of [1..8]P_v
+//   F_f : fixed bases with 128-entry affine tables (shared or global memory), windows of 8 bits
+// One shared doubling chain of 252 doublings (Straus).  NV, NF are compile-time.
+#if defined(__CUDACC__)
+#define EG_ALIGN16 __align__(16)
+#else
+#define EG_ALIGN16 alignas(16)
+#endif
+
+// table of [1..8] P as cached points (per-thread, local memory)
+EG_HD void ge_window_table(ge_cached tbl[8], const ge_ext &P) {
+    ge_ext cur = P;
+    ge_to_cached(tbl[0], cur);
+#pragma unroll 1
+    for (int k = 1; k < 8; k++) {
+        ge_hot_add_cached(cur, (const uint32_t *)&tbl[0], false);
+        ge_to_cached(tbl[k], cur);
+    }
+}
+
+template <int NV, int NF>
+EG_HD void ge_msm_chain(ge_ext &out, const ge_ext *P, const sc *a, const uint32_t *const *ftab, const sc *b) {
+    EG_ALIGN16 ge_cached tbl[NV > 0 ? NV : 1][8];
+    uint32_t ra[NV > 0 ? NV : 1][8];
+    uint32_t rb[NF > 0 ? NF : 1][8];
+#pragma unroll 1
+    for (int v = 0; v < NV; v++) {
+        ge_window_table(tbl[v], P[v]);
+        sc_recode4(ra[v], a[v]);
+    }
+    for (int f = 0; f < NF; f++) sc_recode8(rb[f], b[f]);
+
+    ge_ext acc = ge_identity();
+#pragma unroll 1
+    for (int i = 63; i >= 0; i--) {
+        if (i != 63) ge_hot_dbl(acc, 4);
+#pragma unroll 1
+        for (int v = 0; v < NV; v++) {
+            int d = sc_digit4(ra[v], i);
+            if (d != 0) ge_hot_add_cached(acc, (const uint32_t *)&tbl[v][(d < 0 ? -d : d) - 1], d < 0);
+        }
+        if ((i & 1) == 0) {
+#pragma unroll 1
+            for (int f = 0; f < NF; f++) {
+                int d = sc_digit8(rb[f], i >> 1);
+                if (d != 0) ge_hot_add_niels(acc, ftab[f], (d < 0 ? -d : d) - 1, d < 0);
+            }
+        }
+    }
+    out = acc;
+}
+
+
+// Same chain with run-time term counts (nv <= MAXV, nf <= 2), for the equations that are not of the [a]P + [b]F shape:
+// share verification (two per-item bases), SumOfSquaresProof (G, K and one per-item base; (n+2)-term sums) and
+// Lagrange recombination.  Replaces the general vartime_multi_mul (ristretto.rs:139-146).
+template <int MAXV>
+EG_HD void ge_msm_chain_rt(ge_ext &out, int nv, const ge_ext *P, const sc *a, int nf, const uint32_t *const *ftab, const sc *b) {
+    EG_ALIGN16 ge_cached tbl[MAXV][8];
+    uint32_t ra[MAXV][8];
+    uint32_t rb[2][8];
+#pragma unroll 1
+    for (int v = 0; v < nv; v++) {
+        ge_window_table(tbl[v], P[v]);
+        sc_recode4(ra[v], a[v]);
+    }
+#pragma unroll 1
+    for (int f = 0; f < nf; f++) sc_recode8(rb[f], b[f]);
+    ge_ext acc = ge_identity();
+#pragma unroll 1
+    for (int i = 63; i >= 0; i--) {
+        if (i != 63) ge_hot_dbl(acc, 4);
+#pragma unroll 1
+        for (int v = 0; v < nv; v++) {
+            int d = sc_digit4(ra[v], i);
+            if (d != 0) ge_hot_add_cached(acc, (const uint32_t *)&tbl[v][(d < 0 ? -d : d) - 1], d < 0);
+        }
+        if ((i & 1) == 0) {
+#pragma unroll 1
+            for (int f = 0; f < nf; f++) {
+                int d = sc_digit8(rb[f], i >> 1);
+                if (d != 0) ge_hot_add_niels(acc, ftab[f], (d < 0 ? -d : d) - 1, d < 0);
+            }
+        }
+    }
+    out = acc;
+}
+
+// ------------------------------------------------------------------ chunked tables: 64 doublings per equation
+//
+// A ring proof evaluates several equations on the SAME ciphertext points (one per admissible value, ring.rs:333-361)
+// with different challenges.  Splitting a 253-bit scalar into four 64-bit chunks, a = sum_c 2^(64c) a_c, turns
+// [a]P into sum_c [a_c] P_c with P_c = [2^(64c)] P: the 192 doublings that produce P_1..P_3 (and the four window
+// tables [1..8] P_c) are paid once per point, every equation then needs only 64 shared doublings.  The fixed bases
+// G and K get the same treatment once per context (4 x 128 affine entries each).
+
+#define EG_VCHUNKS 4
+#define EG_VTAB_ENTRY_WORDS 32                                  // one cached point
+#define EG_VTAB_WORDS (EG_VCHUNKS * 8 * EG_VTAB_ENTRY_WORDS)    // 4 KB per point
+#define EG_FCHUNK_TABLE_WORDS (EG_VCHUNKS * EG_FIXED_TABLE_WORDS)   // 48 KB per fixed base
+
 // tab[(c * 8 + k) * 32 ..] = cached((k + 1) * 2^(64 c) * P), c < 4, k < 8.  `tab` is 16-byte aligned scratch.
 static EG_HD_NOINLINE void ge_vtab_build(uint32_t *tab, const ge_ext &P) {
     ge_ext base = P;
 #pragma unroll 1
     for (int c = 0; c < EG_VCHUNKS; c++) {
-        ge_cached c1;
-        ge_to_cached(c1, base);
-        ge_cached_store(tab + (c * 8) * EG_VTAB_ENTRY_WORDS, c1);
+        uint32_t *t0 = tab + (c * 8) * EG_VTAB_ENTRY_WORDS;
+        ge_cached ck;
+        ge_to_cached(ck, base);
+        ge_cached_store(t0, ck);
         ge_ext cur = base;
 #pragma unroll 1
         for (int k = 1; k < 8; k++) {
-            ge_p1p1 t;
-            ge_add_cached_p1p1(t, cur, c1, false);
-            ge_p1p1_to_ext(cur, t);
-            ge_cached ck;
+            ge_hot_add_cached(cur, t0, false);
             ge_to_cached(ck, cur);
-            ge_cached_store(tab + (c * 8 + k) * EG_VTAB_ENTRY_WORDS, ck);
+            ge_cached_store(t0 + k * EG_VTAB_ENTRY_WORDS, ck);
         }
-        if (c + 1 < EG_VCHUNKS) {
-            ge_p1p1 t;
-#pragma unroll 1
-            for (int k = 0; k < 63; k++) { ge_dbl_p1p1(t, base); ge_p1p1_to_proj(base, t); }
-            ge_dbl_p1p1(t, base); ge_p1p1_to_ext(base, t);
-        }
+        if (c + 1 < EG_VCHUNKS) ge_hot_dbl(base, 64);
     }
 }
 
@@ -335,23 +447,27 @@ static EG_HD_NOINLINE void ge_eval64(ge_ext &out, const uint32_t *vtab, const sc
     sc_recode4(ra, a);
     sc_recode8(rb0, b0);
     sc_recode8(rb1, b1);
+    // the accumulator stays in registers for the whole loop: the point formulas are expanded here once each (rolled
+    // loops), with the field operations as calls (see EG_HOT_OPS above for why they are not expanded)
     ge_ext acc = ge_identity();
     ge_p1p1 t;
 #pragma unroll 1
     for (int i = 15; i >= 0; i--) {
         if (i != 15) {
 #pragma unroll 1
-            for (int k = 0; k < 3; k++) { ge_dbl_p1p1(t, acc); ge_p1p1_to_proj(acc, t); }
-            ge_dbl_p1p1(t, acc); ge_p1p1_to_ext(acc, t);
+            for (int k = 0; k < 4; k++) {
+                ge_dbl_p1p1(t, acc);
+                ge_p1p1_to_proj(acc, t);
+                if (k == 3) fe_mul(acc.T, t.E, t.H);
+            }
         }
         if (vtab) {
 #pragma unroll 1
             for (int c = 0; c < EG_VCHUNKS; c++) {
                 int d = sc_digit4(ra, 16 * c + i);
                 if (d != 0) {
-                    int m = d < 0 ? -d : d;
                     ge_cached q;
-                    ge_cached_load(q, vtab + (c * 8 + m - 1) * EG_VTAB_ENTRY_WORDS);
+                    ge_cached_load(q, vtab + (c * 8 + (d < 0 ? -d : d) - 1) * EG_VTAB_ENTRY_WORDS);
                     ge_add_cached_p1p1(t, acc, q, d < 0);
                     ge_p1p1_to_ext(acc, t);
                 }
@@ -366,9 +482,8 @@ static EG_HD_NOINLINE void ge_eval64(ge_ext &out, const uint32_t *vtab, const sc
                 for (int c = 0; c < EG_VCHUNKS; c++) {
                     int d = sc_digit8(rb, 8 * c + (i >> 1));
                     if (d != 0) {
-                        int m = d < 0 ? -d : d;
                         ge_niels n;
-                        ge_niels_load(n, ft + c * EG_FIXED_TABLE_WORDS, m - 1);
+                        ge_niels_load4(n, ft + c * EG_FIXED_TABLE_WORDS, (d < 0 ? -d : d) - 1);
                         ge_add_niels_p1p1(t, acc, n, d < 0);
                         ge_p1p1_to_ext(acc, t);
                     }
@@ -463,64 +578,6 @@ EG_HD void ge_double_compress1(uint32_t w[8], const ge_ext &Q) {
     fe_invert(i, u);
     fe_select(i, i, fe_zero(), z);
     ge_dc_finish(w, s, i);
-}
-
-// Same chain with run-time term counts (nv <= MAXV, nf <= 2), for the equations that are not of the [a]P + [b]F shape:
-// share verification (two per-item bases), SumOfSquaresProof (G, K and one per-item base; (n+2)-term sums) and
-// Lagrange recombination.  Replaces the general vartime_multi_mul (ristretto.rs:139-146).
-template <int MAXV>
-EG_HD void ge_msm_chain_rt(ge_ext &out, int nv, const ge_ext *P, const sc *a, int nf, const uint32_t *const *ftab, const sc *b) {
-    ge_cached tbl[MAXV][8];
-    uint32_t ra[MAXV][8];
-    uint32_t rb[2][8];
-#pragma unroll 1
-    for (int v = 0; v < nv; v++) {
-        ge_ext cur = P[v];
-        ge_cached c1;
-        ge_to_cached(c1, cur);
-        tbl[v][0] = c1;
-#pragma unroll 1
-        for (int k = 1; k < 8; k++) {
-            ge_p1p1 t;
-            ge_add_cached_p1p1(t, cur, c1, false);
-            ge_p1p1_to_ext(cur, t);
-            ge_to_cached(tbl[v][k], cur);
-        }
-        sc_recode4(ra[v], a[v]);
-    }
-#pragma unroll 1
-    for (int f = 0; f < nf; f++) sc_recode8(rb[f], b[f]);
-    ge_ext acc = ge_identity();
-    ge_p1p1 t;
-#pragma unroll 1
-    for (int i = 63; i >= 0; i--) {
-#pragma unroll 1
-        for (int k = 0; k < 3; k++) { ge_dbl_p1p1(t, acc); ge_p1p1_to_proj(acc, t); }
-        ge_dbl_p1p1(t, acc); ge_p1p1_to_ext(acc, t);
-#pragma unroll 1
-        for (int v = 0; v < nv; v++) {
-            int d = sc_digit4(ra[v], i);
-            if (d != 0) {
-                int m = d < 0 ? -d : d;
-                ge_add_cached_p1p1(t, acc, tbl[v][m - 1], d < 0);
-                ge_p1p1_to_ext(acc, t);
-            }
-        }
-        if ((i & 1) == 0) {
-#pragma unroll 1
-            for (int f = 0; f < nf; f++) {
-                int d = sc_digit8(rb[f], i >> 1);
-                if (d != 0) {
-                    int m = d < 0 ? -d : d;
-                    ge_niels n;
-                    ge_niels_load(n, ftab[f], m - 1);
-                    ge_add_niels_p1p1(t, acc, n, d < 0);
-                    ge_p1p1_to_ext(acc, t);
-                }
-            }
-        }
-    }
-    out = acc;
 }
 
 }  // namespace eg
