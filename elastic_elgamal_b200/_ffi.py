@@ -45,6 +45,9 @@ PROTOTYPES = {
     "eg_last_error": (C.c_char_p, [C.c_void_p]),
     "eg_version": (C.c_char_p, []),
     "eg_ctx_set_receiver": (C.c_int32, [C.c_void_p, P8]),
+    "eg_ctx_set_blinding_base": (C.c_int32, [C.c_void_p, P8]),
+    "eg_verify_commitment_equiv_batch": (C.c_int32, [C.c_void_p, C.c_char_p, C.c_size_t, P8, P8, P8, P8]),
+    "eg_verify_possession_batch": (C.c_int32, [C.c_void_p, C.c_char_p, C.c_uint32, C.c_size_t, P8, P8, P8]),
     "eg_elements_validate": (C.c_int32, [C.c_void_p, C.c_size_t, P8, P8]),
     "eg_scalars_validate": (C.c_int32, [C.c_void_p, C.c_size_t, P8, P8]),
     "eg_scalars_from_wide": (C.c_int32, [C.c_void_p, C.c_size_t, P8, P8]),

@@ -251,15 +251,21 @@ __global__ void k_ciphertexts_sum(const uint8_t *parts, size_t n_parts, size_t n
 
 // general multi-scalar equations (share proofs, SumOfSquaresProof, Lagrange recombination)
 __global__ void __launch_bounds__(128) k_msm(const msm_params P) {
-    __shared__ __align__(16) uint32_t s_tab[2 * EG_FIXED_TABLE_WORDS];
+    __shared__ __align__(16) uint32_t s_tab[3 * EG_FIXED_TABLE_WORDS];      // G, K and (when set) the Pedersen base H
     for (int k = threadIdx.x; k < EG_FIXED_TABLE_WORDS; k += blockDim.x) {
         s_tab[k] = P.table_g[k];
         s_tab[EG_FIXED_TABLE_WORDS + k] = P.table_k[k];
+        if (P.table_h) s_tab[2 * EG_FIXED_TABLE_WORDS + k] = P.table_h[k];
     }
     __syncthreads();
     size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= P.n * (size_t)P.n_slots) return;
-    msm_body(P, tid % P.n, (int)(tid / P.n), s_tab, s_tab + EG_FIXED_TABLE_WORDS);
+    msm_body(P, tid % P.n, (int)(tid / P.n), s_tab, s_tab + EG_FIXED_TABLE_WORDS, s_tab + 2 * EG_FIXED_TABLE_WORDS);
+}
+
+__global__ void __launch_bounds__(128) k_sigma_final(const sigma_final_params P) {
+    size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid < P.n) sigma_final_body(P, tid);
 }
 
 __global__ void __launch_bounds__(128) k_sumsq_final(const sumsq_final_params P) {
@@ -340,9 +346,10 @@ struct dev_buf {
 struct eg_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    bool has_receiver = false;
+    bool has_receiver = false, has_blinding_base = false;
     uint8_t key[32];
-    uint32_t *d_table_g = nullptr, *d_table_k = nullptr, *d_status = nullptr;
+    uint8_t blinding_base[32];
+    uint32_t *d_table_g = nullptr, *d_table_k = nullptr, *d_table_h = nullptr, *d_status = nullptr;
     std::string err;
     uint64_t launches = 0, commit_launches = 0, commit_tasks = 0;
     float timings[5] = {0, 0, 0, 0, 0};
@@ -686,9 +693,18 @@ static void launch_ciphertexts_sum(eg_ctx *ctx, const uint8_t *parts, size_t n_p
 static void launch_msm(eg_ctx *ctx, const msm_params &P) {
     size_t total = P.n * (size_t)P.n_slots;
 #ifdef EG_HOSTSIM
-    EG_FOR_HOST(total, msm_body(P, tid % P.n, (int)(tid / P.n), P.table_g, P.table_k))
+    EG_FOR_HOST(total, msm_body(P, tid % P.n, (int)(tid / P.n), P.table_g, P.table_k, P.table_h))
 #else
     k_msm<<<grid_for(total, 128), 128, 0, ctx->stream>>>(P);
+#endif
+    ctx->launches++;
+}
+
+static void launch_sigma_final(eg_ctx *ctx, const sigma_final_params &P) {
+#ifdef EG_HOSTSIM
+    EG_FOR_HOST(P.n, sigma_final_body(P, tid))
+#else
+    k_sigma_final<<<grid_for(P.n, 128), 128, 0, ctx->stream>>>(P);
 #endif
     ctx->launches++;
 }
@@ -820,6 +836,7 @@ extern "C" void eg_ctx_destroy(eg_ctx *ctx) {
     for (dev_buf *b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->d_table_g) cudaFree(ctx->d_table_g);
     if (ctx->d_table_k) cudaFree(ctx->d_table_k);
+    if (ctx->d_table_h) cudaFree(ctx->d_table_h);
     if (ctx->d_status) cudaFree(ctx->d_status);
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
     for (auto &e : ctx->commit_ev) if (e) cudaEventDestroy(e);
@@ -841,6 +858,30 @@ extern "C" eg_status eg_ctx_set_receiver(eg_ctx *ctx, const uint8_t key[32]) {
     if (status == 2) { ctx->has_receiver = false; return fail(ctx, EG_ERR_IDENTITY_KEY, "receiver key is the group identity"); }
     memcpy(ctx->key, key, 32);
     ctx->has_receiver = true;
+    return EG_SUCCESS;
+}
+
+// Pedersen blinding base H of CommitmentEquivalenceProof (commitment.rs:140-145: `commitment_blinding_base`), e.g. the
+// Bulletproofs base of tests/snapshots.rs:253-257.  Gets the same chunked fixed-base table as G and K.
+extern "C" eg_status eg_ctx_set_blinding_base(eg_ctx *ctx, const uint8_t base[32]) {
+    if (!ctx || !base) return EG_ERR_INVALID_ARG;
+    CU(cudaSetDevice(ctx->device));
+    if (!ctx->d_table_h) {
+        cudaError_t ce = cudaMalloc(&ctx->d_table_h, EG_FCHUNK_TABLE_WORDS * 4);
+        if (ce != cudaSuccess) { cudaGetLastError(); ctx->d_table_h = nullptr; return fail(ctx, EG_ERR_OUT_OF_MEMORY, "cudaMalloc H table", ce); }
+    }
+    uint32_t *d_key = ctx->d_status + 16;
+    CU(cudaMemcpyAsync(d_key, base, 32, cudaMemcpyHostToDevice, ctx->stream));
+    launch_build_table(ctx, d_key, 0, ctx->d_table_h, ctx->d_status);
+    uint32_t status = 0;
+    CU(cudaMemcpyAsync(&status, ctx->d_status, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    ctx->has_blinding_base = false;
+    if (status == 1) return fail(ctx, EG_ERR_INVALID_ELEMENT, "blinding base does not represent a group element");
+    if (status == 2) return fail(ctx, EG_ERR_IDENTITY_KEY, "blinding base is the group identity");
+    memcpy(ctx->blinding_base, base, 32);
+    ctx->has_blinding_base = true;
     return EG_SUCCESS;
 }
 
@@ -2060,6 +2101,198 @@ extern "C" eg_status eg_verify_shares_batch(eg_ctx *ctx, const eg_keyset *ks, si
         vp.verdicts = (uint8_t *)ctx->verdicts.p;
         launch_share_verdict(ctx, vp);
         CU(cudaMemcpyAsync(verdicts + S * off, ctx->verdicts.p, k * S, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    return finish_call(ctx);
+}
+
+// =================================================================== CommitmentEquivalenceProof::verify
+
+static bool valid_label(const char *label) { return label && strlen(label) > 0 && strlen(label) < 256; }
+
+static void sigma_set_msg(sigma_msg &g, uint8_t kind, const char *label, uint32_t index, uint32_t count) {
+    memset(&g, 0, sizeof g);
+    g.kind = kind; g.label_len = (uint8_t)strlen(label);
+    memcpy(g.label, label, g.label_len);
+    g.index = index; g.count = count;
+}
+
+// commitment.rs:198-248.  Per item: ciphertext R | B (64 B), commitment C (32 B), proof c | s_r | s_v | s_c (128 B).
+//   E_r = [s_r]G - [c]R ; E_b = [s_v]G + [s_r]K - [c]B ; E_c = [s_v]G + [s_c]H - [c]C
+extern "C" eg_status eg_verify_commitment_equiv_batch(eg_ctx *ctx, const char *label, size_t n, const uint8_t *cts,
+                                                      const uint8_t *commitments, const uint8_t *proofs, uint8_t *verdicts) {
+    TRY(begin_call(ctx));
+    if (!ctx->has_blinding_base) return fail(ctx, EG_ERR_NO_RECEIVER, "eg_ctx_set_blinding_base has not been called");
+    if (!valid_label(label)) return fail(ctx, EG_ERR_INVALID_ARG, "transcript label must be 1..255 bytes");
+    if (n == 0) return EG_SUCCESS;
+    if (!cts || !commitments || !proofs || !verdicts) return fail(ctx, EG_ERR_INVALID_ARG, "null pointer");
+    const size_t chunk = default_chunk(ctx), cm = std::min(chunk, n);
+    TRY(ensure(ctx, ctx->in[0], cm * 64));
+    TRY(ensure(ctx, ctx->in[1], cm * 32));
+    TRY(ensure(ctx, ctx->in[2], cm * 128));
+    TRY(ensure(ctx, ctx->verdicts, cm));
+    TRY(ensure(ctx, ctx->pts, cm * 3 * 128));
+    TRY(ensure(ctx, ctx->enc, cm * 3 * 32));
+    TRY(ensure(ctx, ctx->commit, cm * 3 * 32));
+    TRY(ensure(ctx, ctx->flags, cm * 4));
+    TRY(ensure(ctx, ctx->res[0], cm * 4));
+    transcript prefix;
+    merlin_new(prefix, label, (uint32_t)strlen(label));
+    merlin_append_message(prefix, EG_LBL("dom-sep"), (const uint8_t *)"commitment_equivalence", 22);
+    merlin_append_message(prefix, EG_LBL("K"), ctx->key, 32);
+    for (size_t off = 0; off < n; off += chunk) {
+        const size_t k = std::min(chunk, n - off);
+        CU(cudaMemcpyAsync(ctx->in[0].p, cts + 64 * off, k * 64, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->in[1].p, commitments + 32 * off, k * 32, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->in[2].p, proofs + 128 * off, k * 128, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemsetAsync(ctx->flags.p, 0, k * 4, ctx->stream));
+        in_bufs in;
+        memset(&in, 0, sizeof in);
+        in.buf[0] = (const uint8_t *)ctx->in[0].p; in.stride[0] = 64;
+        in.buf[1] = (const uint8_t *)ctx->in[1].p; in.stride[1] = 32;
+        in.buf[2] = (const uint8_t *)ctx->in[2].p; in.stride[2] = 128;
+        decode_params dp;
+        memset(&dp, 0, sizeof dp);
+        dp.in = in; dp.n = k; dp.n_slots = 3;
+        for (uint32_t q = 0; q < 3; q++) {
+            decode_slot &s = dp.slots[q];
+            s.want_enc = 1; s.enc_index = (uint16_t)q; s.p_index = q;
+            if (q < 2) { s.buf = 0; s.offset = 32 * q; } else { s.buf = 1; s.offset = 0; }
+        }
+        dp.pts = (uint32_t *)ctx->pts.p; dp.enc = (uint32_t *)ctx->enc.p; dp.flags = (uint32_t *)ctx->flags.p;
+        launch_decode(ctx, dp);
+        scalars_params sp;
+        memset(&sp, 0, sizeof sp);
+        sp.in = in; sp.n = k; sp.n_slots = 1; sp.slots[0].buf = 2; sp.slots[0].offset = 0; sp.slots[0].count = 4;
+        sp.flags = (uint32_t *)ctx->flags.p;
+        launch_scalars(ctx, sp);
+        std::vector<msm_slot> slots(3);
+        for (uint32_t q = 0; q < 3; q++) {
+            msm_slot &a = slots[q];
+            memset(&a, 0, sizeof a);
+            a.nv = 1; a.out_enc = 1; a.out_index = q;
+            a.p_index[0] = q; a.vs[0] = src_in(2, 0, true);                         // [-c] {R, B, C}
+        }
+        slots[0].nf = 1; slots[0].fbase[0] = 0; slots[0].fs[0] = src_in(2, 32, false);              // [s_r] G
+        slots[1].nf = 2; slots[1].fbase[0] = 0; slots[1].fs[0] = src_in(2, 64, false);              // [s_v] G
+        slots[1].fbase[1] = 1; slots[1].fs[1] = src_in(2, 32, false);                               // [s_r] K
+        slots[2].nf = 2; slots[2].fbase[0] = 0; slots[2].fs[0] = src_in(2, 64, false);              // [s_v] G
+        slots[2].fbase[1] = 2; slots[2].fs[1] = src_in(2, 96, false);                               // [s_c] H
+        TRY(upload_slots(ctx, slots));
+        msm_params mp;
+        memset(&mp, 0, sizeof mp);
+        mp.in = in; mp.n = k; mp.n_slots = 3; mp.slots = (const msm_slot *)ctx->slots.p;
+        mp.pts = (const uint32_t *)ctx->pts.p; mp.commit = (uint32_t *)ctx->commit.p; mp.pts_out = (uint32_t *)ctx->pts.p;
+        mp.table_g = ctx->d_table_g; mp.table_k = ctx->d_table_k; mp.table_h = ctx->d_table_h;
+        launch_msm(ctx, mp);
+        sigma_final_params fp;
+        memset(&fp, 0, sizeof fp);
+        fp.in = in; fp.n = k; fp.prefix = prefix; fp.n_msgs = 6;
+        sigma_set_msg(fp.msgs[0], 0, "R", 0, 1);
+        sigma_set_msg(fp.msgs[1], 0, "B", 1, 1);
+        sigma_set_msg(fp.msgs[2], 0, "C", 2, 1);
+        sigma_set_msg(fp.msgs[3], 1, "[e_r]G", 0, 1);
+        sigma_set_msg(fp.msgs[4], 1, "[e_v]G + [e_r]K", 1, 1);
+        sigma_set_msg(fp.msgs[5], 1, "[e_v]G + [e_c]H", 2, 1);
+        fp.proof_buf = 2; fp.c_offset = 0;
+        fp.enc = (const uint32_t *)ctx->enc.p; fp.commit = (const uint32_t *)ctx->commit.p; fp.result = (uint32_t *)ctx->res[0].p;
+        launch_sigma_final(ctx, fp);
+        verdict_params vp;
+        memset(&vp, 0, sizeof vp);
+        vp.n = k; vp.flags = (const uint32_t *)ctx->flags.p; vp.n_checks = 1;
+        vp.check[0] = (const uint32_t *)ctx->res[0].p; vp.check_stride[0] = 1; vp.code[0] = EG_V_CHALLENGE_MISMATCH;
+        vp.verdicts = (uint8_t *)ctx->verdicts.p;
+        launch_verdict(ctx, vp);
+        CU(cudaMemcpyAsync(verdicts + off, ctx->verdicts.p, k, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    return finish_call(ctx);
+}
+
+// =================================================================== ProofOfPossession::verify
+
+// possession.rs:137-163.  Per item: `keys_per_proof` public keys (32 B each) and the proof c | s_0 .. s_{k-1}.
+//   R_j = [s_j]G - [c]K_j ; transcript: start_proof("multi_pop"), "K" x k, "R" x k, challenge "c".
+// A key that is undecodable or the identity is malformed (PublicKey::from_bytes, keys/mod.rs:161-176).  No receiver needed.
+extern "C" eg_status eg_verify_possession_batch(eg_ctx *ctx, const char *label, uint32_t keys_per_proof, size_t n, const uint8_t *keys,
+                                                const uint8_t *proofs, uint8_t *verdicts) {
+    if (!ctx) return EG_ERR_INVALID_ARG;
+    CU(cudaSetDevice(ctx->device));
+    ctx->err.clear(); ctx->commit_ev_used = 0; ctx->call_commit_tasks = 0; ctx->call_commit_launches = 0;
+    if (!valid_label(label)) return fail(ctx, EG_ERR_INVALID_ARG, "transcript label must be 1..255 bytes");
+    const uint32_t K = keys_per_proof;
+    if (K == 0 || K > EG_MAX_RINGS) return fail(ctx, EG_ERR_INVALID_ARG, "keys_per_proof must be in 1..64");
+    if (n == 0) return EG_SUCCESS;
+    if (!keys || !proofs || !verdicts) return fail(ctx, EG_ERR_INVALID_ARG, "null pointer");
+    const size_t chunk = std::max<size_t>(1, default_chunk(ctx) / K), cm = std::min(chunk, n);
+    TRY(ensure(ctx, ctx->in[0], cm * 32 * K));
+    TRY(ensure(ctx, ctx->in[1], cm * 32 * (1 + K)));
+    TRY(ensure(ctx, ctx->verdicts, cm));
+    TRY(ensure(ctx, ctx->pts, cm * K * 128));
+    TRY(ensure(ctx, ctx->enc, cm * K * 32));
+    TRY(ensure(ctx, ctx->commit, cm * K * 32));
+    TRY(ensure(ctx, ctx->flags, cm * 4));
+    TRY(ensure(ctx, ctx->res[0], cm * 4));
+    transcript prefix;
+    merlin_new(prefix, label, (uint32_t)strlen(label));
+    merlin_append_message(prefix, EG_LBL("dom-sep"), (const uint8_t *)"multi_pop", 9);
+    for (size_t off = 0; off < n; off += chunk) {
+        const size_t k = std::min(chunk, n - off);
+        CU(cudaMemcpyAsync(ctx->in[0].p, keys + 32 * (size_t)K * off, k * 32 * K, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->in[1].p, proofs + 32 * (size_t)(1 + K) * off, k * 32 * (1 + K), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemsetAsync(ctx->flags.p, 0, k * 4, ctx->stream));
+        in_bufs in;
+        memset(&in, 0, sizeof in);
+        in.buf[0] = (const uint8_t *)ctx->in[0].p; in.stride[0] = 32 * K;
+        in.buf[1] = (const uint8_t *)ctx->in[1].p; in.stride[1] = 32 * (1 + K);
+        for (uint32_t q0 = 0; q0 < K; q0 += EG_MAX_SLOTS) {
+            decode_params dp;
+            memset(&dp, 0, sizeof dp);
+            dp.in = in; dp.n = k;
+            int ns = 0;
+            for (uint32_t q = q0; q < K && ns < EG_MAX_SLOTS; q++, ns++) {
+                decode_slot &s = dp.slots[ns];
+                s.buf = 0; s.want_enc = 1; s.reject_identity = 1; s.enc_index = (uint16_t)q; s.offset = 32 * q; s.p_index = q;
+            }
+            dp.n_slots = ns;
+            dp.pts = (uint32_t *)ctx->pts.p; dp.enc = (uint32_t *)ctx->enc.p; dp.flags = (uint32_t *)ctx->flags.p;
+            launch_decode(ctx, dp);
+        }
+        scalars_params sp;
+        memset(&sp, 0, sizeof sp);
+        sp.in = in; sp.n = k; sp.n_slots = 1; sp.slots[0].buf = 1; sp.slots[0].offset = 0; sp.slots[0].count = 1 + K;
+        sp.flags = (uint32_t *)ctx->flags.p;
+        launch_scalars(ctx, sp);
+        for (uint32_t q0 = 0; q0 < K; q0 += EG_MAX_SLOTS) {
+            commit_params cp;
+            memset(&cp, 0, sizeof cp);
+            cp.in = in; cp.n = k;
+            cp.pts = (const uint32_t *)ctx->pts.p; cp.commit = (uint32_t *)ctx->commit.p;
+            cp.table_g = ctx->d_table_g; cp.table_k = ctx->d_table_g;
+            int ns = 0;
+            for (uint32_t q = q0; q < K && ns < EG_MAX_SLOTS; q++, ns++) {
+                commit_slot &s = cp.slots[ns];
+                s.p_index = q; s.adm_index = -1; s.base = 0; s.e_planar = 0; s.e_buf = 1; s.s_buf = 1;
+                s.e_offset = 0; s.s_offset = 32 * (1 + q); s.out_index = q;
+            }
+            cp.n_slots = ns;
+            launch_commit(ctx, cp);
+        }
+        sigma_final_params fp;
+        memset(&fp, 0, sizeof fp);
+        fp.in = in; fp.n = k; fp.prefix = prefix; fp.n_msgs = 2;
+        sigma_set_msg(fp.msgs[0], 0, "K", 0, K);
+        sigma_set_msg(fp.msgs[1], 1, "R", 0, K);
+        fp.proof_buf = 1; fp.c_offset = 0;
+        fp.enc = (const uint32_t *)ctx->enc.p; fp.commit = (const uint32_t *)ctx->commit.p; fp.result = (uint32_t *)ctx->res[0].p;
+        launch_sigma_final(ctx, fp);
+        verdict_params vp;
+        memset(&vp, 0, sizeof vp);
+        vp.n = k; vp.flags = (const uint32_t *)ctx->flags.p; vp.n_checks = 1;
+        vp.check[0] = (const uint32_t *)ctx->res[0].p; vp.check_stride[0] = 1; vp.code[0] = EG_V_CHALLENGE_MISMATCH;
+        vp.verdicts = (uint8_t *)ctx->verdicts.p;
+        launch_verdict(ctx, vp);
+        CU(cudaMemcpyAsync(verdicts + off, ctx->verdicts.p, k, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
     }
     return finish_call(ctx);

@@ -79,6 +79,7 @@ EG_HD const uint8_t *in_ptr(const in_bufs &in, int k, size_t item) {
 struct decode_slot {
     uint8_t buf;                // which input buffer
     uint8_t want_enc;           // also store the 8 encoding words (for transcript "enc" messages)
+    uint8_t reject_identity;    // the element is a PublicKey: the identity is malformed too (keys/mod.rs:161-176)
     uint16_t enc_index;         // planar index in enc (8 words each)
     uint32_t offset;            // byte offset inside the item
     uint32_t p_index;           // planar point index
@@ -102,6 +103,7 @@ EG_HD void decode_body(const decode_params &P, size_t item, int slot) {
     load32_bytes(w, in_ptr(P.in, s.buf, item) + s.offset);
     ge_ext p;
     bool ok = ge_decode(p, w);
+    if (s.reject_identity && ge_is_identity(p)) ok = false;
     planar_store_point(P.pts, P.n, s.p_index, item, p);
     if (s.want_enc) planar_store_words(P.enc, P.n, s.enc_index, 8, item, w);
     if (!ok) {
@@ -229,7 +231,7 @@ struct msm_slot {
     uint32_t out_index;
     uint32_t p_index[EG_MSM_MAXV];   // planar point index, or index into const_pts when bit 31 is set
     scalar_src vs[EG_MSM_MAXV];
-    uint8_t fbase[2];           // 0: G, 1: K
+    uint8_t fbase[2];           // 0: G, 1: K, 2: H (Pedersen blinding base, eg_ctx_set_blinding_base)
     uint8_t pad2[2];
     scalar_src fs[2];
 };
@@ -246,6 +248,7 @@ struct msm_params {
     uint32_t *commit;           // planar encodings out
     uint32_t *pts_out;          // planar points out
     const uint32_t *table_g, *table_k;
+    const uint32_t *table_h;    // may be null when no slot uses base 2
 };
 
 EG_HD bool load_scalar(sc &out, const msm_params &P, const scalar_src &src, size_t item) {
@@ -260,7 +263,7 @@ EG_HD bool load_scalar(sc &out, const msm_params &P, const scalar_src &src, size
     return ok;
 }
 
-EG_HD void msm_body(const msm_params &P, size_t item, int slot, const uint32_t *tab_g, const uint32_t *tab_k) {
+EG_HD void msm_body(const msm_params &P, size_t item, int slot, const uint32_t *tab_g, const uint32_t *tab_k, const uint32_t *tab_h) {
     const msm_slot &s = P.slots[slot];
     ge_ext pts[EG_MSM_MAXV];
     sc a[EG_MSM_MAXV], b[2];
@@ -272,7 +275,7 @@ EG_HD void msm_body(const msm_params &P, size_t item, int slot, const uint32_t *
         load_scalar(a[v], P, s.vs[v], item);
     }
     for (int f = 0; f < s.nf; f++) {
-        ft[f] = s.fbase[f] ? tab_k : tab_g;
+        ft[f] = s.fbase[f] == 0 ? tab_g : (s.fbase[f] == 1 ? tab_k : tab_h);
         load_scalar(b[f], P, s.fs[f], item);
     }
     ge_ext acc;
@@ -675,6 +678,55 @@ EG_HD void logeq_final_body(const logeq_final_params &P, size_t item) {
     merlin_append_words(t, EG_LBL("[x]G"), w, 8);
     planar_load_words(w, P.commit, P.n, P.commit_index + 1, 8, item);
     merlin_append_words(t, EG_LBL("[x]K"), w, 8);
+    sc c, cc;
+    merlin_challenge_scalar(t, EG_LBL("c"), c);
+    load32_bytes(w, in_ptr(P.in, P.proof_buf, item) + P.c_offset);
+    bool ok = sc_from_words(cc, w);
+    P.result[item] = (ok && sc_eq(c, cc)) ? 1u : 0u;
+}
+
+// ------------------------------------------------------------------ generic Fiat-Shamir tail of a sigma proof
+//
+// Appends a list of 32-byte messages (input encodings, recomputed commitments) to a prepared transcript prefix, squeezes
+// the challenge and compares it with the proof's.  Used by CommitmentEquivalenceProof::verify (commitment.rs:198-248)
+// and ProofOfPossession::verify (possession.rs:137-163); a message entry with count > 1 is a run of messages with the
+// same label and consecutive indexes (the "K" / "R" runs of a multi-key proof of possession).
+#define EG_SIGMA_MAX_MSGS 8
+
+struct sigma_msg {
+    uint8_t kind;               // 0: planar `enc`, 1: planar `commit`
+    uint8_t label_len;
+    char label[22];
+    uint32_t index;             // first planar index
+    uint32_t count;             // messages in the run
+};
+
+struct sigma_final_params {
+    in_bufs in;
+    size_t n;
+    transcript prefix;
+    int n_msgs;
+    sigma_msg msgs[EG_SIGMA_MAX_MSGS];
+    uint8_t proof_buf;
+    uint32_t c_offset;          // byte offset of the proof's challenge in its item
+    const uint32_t *enc;
+    const uint32_t *commit;
+    uint32_t *result;
+};
+
+EG_HD void sigma_final_body(const sigma_final_params &P, size_t item) {
+    transcript t = P.prefix;
+    uint32_t w[8];
+#pragma unroll 1
+    for (int m = 0; m < P.n_msgs; m++) {
+        const sigma_msg &g = P.msgs[m];
+        const uint32_t *base = g.kind ? P.commit : P.enc;
+#pragma unroll 1
+        for (uint32_t r = 0; r < g.count; r++) {
+            planar_load_words(w, base, P.n, g.index + r, 8, item);
+            merlin_append_words(t, g.label, g.label_len, w, 8);
+        }
+    }
     sc c, cc;
     merlin_challenge_scalar(t, EG_LBL("c"), c);
     load32_bytes(w, in_ptr(P.in, P.proof_buf, item) + P.c_offset);

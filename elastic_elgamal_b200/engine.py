@@ -80,6 +80,11 @@ class Engine:
         key = _u8(np.frombuffer(bytes(key), dtype=np.uint8), (32,))
         self._check(self.lib.eg_ctx_set_receiver(self.h, _addr(key)))
 
+    # ---- Pedersen blinding base H (CommitmentEquivalenceProof)
+    def set_blinding_base(self, base):
+        base = _u8(np.frombuffer(bytes(base), dtype=np.uint8), (32,))
+        self._check(self.lib.eg_ctx_set_blinding_base(self.h, _addr(base)))
+
     # ---- group helpers
     def elements_validate(self, enc):
         enc = _u8(enc, (-1, 32))
@@ -149,6 +154,23 @@ class Engine:
         self._check(self.lib.eg_verify_choice_batch(self.h, n, options, int(single), _addr(choices), _addr(rings),
                                                     _addr(sums) if single else None, _addr(v), _addr(t)))
         return v, t
+
+    def verify_commitment_equiv(self, label, cts, commitments, proofs):
+        cts = _u8(cts, (-1, 64))
+        n = cts.shape[0]
+        commitments, proofs = _u8(commitments, (n, 32)), _u8(proofs, (n, 128))
+        v = np.empty(n, np.uint8)
+        self._check(self.lib.eg_verify_commitment_equiv_batch(self.h, label.encode(), n, _addr(cts), _addr(commitments),
+                                                              _addr(proofs), _addr(v)))
+        return v
+
+    def verify_possession(self, label, keys, proofs):
+        keys = _u8(keys)
+        n, k = keys.shape[0], keys.shape[1]
+        keys, proofs = keys.reshape(n, k, 32), _u8(proofs, (n, 1 + k, 32))
+        v = np.empty(n, np.uint8)
+        self._check(self.lib.eg_verify_possession_batch(self.h, label.encode(), k, n, _addr(keys), _addr(proofs), _addr(v)))
+        return v
 
     # ---- encryption side (randomness supplied by the caller as 64-byte blocks in the reference's draw order)
     def encrypt_bool(self, values, wide_rand):

@@ -77,6 +77,11 @@ const char *eg_version(void);
  * keeps its bytes for the transcripts (PublicKey::as_bytes :188-190) and builds K's fixed-base table. */
 eg_status eg_ctx_set_receiver(eg_ctx *ctx, const uint8_t key[32]);
 
+/* The Pedersen blinding base H of CommitmentEquivalenceProof (`commitment_blinding_base`, src/proofs/commitment.rs:140-145),
+ * e.g. the Bulletproofs base of tests/snapshots.rs:253-257.  Validated like a public key (decodable, not the identity);
+ * gets the same fixed-base table as G and K. */
+eg_status eg_ctx_set_blinding_base(eg_ctx *ctx, const uint8_t base[32]);
+
 /* ---- group-level helpers (Group / ElementOps / ScalarOps for Ristretto, src/group/ristretto.rs) -- */
 
 /* ElementOps::deserialize_element :93-95 over a batch: ok[i] = 1 if encodings[i] decodes */
@@ -163,6 +168,22 @@ eg_status eg_verify_shares_batch(eg_ctx *ctx, const eg_keyset *keyset, size_t n_
                                  const uint8_t *shares /* n_tallies*n_shares*32 */,
                                  const uint8_t *proofs /* n_tallies*n_shares*64 */,
                                  uint8_t *verdicts /* n_tallies*n_shares */);
+
+/* CommitmentEquivalenceProof::verify (src/proofs/commitment.rs:198-248) over a batch, against the receiver key and the
+ * blinding base of the context, with `Transcript::new(label)`.  The reference gives this proof a serde form only; the
+ * 128-byte layout is the struct's field order (:126-135): challenge | randomness_response | value_response |
+ * commitment_response.  verdicts: EG_V_OK / EG_V_MALFORMED / EG_V_CHALLENGE_MISMATCH. */
+eg_status eg_verify_commitment_equiv_batch(eg_ctx *ctx, const char *transcript_label, size_t n, const uint8_t *cts /* n*64 */,
+                                           const uint8_t *commitments /* n*32 */, const uint8_t *proofs /* n*128 */,
+                                           uint8_t *verdicts /* n */);
+
+/* ProofOfPossession::verify (src/proofs/possession.rs:137-163) over a batch of proofs for `keys_per_proof` public keys
+ * each (1..64), with `Transcript::new(label)`.  Proof layout = struct field order (:71-76): challenge | responses.
+ * A key that does not decode or is the identity is EG_V_MALFORMED (PublicKey::from_bytes, src/keys/mod.rs:161-176); a
+ * responses / keys count mismatch cannot occur in a fixed-stride batch.  Needs no receiver key. */
+eg_status eg_verify_possession_batch(eg_ctx *ctx, const char *transcript_label, uint32_t keys_per_proof, size_t n,
+                                     const uint8_t *keys /* n*keys_per_proof*32 */,
+                                     const uint8_t *proofs /* n*(1+keys_per_proof)*32 */, uint8_t *verdicts /* n */);
 
 /* DiscreteLogTable::new (src/encryption.rs:267-284) for the values lo..hi (exclusive); lives on the device */
 eg_status eg_dlog_table_create(eg_ctx *ctx, uint64_t lo, uint64_t hi, eg_dlog_table **out);

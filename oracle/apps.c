@@ -818,3 +818,229 @@ int eo_verify_qv_batch(const uint8_t pkb[32], const eo_qv_params *p, size_t n, c
     qv_ctx_free(&c.q);
     return 0;
 }
+
+/* ================================================================== CommitmentEquivalenceProof (proofs/commitment.rs)
+ * Proof bytes (the reference has serde only; field order of the struct, commitment.rs:126-135):
+ *   challenge | randomness_response | value_response | commitment_response  = 128 B.                           */
+
+/* commitment.rs:146-193.  Draw order: e_r, e_v, e_c. */
+static void ceq_prove_pk(const eo_pk *pk, const eo_ct *ct, const eo_sc *value, const eo_sc *randomness, const eo_sc *blinding,
+                         const eo_pt *h, eo_transcript *t, eo_rng *rng, uint8_t commitment[32], uint8_t proof[128]) {
+    eo_pt c, vg, bh, er_g, ev_g, er_k, ec_h, eb, ec;
+    eo_pt_mul_generator(&vg, value);
+    eo_pt_mul(&bh, blinding, h);
+    eo_pt_add(&c, &vg, &bh);
+    eo_transcript_start_proof(t, "commitment_equivalence");
+    eo_transcript_append_message(t, "K", pk->bytes, 32);
+    eo_transcript_append_element(t, "R", &ct->R);
+    eo_transcript_append_element(t, "B", &ct->B);
+    eo_transcript_append_element(t, "C", &c);
+    eo_sc e_r, e_v, e_c, ch, s;
+    eo_rng_scalar(rng, &e_r);
+    eo_rng_scalar(rng, &e_v);
+    eo_rng_scalar(rng, &e_c);
+    eo_pt_mul_generator(&er_g, &e_r);
+    eo_transcript_append_element(t, "[e_r]G", &er_g);
+    eo_pt_mul_generator(&ev_g, &e_v);
+    eo_pt_mul(&er_k, &e_r, &pk->element);
+    eo_pt_add(&eb, &ev_g, &er_k);
+    eo_transcript_append_element(t, "[e_v]G + [e_r]K", &eb);
+    eo_pt_mul(&ec_h, &e_c, h);
+    eo_pt_add(&ec, &ev_g, &ec_h);
+    eo_transcript_append_element(t, "[e_v]G + [e_c]H", &ec);
+    eo_transcript_challenge_scalar(t, "c", &ch);
+    eo_sc_tobytes(proof, &ch);
+    eo_sc_mul(&s, &ch, randomness); eo_sc_add(&s, &s, &e_r); eo_sc_tobytes(proof + 32, &s);
+    eo_sc_mul(&s, &ch, value);      eo_sc_add(&s, &s, &e_v); eo_sc_tobytes(proof + 64, &s);
+    eo_sc_mul(&s, &ch, blinding);   eo_sc_add(&s, &s, &e_c); eo_sc_tobytes(proof + 96, &s);
+    eo_pt_encode(commitment, &c);
+}
+
+/* commitment.rs:198-248 */
+static int ceq_verify_pk(const eo_pk *pk, const eo_pt *h, const char *label, const uint8_t ctb[64], const uint8_t commitment[32],
+                         const uint8_t proof[128]) {
+    eo_ct ct;
+    eo_pt c;
+    eo_sc s[4];
+    if (!eo_ct_decode(&ct, ctb) || !eo_pt_decode(&c, commitment)) return EO_MALFORMED;
+    if (!eo_scalars_decode(s, proof, 4)) return EO_MALFORMED;
+    eo_transcript t;
+    eo_transcript_new(&t, label);
+    eo_transcript_start_proof(&t, "commitment_equivalence");
+    eo_transcript_append_message(&t, "K", pk->bytes, 32);
+    eo_transcript_append_element(&t, "R", &ct.R);
+    eo_transcript_append_element(&t, "B", &ct.B);
+    eo_transcript_append_element(&t, "C", &c);
+    eo_sc neg_c, expected;
+    eo_sc_neg(&neg_c, &s[0]);
+    eo_pt e;
+    eo_pt_double_mul_generator(&e, &neg_c, &ct.R, &s[1]);
+    eo_transcript_append_element(&t, "[e_r]G", &e);
+    eo_pt g;
+    eo_sc one;
+    eo_sc_from_u64(&one, 1);
+    eo_pt_mul_generator(&g, &one);
+    eo_sc sc3[3] = {s[2], s[1], neg_c};
+    eo_pt pt3[3] = {g, pk->element, ct.B};
+    eo_pt_multi_mul(&e, sc3, pt3, 3);
+    eo_transcript_append_element(&t, "[e_v]G + [e_r]K", &e);
+    eo_sc sc3b[3] = {s[2], s[3], neg_c};
+    eo_pt pt3b[3] = {g, *h, c};
+    eo_pt_multi_mul(&e, sc3b, pt3b, 3);
+    eo_transcript_append_element(&t, "[e_v]G + [e_c]H", &e);
+    eo_transcript_challenge_scalar(&t, "c", &expected);
+    return eo_sc_eq(&expected, &s[0]) ? EO_OK : EO_CHALLENGE_MISMATCH;
+}
+
+/* tests/snapshots.rs:163-189 order: CiphertextWithValue::new(value) (draws r), SecretKey::generate (blinding), proof */
+int eo_commitment_equiv_prove(const uint8_t pkb[32], uint64_t value, const uint8_t hb[32], const char *label, eo_rng *rng,
+                              uint8_t ctb[64], uint8_t commitment[32], uint8_t proof[128], uint8_t blinding_out[32]) {
+    eo_pk pk;
+    eo_pt h, vg;
+    if (eo_pk_from_bytes(&pk, pkb) || !eo_pt_decode(&h, hb)) return -1;
+    eo_sc v, r, blinding;
+    eo_ct ct;
+    eo_sc_from_u64(&v, value);
+    eo_pt_mul_generator(&vg, &v);
+    eo_ext_ct_new(&ct, &r, &vg, &pk, rng);
+    eo_rng_scalar(rng, &blinding);
+    eo_transcript t;
+    eo_transcript_new(&t, label);
+    ceq_prove_pk(&pk, &ct, &v, &r, &blinding, &h, &t, rng, commitment, proof);
+    eo_ct_encode(ctb, &ct);
+    if (blinding_out) eo_sc_tobytes(blinding_out, &blinding);
+    return 0;
+}
+
+int eo_commitment_equiv_verify(const uint8_t pkb[32], const uint8_t hb[32], const char *label, const uint8_t ctb[64],
+                               const uint8_t commitment[32], const uint8_t proof[128]) {
+    eo_pk pk;
+    eo_pt h;
+    if (eo_pk_from_bytes(&pk, pkb) || !eo_pt_decode(&h, hb)) return -1;
+    return ceq_verify_pk(&pk, &h, label, ctb, commitment, proof);
+}
+
+typedef struct {
+    eo_pk pk; eo_pt h; const uint8_t *hb; const char *label; const uint8_t *seed; size_t first; const uint64_t *values;
+    uint8_t *cts, *commitments, *proofs; const uint8_t *ccts, *ccommitments, *cproofs; uint8_t *verdicts;
+} ceq_ctx;
+
+static void gen_ceq_item(void *p, size_t i) {
+    ceq_ctx *c = (ceq_ctx *)p;
+    eo_rng rng;
+    item_rng(&rng, c->seed, c->first + i);
+    eo_commitment_equiv_prove(c->pk.bytes, c->values[i], c->hb, c->label, &rng, c->cts + 64 * i, c->commitments + 32 * i,
+                              c->proofs + 128 * i, NULL);
+}
+
+int eo_gen_ceq_batch(const uint8_t pkb[32], const uint8_t hb[32], const char *label, const uint8_t seed[32], size_t first,
+                     size_t n, const uint64_t *values, uint8_t *cts, uint8_t *commitments, uint8_t *proofs, int threads) {
+    ceq_ctx c;
+    if (eo_pk_from_bytes(&c.pk, pkb) || !eo_pt_decode(&c.h, hb)) return -1;
+    c.hb = hb; c.label = label; c.seed = seed; c.first = first; c.values = values;
+    c.cts = cts; c.commitments = commitments; c.proofs = proofs;
+    parallel_for(gen_ceq_item, &c, n, threads);
+    return 0;
+}
+
+static void verify_ceq_item(void *p, size_t i) {
+    ceq_ctx *c = (ceq_ctx *)p;
+    c->verdicts[i] = (uint8_t)ceq_verify_pk(&c->pk, &c->h, c->label, c->ccts + 64 * i, c->ccommitments + 32 * i, c->cproofs + 128 * i);
+}
+
+int eo_verify_ceq_batch(const uint8_t pkb[32], const uint8_t hb[32], const char *label, size_t n, const uint8_t *cts,
+                        const uint8_t *commitments, const uint8_t *proofs, uint8_t *verdicts, int threads) {
+    ceq_ctx c;
+    if (eo_pk_from_bytes(&c.pk, pkb) || !eo_pt_decode(&c.h, hb)) return -1;
+    c.label = label; c.ccts = cts; c.ccommitments = commitments; c.cproofs = proofs; c.verdicts = verdicts;
+    parallel_for(verify_ceq_item, &c, n, threads);
+    return 0;
+}
+
+/* ================================================================== ProofOfPossession (proofs/possession.rs)
+ * Proof bytes: challenge | responses[k]  = 32 (1 + k) B (struct field order, possession.rs:71-76).             */
+
+/* possession.rs:94-130: secrets / public keys of k keypairs; one nonce draw per key, in key order */
+int eo_pop_prove(uint32_t k, const uint8_t *secrets /* k*32 */, const uint8_t *keys /* k*32 */, const char *label, eo_rng *rng,
+                 uint8_t *proof /* 32 (1+k) */) {
+    if (k == 0 || k > EO_MAX_RINGS) return -1;
+    eo_transcript t;
+    eo_transcript_new(&t, label);
+    eo_transcript_start_proof(&t, "multi_pop");
+    for (uint32_t i = 0; i < k; i++) eo_transcript_append_message(&t, "K", keys + 32 * i, 32);
+    eo_sc nonce[EO_MAX_RINGS], ch;
+    for (uint32_t i = 0; i < k; i++) {
+        eo_pt r;
+        eo_rng_scalar(rng, &nonce[i]);
+        eo_pt_mul_generator(&r, &nonce[i]);
+        eo_transcript_append_element(&t, "R", &r);
+    }
+    eo_transcript_challenge_scalar(&t, "c", &ch);
+    eo_sc_tobytes(proof, &ch);
+    for (uint32_t i = 0; i < k; i++) {
+        eo_sc x, s;
+        if (!eo_sc_from_canonical(&x, secrets + 32 * i)) return -1;
+        eo_sc_mul(&s, &x, &ch);
+        eo_sc_add(&s, &s, &nonce[i]);
+        eo_sc_tobytes(proof + 32 * (1 + i), &s);
+    }
+    return 0;
+}
+
+/* possession.rs:137-163.  Keys are PublicKey values: an undecodable or identity key is rejected when the key is
+ * parsed (keys/mod.rs:161-176) -> EO_MALFORMED here. */
+int eo_pop_verify(uint32_t k, const uint8_t *keys, const char *label, const uint8_t *proof) {
+    if (k == 0 || k > EO_MAX_RINGS) return -1;
+    eo_pk pk[EO_MAX_RINGS];
+    eo_sc ch, s[EO_MAX_RINGS], neg_c, expected;
+    for (uint32_t i = 0; i < k; i++)
+        if (eo_pk_from_bytes(&pk[i], keys + 32 * i)) return EO_MALFORMED;
+    if (!eo_sc_from_canonical(&ch, proof) || !eo_scalars_decode(s, proof + 32, k)) return EO_MALFORMED;
+    eo_transcript t;
+    eo_transcript_new(&t, label);
+    eo_transcript_start_proof(&t, "multi_pop");
+    for (uint32_t i = 0; i < k; i++) eo_transcript_append_message(&t, "K", keys + 32 * i, 32);
+    eo_sc_neg(&neg_c, &ch);
+    for (uint32_t i = 0; i < k; i++) {
+        eo_pt r;
+        eo_pt_double_mul_generator(&r, &neg_c, &pk[i].element, &s[i]);
+        eo_transcript_append_element(&t, "R", &r);
+    }
+    eo_transcript_challenge_scalar(&t, "c", &expected);
+    return eo_sc_eq(&expected, &ch) ? EO_OK : EO_CHALLENGE_MISMATCH;
+}
+
+typedef struct { uint32_t k; const char *label; const uint8_t *seed; size_t first; uint8_t *keys, *proofs; const uint8_t *ckeys, *cproofs; uint8_t *verdicts; } pop_ctx;
+
+static void gen_pop_item(void *p, size_t i) {
+    pop_ctx *c = (pop_ctx *)p;
+    eo_rng rng;
+    uint8_t secrets[32 * EO_MAX_RINGS];
+    item_rng(&rng, c->seed, c->first + i);
+    for (uint32_t j = 0; j < c->k; j++) eo_keypair_generate(&rng, secrets + 32 * j, c->keys + 32 * ((size_t)c->k * i + j));
+    eo_pop_prove(c->k, secrets, c->keys + 32 * (size_t)c->k * i, c->label, &rng, c->proofs + 32 * (size_t)(1 + c->k) * i);
+}
+
+/* item i: k fresh keypairs (k draws) then the proof (k draws) */
+int eo_gen_pop_batch(uint32_t k, const char *label, const uint8_t seed[32], size_t first, size_t n, uint8_t *keys,
+                     uint8_t *proofs, int threads) {
+    if (k == 0 || k > EO_MAX_RINGS) return -1;
+    pop_ctx c;
+    c.k = k; c.label = label; c.seed = seed; c.first = first; c.keys = keys; c.proofs = proofs;
+    parallel_for(gen_pop_item, &c, n, threads);
+    return 0;
+}
+
+static void verify_pop_item(void *p, size_t i) {
+    pop_ctx *c = (pop_ctx *)p;
+    c->verdicts[i] = (uint8_t)eo_pop_verify(c->k, c->ckeys + 32 * (size_t)c->k * i, c->label, c->cproofs + 32 * (size_t)(1 + c->k) * i);
+}
+
+int eo_verify_pop_batch(uint32_t k, const char *label, size_t n, const uint8_t *keys, const uint8_t *proofs, uint8_t *verdicts,
+                        int threads) {
+    if (k == 0 || k > EO_MAX_RINGS) return -1;
+    pop_ctx c;
+    c.k = k; c.label = label; c.ckeys = keys; c.cproofs = proofs; c.verdicts = verdicts;
+    parallel_for(verify_pop_item, &c, n, threads);
+    return 0;
+}

@@ -243,6 +243,28 @@ int  eo_gen_qv_batch(const uint8_t pk[32], const eo_qv_params *p, const uint8_t 
                      const uint64_t *votes /* n*options */, uint8_t *ballots, int threads);
 int  eo_verify_qv_batch(const uint8_t pk[32], const eo_qv_params *p, size_t n, const uint8_t *ballots,
                         uint8_t *verdicts, uint8_t *tally, int threads);
+/* CommitmentEquivalenceProof proofs/commitment.rs:126-248.  proof = challenge | s_r | s_v | s_c (128 B; struct field
+ * order, the reference has serde only).  prove follows tests/snapshots.rs:163-189: encrypt(value) draws r, then the
+ * commitment blinding, then e_r, e_v, e_c.  verify returns a verdict (EO_OK / EO_MALFORMED / EO_CHALLENGE_MISMATCH),
+ * -1 when the receiver key or the blinding base is invalid. */
+int  eo_commitment_equiv_prove(const uint8_t pk[32], uint64_t value, const uint8_t blinding_base[32], const char *label,
+                               eo_rng *rng, uint8_t ct[64], uint8_t commitment[32], uint8_t proof[128],
+                               uint8_t blinding_out[32] /* may be NULL */);
+int  eo_commitment_equiv_verify(const uint8_t pk[32], const uint8_t blinding_base[32], const char *label,
+                                const uint8_t ct[64], const uint8_t commitment[32], const uint8_t proof[128]);
+int  eo_gen_ceq_batch(const uint8_t pk[32], const uint8_t blinding_base[32], const char *label, const uint8_t seed[32],
+                      size_t first, size_t n, const uint64_t *values, uint8_t *cts, uint8_t *commitments, uint8_t *proofs,
+                      int threads);
+int  eo_verify_ceq_batch(const uint8_t pk[32], const uint8_t blinding_base[32], const char *label, size_t n,
+                         const uint8_t *cts, const uint8_t *commitments, const uint8_t *proofs, uint8_t *verdicts, int threads);
+
+/* ProofOfPossession proofs/possession.rs:71-163.  proof = challenge | responses[k] (32 (1 + k) B). */
+int  eo_pop_prove(uint32_t k, const uint8_t *secrets, const uint8_t *keys, const char *label, eo_rng *rng, uint8_t *proof);
+int  eo_pop_verify(uint32_t k, const uint8_t *keys, const char *label, const uint8_t *proof);
+int  eo_gen_pop_batch(uint32_t k, const char *label, const uint8_t seed[32], size_t first, size_t n, uint8_t *keys,
+                      uint8_t *proofs, int threads);
+int  eo_verify_pop_batch(uint32_t k, const char *label, size_t n, const uint8_t *keys, const uint8_t *proofs,
+                         uint8_t *verdicts, int threads);
 int  eo_hw_threads(void);
 
 #ifdef __cplusplus

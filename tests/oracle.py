@@ -453,5 +453,65 @@ def verify_qv_batch(pk, p, ballots, threads=0):
     return verdicts, tally
 
 
+# ---------------------------------------------------------------- CommitmentEquivalenceProof / ProofOfPossession
+
+def commitment_equiv_prove(pk, value, blinding_base, label, rng):
+    ct, commitment, proof, blinding = buf(64), buf(32), buf(128), buf(32)
+    assert lib().eo_commitment_equiv_prove(pk, C.c_uint64(value), bytes(blinding_base), label.encode(), C.byref(rng), ct,
+                                           commitment, proof, blinding) == 0
+    return raw(ct), raw(commitment), raw(proof), raw(blinding)
+
+
+def commitment_equiv_verify(pk, blinding_base, label, ct, commitment, proof):
+    return lib().eo_commitment_equiv_verify(pk, bytes(blinding_base), label.encode(), bytes(ct), bytes(commitment), bytes(proof))
+
+
+def gen_ceq_batch(pk, blinding_base, label, seed, values, first=0, threads=0):
+    np = _np()
+    values = np.ascontiguousarray(values, dtype=np.uint64)
+    n = values.shape[0]
+    cts, commitments, proofs = np.empty((n, 64), np.uint8), np.empty((n, 32), np.uint8), np.empty((n, 128), np.uint8)
+    assert lib().eo_gen_ceq_batch(pk, bytes(blinding_base), label.encode(), bytes(seed), C.c_size_t(first), C.c_size_t(n),
+                                  _ptr(values), _ptr(cts), _ptr(commitments), _ptr(proofs), threads) == 0
+    return cts, commitments, proofs
+
+
+def verify_ceq_batch(pk, blinding_base, label, cts, commitments, proofs, threads=0):
+    np = _np()
+    n = cts.shape[0]
+    verdicts = np.empty(n, np.uint8)
+    cts, commitments, proofs = np.ascontiguousarray(cts), np.ascontiguousarray(commitments), np.ascontiguousarray(proofs)
+    assert lib().eo_verify_ceq_batch(pk, bytes(blinding_base), label.encode(), C.c_size_t(n), _ptr(cts), _ptr(commitments),
+                                     _ptr(proofs), _ptr(verdicts), threads) == 0
+    return verdicts
+
+
+def pop_prove(secrets, keys, label, rng):
+    k = len(keys)
+    proof = buf(32 * (1 + k))
+    assert lib().eo_pop_prove(k, b"".join(secrets), b"".join(keys), label.encode(), C.byref(rng), proof) == 0
+    return raw(proof)
+
+
+def pop_verify(keys, label, proof):
+    return lib().eo_pop_verify(len(keys), b"".join(keys), label.encode(), bytes(proof))
+
+
+def gen_pop_batch(k, label, seed, n, first=0, threads=0):
+    np = _np()
+    keys, proofs = np.empty((n, k, 32), np.uint8), np.empty((n, 1 + k, 32), np.uint8)
+    assert lib().eo_gen_pop_batch(k, label.encode(), bytes(seed), C.c_size_t(first), C.c_size_t(n), _ptr(keys), _ptr(proofs), threads) == 0
+    return keys, proofs
+
+
+def verify_pop_batch(label, keys, proofs, threads=0):
+    np = _np()
+    n, k = keys.shape[0], keys.shape[1]
+    verdicts = np.empty(n, np.uint8)
+    keys, proofs = np.ascontiguousarray(keys), np.ascontiguousarray(proofs)
+    assert lib().eo_verify_pop_batch(k, label.encode(), C.c_size_t(n), _ptr(keys), _ptr(proofs), _ptr(verdicts), threads) == 0
+    return verdicts
+
+
 def hw_threads():
     return lib().eo_hw_threads()

@@ -391,3 +391,91 @@ def check_encrypt_against_reference_snapshots(e):
         assert e.verify_choice(5, cts, rings, None, single=False)[0].tolist() == [0]
     finally:
         e.set_receiver(W.receiver()[1])
+
+
+# ---------------------------------------------------------------- CommitmentEquivalenceProof / ProofOfPossession
+
+# Blinding base used in Bulletproofs (tests/snapshots.rs:253-257)
+BLINDING_BASE = bytes([140, 146, 64, 180, 86, 169, 230, 220, 101, 195, 119, 161, 4, 141, 116, 95, 148, 160,
+                       140, 219, 127, 68, 203, 205, 123, 70, 243, 64, 72, 135, 17, 52])
+
+
+def check_commitment_equiv(e, pk, n=24, label="test", seed=W.SEED_CHOICE):
+    from elastic_elgamal_b200 import EngineError, _ffi
+    e.set_blinding_base(BLINDING_BASE)
+    values = (np.arange(n, dtype=np.uint64) * 977) % 100000
+    cts, coms, proofs = O.gen_ceq_batch(pk, BLINDING_BASE, label, seed, values)
+    cts, coms, proofs = cts.copy(), coms.copy(), proofs.copy()
+    if n >= 10:
+        # commitment.rs:300-333 negative cases + malformed inputs
+        cts[1] = cts[2]                                                                   # proof for another ciphertext
+        coms[3] = np.frombuffer(O.point_add(bytes(coms[3]), W.G_ENC), np.uint8)           # commitment + G
+        proofs[4, 32:64], proofs[4, 64:96] = proofs[4, 64:96].copy(), proofs[4, 32:64].copy()
+        proofs[5, 96:] = np.frombuffer(W.BAD_SCALAR, np.uint8)
+        coms[6] = np.frombuffer(W.BAD_POINT2, np.uint8)
+        cts[7, 32:] = np.frombuffer(W.BAD_POINT, np.uint8)
+        proofs[8, 0] ^= 1
+    expected = O.verify_ceq_batch(pk, BLINDING_BASE, label, cts, coms, proofs)
+    got = e.verify_commitment_equiv(label, cts, coms, proofs)
+    assert got.tolist() == expected.tolist(), (got, expected)
+    if n >= 10:
+        assert expected[0] == O.OK and expected[1] == O.CHALLENGE_MISMATCH and expected[3] == O.CHALLENGE_MISMATCH
+        assert expected[5] == O.MALFORMED and expected[6] == O.MALFORMED and expected[7] == O.MALFORMED
+    # another transcript label rejects everything that was accepted (commitment.rs:322-332)
+    other = e.verify_commitment_equiv("other_" + label, cts, coms, proofs)
+    assert other.tolist() == O.verify_ceq_batch(pk, BLINDING_BASE, "other_" + label, cts, coms, proofs).tolist()
+    assert not (other == O.OK).any()
+    assert e.verify_commitment_equiv(label, cts[:0], coms[:0], proofs[:0]).shape == (0,)
+    for bad, status in ((bytes(32), _ffi.ERR_IDENTITY_KEY), (W.BAD_POINT, _ffi.ERR_INVALID_ELEMENT)):
+        try:
+            e.set_blinding_base(bad)
+            raise AssertionError("invalid blinding base accepted")
+        except EngineError as exc:
+            assert exc.status == status
+    try:
+        e.verify_commitment_equiv(label, cts, coms, proofs)
+        raise AssertionError("verification without a blinding base")
+    except EngineError as exc:
+        assert exc.status == _ffi.ERR_NO_RECEIVER
+    e.set_blinding_base(BLINDING_BASE)
+
+
+def check_commitment_equiv_snapshot(e):
+    """tests/snapshots.rs:163-189: the reference's own ciphertext / commitment / proof for seed 12345 verifies."""
+    import json
+    import pathlib
+    gold = json.loads((pathlib.Path(__file__).parent / "golden" / "ristretto_snapshots.json").read_text())["commitment-equiv-proof"]
+    rng = O.rng_from_u64(12345)
+    sk, pk = O.keypair(rng)
+    e.set_receiver(pk)
+    e.set_blinding_base(BLINDING_BASE)
+    ct = bytes.fromhex(gold["ciphertext"]["random_element"]) + bytes.fromhex(gold["ciphertext"]["blinded_element"])
+    pr = gold["proof"]
+    proof = b"".join(bytes.fromhex(pr[k]) for k in ("challenge", "randomness_response", "value_response", "commitment_response"))
+    com = bytes.fromhex(gold["commitment"])
+    as_np = lambda b: np.frombuffer(b, np.uint8)
+    assert e.verify_commitment_equiv("test", as_np(ct), as_np(com), as_np(proof)).tolist() == [O.OK]
+    assert e.verify_commitment_equiv("tesT", as_np(ct), as_np(com), as_np(proof)).tolist() == [O.CHALLENGE_MISMATCH]
+
+
+def check_possession(e, n=12, keys_per_proof=5, label="test_multi_PoP", seed=b"\x0b" * 32):
+    k = keys_per_proof
+    keys, proofs = O.gen_pop_batch(k, label, seed, n)
+    keys, proofs = keys.copy(), proofs.copy()
+    if n >= 8:
+        keys[1] = keys[1, ::-1].copy() if k > 1 else keys[2]            # possession.rs:55-66: keys in another order
+        proofs[2] = proofs[3]                                           # proof of other keys
+        proofs[4, 1] = np.frombuffer(W.BAD_SCALAR2, np.uint8)
+        keys[5, k - 1] = np.frombuffer(W.BAD_POINT, np.uint8)
+        keys[6, 0] = 0                                                  # identity key
+        proofs[7, 0, 0] ^= 1
+    expected = O.verify_pop_batch(label, keys, proofs)
+    got = e.verify_possession(label, keys, proofs)
+    assert got.tolist() == expected.tolist(), (got, expected)
+    if n >= 8:
+        assert expected[0] == O.OK and expected[2] == O.CHALLENGE_MISMATCH and expected[4] == O.MALFORMED
+        assert expected[5] == O.MALFORMED and expected[6] == O.MALFORMED and expected[7] in (O.CHALLENGE_MISMATCH, O.MALFORMED)
+        if k > 1:
+            assert expected[1] == O.CHALLENGE_MISMATCH
+    assert not (e.verify_possession(label + "x", keys, proofs) == O.OK).any()
+    assert e.verify_possession(label, keys[:0], proofs[:0]).shape == (0,)

@@ -182,3 +182,19 @@ def test_encrypt_verify_round_trip_large(env):
     assert (v == 0).all()
     table = O.DlogTable(0, n + 1)
     assert [table.get(O.decrypt_to_element(sk, bytes(t[k]))) for k in range(m)] == values.sum(axis=0).tolist()
+
+
+def test_commitment_equivalence(env):
+    PC.check_commitment_equiv(env[0], env[2], n=400)
+
+
+def test_commitment_equivalence_reference_snapshot(env):
+    try:
+        PC.check_commitment_equiv_snapshot(env[0])
+    finally:
+        env[0].set_receiver(env[2])
+
+
+@pytest.mark.parametrize("k", [1, 2, 5, 41, 64])
+def test_proof_of_possession(env, k):
+    PC.check_possession(env[0], n=60 if k <= 5 else 12, keys_per_proof=k)

@@ -101,3 +101,19 @@ def test_encrypt_choice(env):
 
 def test_encrypt_reference_snapshots(env):
     PC.check_encrypt_against_reference_snapshots(env[0])
+
+
+def test_commitment_equivalence(env):
+    PC.check_commitment_equiv(env[0], env[2], n=12)
+
+
+def test_commitment_equivalence_reference_snapshot(env):
+    try:
+        PC.check_commitment_equiv_snapshot(env[0])
+    finally:
+        env[0].set_receiver(env[2])
+
+
+@pytest.mark.parametrize("k", [1, 5])
+def test_proof_of_possession(env, k):
+    PC.check_possession(env[0], n=8, keys_per_proof=k)
