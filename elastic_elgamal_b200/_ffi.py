@@ -48,6 +48,11 @@ PROTOTYPES = {
     "eg_ctx_set_blinding_base": (C.c_int32, [C.c_void_p, P8]),
     "eg_verify_commitment_equiv_batch": (C.c_int32, [C.c_void_p, C.c_char_p, C.c_size_t, P8, P8, P8, P8]),
     "eg_verify_possession_batch": (C.c_int32, [C.c_void_p, C.c_char_p, C.c_uint32, C.c_size_t, P8, P8, P8]),
+    "eg_base64url_chars": (C.c_size_t, [C.c_size_t]),
+    "eg_base64url_decode_batch": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_size_t, P8, P8, P8]),
+    "eg_base64url_encode_batch": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_size_t, P8, P8]),
+    "eg_base64url_decode_batch_dev": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_size_t, P8, P8, P8]),
+    "eg_base64url_encode_batch_dev": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_size_t, P8, P8]),
     "eg_elements_validate": (C.c_int32, [C.c_void_p, C.c_size_t, P8, P8]),
     "eg_scalars_validate": (C.c_int32, [C.c_void_p, C.c_size_t, P8, P8]),
     "eg_scalars_from_wide": (C.c_int32, [C.c_void_p, C.c_size_t, P8, P8]),

@@ -230,6 +230,13 @@ __global__ void __launch_bounds__(256) k_scalars_validate(const uint8_t *s, size
     if (i < n) scalars_validate_body(i, s, ok);
 }
 
+template <int ENCODE>
+__global__ void __launch_bounds__(256) k_b64url(const b64_params P) {
+    size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= P.n * (size_t)P.groups) return;
+    if (ENCODE) b64url_encode_body(P, tid); else b64url_decode_body(P, tid);
+}
+
 __global__ void __launch_bounds__(256) k_scalars_from_wide(const uint8_t *wide, size_t n, uint8_t *out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) scalars_from_wide_body(i, wide, out);
@@ -659,6 +666,17 @@ static void launch_scalars_validate(eg_ctx *ctx, const uint8_t *sc_in, size_t n,
     EG_FOR_HOST(n, scalars_validate_body(tid, sc_in, ok))
 #else
     k_scalars_validate<<<grid_for(n, 256), 256, 0, ctx->stream>>>(sc_in, n, ok);
+#endif
+    ctx->launches++;
+}
+
+static void launch_b64url(eg_ctx *ctx, const b64_params &P, bool encode) {
+    const size_t total = P.n * (size_t)P.groups;
+#ifdef EG_HOSTSIM
+    if (encode) { EG_FOR_HOST(total, b64url_encode_body(P, tid)) } else { EG_FOR_HOST(total, b64url_decode_body(P, tid)) }
+#else
+    if (encode) k_b64url<1><<<grid_for(total, 256), 256, 0, ctx->stream>>>(P);
+    else k_b64url<0><<<grid_for(total, 256), 256, 0, ctx->stream>>>(P);
 #endif
     ctx->launches++;
 }
@@ -2104,6 +2122,89 @@ extern "C" eg_status eg_verify_shares_batch(eg_ctx *ctx, const eg_keyset *ks, si
         CU(cudaStreamSynchronize(ctx->stream));
     }
     return finish_call(ctx);
+}
+
+// =================================================================== wire format (serde.rs:19-80)
+
+static bool b64_shape(b64_params &P, size_t n, size_t bytes_per_item) {
+    if (bytes_per_item == 0 || bytes_per_item > (1u << 20)) return false;
+    P.n = n; P.bytes = (uint32_t)bytes_per_item; P.chars = (uint32_t)((4 * bytes_per_item + 2) / 3); P.groups = (P.chars + 3) / 4;
+    return true;
+}
+
+extern "C" size_t eg_base64url_chars(size_t bytes_per_item) { return (4 * bytes_per_item + 2) / 3; }
+
+extern "C" eg_status eg_base64url_decode_batch_dev(eg_ctx *ctx, size_t n, size_t bytes_per_item, const char *d_text, uint8_t *d_raw,
+                                                   uint8_t *d_ok) {
+    if (!ctx) return EG_ERR_INVALID_ARG;
+    CU(cudaSetDevice(ctx->device));
+    ctx->err.clear();
+    b64_params P;
+    if (!b64_shape(P, n, bytes_per_item)) return fail(ctx, EG_ERR_INVALID_ARG, "bytes_per_item must be in 1..2^20");
+    if (n == 0) return EG_SUCCESS;
+    if (!d_text || !d_raw || !d_ok) return fail(ctx, EG_ERR_INVALID_ARG, "null pointer");
+    P.text = (uint8_t *)d_text; P.raw = d_raw; P.ok = d_ok;
+    CU(cudaMemsetAsync(d_ok, 1, n, ctx->stream));
+    launch_b64url(ctx, P, false);
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    return EG_SUCCESS;
+}
+
+extern "C" eg_status eg_base64url_encode_batch_dev(eg_ctx *ctx, size_t n, size_t bytes_per_item, const uint8_t *d_raw, char *d_text) {
+    if (!ctx) return EG_ERR_INVALID_ARG;
+    CU(cudaSetDevice(ctx->device));
+    ctx->err.clear();
+    b64_params P;
+    if (!b64_shape(P, n, bytes_per_item)) return fail(ctx, EG_ERR_INVALID_ARG, "bytes_per_item must be in 1..2^20");
+    if (n == 0) return EG_SUCCESS;
+    if (!d_text || !d_raw) return fail(ctx, EG_ERR_INVALID_ARG, "null pointer");
+    P.text = (uint8_t *)d_text; P.raw = (uint8_t *)d_raw; P.ok = nullptr;
+    launch_b64url(ctx, P, true);
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    return EG_SUCCESS;
+}
+
+// host-buffer variants: chunked H2D -> kernel -> D2H
+static eg_status b64_host(eg_ctx *ctx, size_t n, size_t bytes_per_item, const uint8_t *src, uint8_t *dst, uint8_t *ok, bool encode) {
+    if (!ctx) return EG_ERR_INVALID_ARG;
+    CU(cudaSetDevice(ctx->device));
+    ctx->err.clear();
+    b64_params shape;
+    if (!b64_shape(shape, n, bytes_per_item)) return fail(ctx, EG_ERR_INVALID_ARG, "bytes_per_item must be in 1..2^20");
+    if (n == 0) return EG_SUCCESS;
+    if (!src || !dst || (!encode && !ok)) return fail(ctx, EG_ERR_INVALID_ARG, "null pointer");
+    const size_t in_sz = encode ? shape.bytes : shape.chars, out_sz = encode ? shape.chars : shape.bytes;
+    const size_t chunk = std::max<size_t>(1, ((size_t)256 << 20) / in_sz), cm = std::min(chunk, n);
+    TRY(ensure(ctx, ctx->in[0], cm * in_sz));
+    TRY(ensure(ctx, ctx->in[1], cm * out_sz));
+    TRY(ensure(ctx, ctx->verdicts, cm));
+    for (size_t off = 0; off < n; off += chunk) {
+        const size_t k = std::min(chunk, n - off);
+        b64_params P = shape;
+        P.n = k;
+        CU(cudaMemcpyAsync(ctx->in[0].p, src + off * in_sz, k * in_sz, cudaMemcpyHostToDevice, ctx->stream));
+        if (encode) { P.raw = (uint8_t *)ctx->in[0].p; P.text = (uint8_t *)ctx->in[1].p; P.ok = nullptr; }
+        else {
+            P.text = (uint8_t *)ctx->in[0].p; P.raw = (uint8_t *)ctx->in[1].p; P.ok = (uint8_t *)ctx->verdicts.p;
+            CU(cudaMemsetAsync(P.ok, 1, k, ctx->stream));
+        }
+        launch_b64url(ctx, P, encode);
+        CU(cudaMemcpyAsync(dst + off * out_sz, ctx->in[1].p, k * out_sz, cudaMemcpyDeviceToHost, ctx->stream));
+        if (!encode) CU(cudaMemcpyAsync(ok + off, ctx->verdicts.p, k, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    CU(cudaGetLastError());
+    return EG_SUCCESS;
+}
+
+extern "C" eg_status eg_base64url_decode_batch(eg_ctx *ctx, size_t n, size_t bytes_per_item, const char *text, uint8_t *raw, uint8_t *ok) {
+    return b64_host(ctx, n, bytes_per_item, (const uint8_t *)text, raw, ok, false);
+}
+
+extern "C" eg_status eg_base64url_encode_batch(eg_ctx *ctx, size_t n, size_t bytes_per_item, const uint8_t *raw, char *text) {
+    return b64_host(ctx, n, bytes_per_item, raw, (uint8_t *)text, nullptr, true);
 }
 
 // =================================================================== CommitmentEquivalenceProof::verify

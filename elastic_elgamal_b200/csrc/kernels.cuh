@@ -872,6 +872,60 @@ EG_HD void scalars_validate_body(size_t i, const uint8_t *s, uint8_t *ok) {
     ok[i] = sc_is_canonical_words(w) ? 1 : 0;
 }
 
+// ------------------------------------------------------------------ wire format: Base64UrlUnpadded (serde.rs:19-80)
+//
+// Human-readable serde forms of every element / scalar / proof are unpadded base64url strings (serialize_bytes
+// serde.rs:19-27, Base64Visitor :41-44).  Fields have fixed sizes, so a batch is n items of `chars` characters ->
+// `bytes` bytes with chars = ceil(4 bytes / 3).  One thread = one 4-character group (3 bytes).  Decoding is strict like
+// base64ct's: characters outside the URL-safe alphabet (including '=' padding) and non-zero trailing bits are rejected.
+EG_HD int b64url_value(uint32_t c) {
+    if (c - 'A' < 26u) return (int)(c - 'A');
+    if (c - 'a' < 26u) return (int)(c - 'a') + 26;
+    if (c - '0' < 10u) return (int)(c - '0') + 52;
+    if (c == '-') return 62;
+    if (c == '_') return 63;
+    return -1;
+}
+EG_HD uint8_t b64url_char(uint32_t v) {
+    return (uint8_t)(v < 26 ? 'A' + v : v < 52 ? 'a' + (v - 26) : v < 62 ? '0' + (v - 52) : v == 62 ? '-' : '_');
+}
+
+struct b64_params {
+    size_t n;
+    uint32_t bytes, chars, groups;      // per item; groups = ceil(chars / 4)
+    uint8_t *text;
+    uint8_t *raw;
+    uint8_t *ok;                        // decode only: pre-set to 1, cleared by any failing group
+};
+
+EG_HD void b64url_decode_body(const b64_params &P, size_t tid) {
+    const size_t item = tid / P.groups;
+    const uint32_t g = (uint32_t)(tid % P.groups);
+    const uint8_t *src = P.text + item * P.chars + 4 * g;
+    uint8_t *dst = P.raw + item * P.bytes + 3 * g;
+    const uint32_t nc = (P.chars - 4 * g) < 4 ? (P.chars - 4 * g) : 4;      // 4, or 2 / 3 in the tail group
+    int v[4] = {0, 0, 0, 0};
+    bool good = nc != 1;
+    for (uint32_t k = 0; k < nc; k++) { v[k] = b64url_value(src[k]); good = good && v[k] >= 0; }
+    const uint32_t x = ((uint32_t)(v[0] & 63) << 18) | ((uint32_t)(v[1] & 63) << 12) | ((uint32_t)(v[2] & 63) << 6) | (uint32_t)(v[3] & 63);
+    if (nc == 2) good = good && (x & 0xffffu) == 0;      // 4 unused bits of the second character
+    if (nc == 3) good = good && (x & 0xffu) == 0;        // 2 unused bits of the third character
+    const uint32_t nb = nc - 1;
+    for (uint32_t k = 0; k < nb; k++) dst[k] = (uint8_t)(x >> (16 - 8 * k));
+    if (!good) P.ok[item] = 0;
+}
+
+EG_HD void b64url_encode_body(const b64_params &P, size_t tid) {
+    const size_t item = tid / P.groups;
+    const uint32_t g = (uint32_t)(tid % P.groups);
+    const uint8_t *src = P.raw + item * P.bytes + 3 * g;
+    uint8_t *dst = P.text + item * P.chars + 4 * g;
+    const uint32_t nb = (P.bytes - 3 * g) < 3 ? (P.bytes - 3 * g) : 3;
+    uint32_t x = 0;
+    for (uint32_t k = 0; k < nb; k++) x |= (uint32_t)src[k] << (16 - 8 * k);
+    for (uint32_t k = 0; k < nb + 1; k++) dst[k] = b64url_char((x >> (18 - 6 * k)) & 63);
+}
+
 EG_HD void scalars_from_wide_body(size_t i, const uint8_t *wide, uint8_t *out) {
     uint32_t w[16];
     load32_bytes(w, wide + 64 * i);

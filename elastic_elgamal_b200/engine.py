@@ -85,6 +85,23 @@ class Engine:
         base = _u8(np.frombuffer(bytes(base), dtype=np.uint8), (32,))
         self._check(self.lib.eg_ctx_set_blinding_base(self.h, _addr(base)))
 
+    # ---- wire format: unpadded base64url of fixed-size fields (serde.rs:19-80)
+    def base64url_decode(self, text, bytes_per_item):
+        chars = self.lib.eg_base64url_chars(bytes_per_item)
+        text = _u8(text, (-1, chars))
+        n = text.shape[0]
+        raw, ok = np.empty((n, bytes_per_item), np.uint8), np.empty(n, np.uint8)
+        self._check(self.lib.eg_base64url_decode_batch(self.h, n, bytes_per_item, _addr(text), _addr(raw), _addr(ok)))
+        return raw, ok.astype(bool)
+
+    def base64url_encode(self, raw):
+        raw = _u8(raw)
+        n, b = raw.shape[0], int(np.prod(raw.shape[1:]))
+        raw = raw.reshape(n, b)
+        text = np.empty((n, self.lib.eg_base64url_chars(b)), np.uint8)
+        self._check(self.lib.eg_base64url_encode_batch(self.h, n, b, _addr(raw), _addr(text)))
+        return text
+
     # ---- group helpers
     def elements_validate(self, enc):
         enc = _u8(enc, (-1, 32))

@@ -101,6 +101,21 @@ eg_status eg_mul_generator_batch(eg_ctx *ctx, size_t n, const uint8_t *k /* n*32
 eg_status eg_ciphertexts_sum(eg_ctx *ctx, size_t n_parts, size_t n_cts, const uint8_t *parts /* n_parts*n_cts*64 */,
                              uint8_t *out /* n_cts*64 */, uint8_t *ok /* 1 */);
 
+/* ---- wire format (src/serde.rs:19-80) ----------------------------------------------------------- */
+
+/* The human-readable serde form of every element, scalar and proof is an unpadded base64url string
+ * (serialize_bytes :19-27 / Base64Visitor :41-44, base64ct::Base64UrlUnpadded).  Fields have fixed sizes, so a batch is
+ * n strings of eg_base64url_chars(bytes_per_item) = ceil(4 * bytes / 3) characters, back to back, no terminators.
+ * Decoding is strict like base64ct's: ok[i] = 0 for characters outside the URL-safe alphabet ('=' padding included)
+ * or non-zero trailing bits; raw[i] is then unspecified.  (A wrong string length is the caller's framing error.) */
+size_t    eg_base64url_chars(size_t bytes_per_item);
+eg_status eg_base64url_decode_batch(eg_ctx *ctx, size_t n, size_t bytes_per_item, const char *text, uint8_t *raw /* n*bytes */,
+                                    uint8_t *ok /* n */);
+eg_status eg_base64url_encode_batch(eg_ctx *ctx, size_t n, size_t bytes_per_item, const uint8_t *raw, char *text);
+eg_status eg_base64url_decode_batch_dev(eg_ctx *ctx, size_t n, size_t bytes_per_item, const char *d_text, uint8_t *d_raw,
+                                        uint8_t *d_ok);
+eg_status eg_base64url_encode_batch_dev(eg_ctx *ctx, size_t n, size_t bytes_per_item, const uint8_t *d_raw, char *d_text);
+
 /* ---- proofs and applications ------------------------------------------------------------------- */
 
 /* PublicKey::verify_zero (src/keys/impls.rs:59-69) -> LogEqualityProof::verify (src/proofs/log_equality.rs:153-180) */

@@ -479,3 +479,49 @@ def check_possession(e, n=12, keys_per_proof=5, label="test_multi_PoP", seed=b"\
             assert expected[1] == O.CHALLENGE_MISMATCH
     assert not (e.verify_possession(label + "x", keys, proofs) == O.OK).any()
     assert e.verify_possession(label, keys[:0], proofs[:0]).shape == (0,)
+
+
+# ---------------------------------------------------------------- wire format
+
+def check_base64url(e, n=200):
+    """Against Python's base64 module (RFC 4648 section 5, no padding = base64ct::Base64UrlUnpadded) and the reference's
+    own serde vectors (serde.rs:402-429; tests/snapshots/*.snap strings)."""
+    import base64
+    import json
+    import pathlib
+    rs = np.random.RandomState(11)
+    for size in (1, 2, 3, 31, 32, 33, 64, 96, 128, 352):
+        raw = rs.randint(0, 256, (n, size)).astype(np.uint8)
+        raw[0] = 0
+        raw[1] = 0xff
+        text = e.base64url_encode(raw)
+        expect = [base64.urlsafe_b64encode(bytes(r)).rstrip(b"=") for r in raw]
+        assert [bytes(t) for t in text] == expect
+        back, ok = e.base64url_decode(text, size)
+        assert ok.all() and (back == raw).all()
+        # strictness: padding, the standard alphabet's '+' and '/', whitespace, non-canonical trailing bits
+        bad = text.copy()
+        bad[2, 0] = ord("=")
+        bad[3, -1] = ord("+")
+        bad[4, 0] = ord("/")
+        bad[5, 0] = ord(" ")
+        bad[6, -1] = 0x80
+        _, ok = e.base64url_decode(bad, size)
+        assert ok.tolist()[:8] == [True, True, False, False, False, False, False, True]
+        if size % 3:
+            nc = text.copy()
+            v = nc[7, -1]
+            alphabet = b"ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789-_"
+            nc[7, -1] = alphabet[alphabet.index(bytes([v])) | 1]       # set an unused trailing bit
+            _, ok = e.base64url_decode(nc, size)
+            assert not ok[7] and ok[8:].all()
+    # serde.rs:402-404 / :427-429: these strings decode (the *values* are then rejected by the element / scalar checks)
+    for s_, valid_el, valid_sc in (("tNDkeYUVQWgh34d-RqaElOk7yFB8d2qCh5f4Vi2euT0", False, None),
+                                   ("nN3xf7lSOX0_zs6QPBwWHYi0Dkx2Ln_z1MPwnbzaM_8", None, False)):
+        raw, ok = e.base64url_decode(np.frombuffer(s_.encode(), np.uint8), 32)
+        assert ok.all() and bytes(raw[0]) == base64.urlsafe_b64decode(s_ + "=")
+        if valid_el is not None:
+            assert e.elements_validate(raw).tolist() == [valid_el]
+        if valid_sc is not None:
+            assert e.scalars_validate(raw).tolist() == [valid_sc]
+    assert e.base64url_decode(np.zeros((0, 43), np.uint8), 32)[0].shape == (0, 32)

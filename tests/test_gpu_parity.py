@@ -198,3 +198,7 @@ def test_commitment_equivalence_reference_snapshot(env):
 @pytest.mark.parametrize("k", [1, 2, 5, 41, 64])
 def test_proof_of_possession(env, k):
     PC.check_possession(env[0], n=60 if k <= 5 else 12, keys_per_proof=k)
+
+
+def test_base64url_wire_format(env):
+    PC.check_base64url(env[0], n=3000)
