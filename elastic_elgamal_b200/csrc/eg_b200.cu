@@ -108,6 +108,29 @@ __global__ void __launch_bounds__(EG_RING_THREADS, EG_RING_MINBLOCKS) k_prove(co
     }
 }
 
+// RangeProof::new: same persistent shape.  PHASE 0: ciphertexts + Ring::new (n_rings + 1 slots per item), 1: common challenge,
+// 2: Ring::finalize
+template <int PHASE>
+__global__ void __launch_bounds__(EG_RING_THREADS, EG_RING_MINBLOCKS) k_rprove(const rprove_params P, uint32_t *scratch_base) {
+    extern __shared__ __align__(16) uint32_t s_rtab[];
+    if (PHASE != 1) {
+        for (int k = threadIdx.x; k < EG_FCHUNK_TABLE_WORDS; k += blockDim.x) {
+            s_rtab[k] = P.table_g[k];
+            s_rtab[EG_FCHUNK_TABLE_WORDS + k] = P.table_k[k];
+        }
+        __syncthreads();
+    }
+    const size_t slots = PHASE == 0 ? P.n_rings + 1 : (PHASE == 1 ? 1 : P.n_rings);
+    const size_t total = P.n * slots, stride = (size_t)gridDim.x * blockDim.x;
+    const size_t slot = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t *scratch = scratch_base + slot * (2 * EG_VTAB_WORDS);
+    for (size_t tid = slot; tid < total; tid += stride) {
+        if (PHASE == 0) rprove_ring1_body(P, tid % P.n, (uint32_t)(tid / P.n), scratch, s_rtab, s_rtab + EG_FCHUNK_TABLE_WORDS);
+        if (PHASE == 1) rprove_common_body(P, tid);
+        if (PHASE == 2) rprove_ring2_body(P, tid % P.n, (uint32_t)(tid / P.n), scratch, s_rtab, s_rtab + EG_FCHUNK_TABLE_WORDS);
+    }
+}
+
 __global__ void __launch_bounds__(128) k_ring_hash(const ring_hash_params P) {
     size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= P.n * (size_t)P.n_slots) return;
@@ -372,6 +395,7 @@ struct eg_ctx {
     int ring_mode = 2;        // 2: k_ring (one thread per ring, chunked tables); 1: k_commit / k_ring_hash launches per equation
     int ring_grid = 0;        // resident CTAs of k_ring (queried once)
     int prove_grid[3] = {0, 0, 0};
+    int rprove_grid[3] = {0, 0, 0};
     dev_buf ring_scratch;
 };
 
@@ -539,6 +563,43 @@ static eg_status launch_prove(eg_ctx *ctx, const prove_params &P) {
     TRY(launch_prove_phase<0>(ctx, P, ctx->prove_grid[0]));
     TRY(launch_prove_phase<1>(ctx, P, ctx->prove_grid[1]));
     TRY(launch_prove_phase<2>(ctx, P, ctx->prove_grid[2]));
+#endif
+    return EG_SUCCESS;
+}
+
+#ifndef EG_HOSTSIM
+template <int PHASE>
+static eg_status launch_rprove_phase(eg_ctx *ctx, const rprove_params &P, int &grid_cache) {
+    const size_t smem = PHASE == 1 ? 0 : 2 * EG_FCHUNK_TABLE_WORDS * 4;
+    if (grid_cache == 0) {
+        CU(cudaFuncSetAttribute(k_rprove<PHASE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0, sms = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rprove<PHASE>, EG_RING_THREADS, smem));
+        CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+        if (per_sm < 1) return fail(ctx, EG_ERR_CUDA, "k_rprove does not fit on an SM");
+        grid_cache = per_sm * sms;
+    }
+    const size_t total = P.n * (size_t)(PHASE == 0 ? P.n_rings + 1 : (PHASE == 1 ? 1 : P.n_rings));
+    const unsigned grid = (unsigned)std::min<size_t>((size_t)grid_cache, (total + EG_RING_THREADS - 1) / EG_RING_THREADS);
+    TRY(ensure(ctx, ctx->ring_scratch, (size_t)grid_cache * EG_RING_THREADS * 2 * EG_VTAB_WORDS * 4));
+    k_rprove<PHASE><<<grid, EG_RING_THREADS, smem, ctx->stream>>>(P, (uint32_t *)ctx->ring_scratch.p);
+    ctx->launches++;
+    return EG_SUCCESS;
+}
+#endif
+
+static eg_status launch_rprove(eg_ctx *ctx, const rprove_params &P) {
+#ifdef EG_HOSTSIM
+    TRY(ensure(ctx, ctx->ring_scratch, 2 * EG_VTAB_WORDS * 4));
+    uint32_t *scratch = (uint32_t *)ctx->ring_scratch.p;
+    EG_FOR_HOST(P.n * (size_t)(P.n_rings + 1), rprove_ring1_body(P, tid % P.n, (uint32_t)(tid / P.n), scratch, P.table_g, P.table_k))
+    EG_FOR_HOST(P.n, rprove_common_body(P, tid))
+    EG_FOR_HOST(P.n * (size_t)P.n_rings, rprove_ring2_body(P, tid % P.n, (uint32_t)(tid / P.n), scratch, P.table_g, P.table_k))
+    ctx->launches += 3;
+#else
+    TRY(launch_rprove_phase<0>(ctx, P, ctx->rprove_grid[0]));
+    TRY(launch_rprove_phase<1>(ctx, P, ctx->rprove_grid[1]));
+    TRY(launch_rprove_phase<2>(ctx, P, ctx->rprove_grid[2]));
 #endif
     return EG_SUCCESS;
 }
@@ -1036,6 +1097,8 @@ static eg_status ensure_bool_adm(eg_ctx *ctx) {
     ctx->adm_cache_key["bool"] = {0, 1};
     return EG_SUCCESS;
 }
+
+static bool valid_label(const char *label) { return label && strlen(label) > 0 && strlen(label) < 256; }
 
 static size_t default_chunk(const eg_ctx *ctx) { return ctx->chunk_items ? ctx->chunk_items : ((size_t)1 << 18); }
 
@@ -1608,6 +1671,9 @@ const opt_entry &range_optimize(uint64_t ub, std::map<uint64_t, opt_entry> &memo
 
 uint64_t range_rings_size(const eg_range &r) { uint64_t s = 0; for (uint32_t i = 0; i < r.n_rings; i++) s += r.size[i]; return s; }
 
+// RangeDecomposition::upper_bound (range.rs:131-137): 1 + sum (size - 1) * step
+uint64_t range_upper_bound(const eg_range &r) { uint64_t u = 1; for (uint32_t i = 0; i < r.n_rings; i++) u += (r.size[i] - 1) * r.step[i]; return u; }
+
 bool range_valid(const eg_range *r) {
     if (!r || r->n_rings == 0 || r->n_rings > 64) return false;
     for (uint32_t i = 0; i < r->n_rings; i++) if (r->size[i] < 1 || r->size[i] > 4096 || r->step[i] == 0) return false;
@@ -2124,6 +2190,82 @@ extern "C" eg_status eg_verify_shares_batch(eg_ctx *ctx, const eg_keyset *ks, si
     return finish_call(ctx);
 }
 
+// =================================================================== PublicKey::encrypt_range / RangeProof::new
+
+static void range_prover_shape(rprove_params &P, const eg_range &range) {
+    uint32_t start = 0;
+    P.n_rings = range.n_rings;
+    for (uint32_t r = 0; r < range.n_rings; r++) {
+        P.sizes[r] = (uint16_t)range.size[r]; P.starts[r] = (uint16_t)start; P.steps[r] = range.step[r];
+        start += (uint32_t)range.size[r];
+    }
+    P.total = start;
+}
+
+static void range_prover_prefix(transcript &t, const eg_range &range, const char *label, const uint8_t key[32]) {
+    merlin_new(t, label, (uint32_t)strlen(label));
+    char display[4096];
+    size_t dlen = eg_range_display(&range, display, sizeof display);
+    merlin_append_message(t, EG_LBL("dom-sep"), (const uint8_t *)"encryption_range_proof", 22);     // range.rs:491
+    merlin_append_message(t, EG_LBL("range"), (const uint8_t *)display, (uint32_t)dlen);            // range.rs:492
+    host_ring_initialize(t, key);
+}
+
+extern "C" size_t eg_range_prover_draws(const eg_range *range) {
+    return range ? (size_t)range->n_rings + (size_t)range_rings_size(*range) : 0;
+}
+
+// keys/impls.rs:121-141 (encrypt_range) -> range.rs:462-534.  values[i] must be below the range's upper bound (the
+// reference panics, range.rs:365-369): checked up front, EG_ERR_INVALID_ARG.
+extern "C" eg_status eg_encrypt_range_batch(eg_ctx *ctx, const eg_range *range, const char *label, size_t n, const uint64_t *values,
+                                            const uint8_t *wide_rand, uint8_t *cts, uint8_t *partials, uint8_t *rings) {
+    TRY(begin_call(ctx));
+    if (!range || !range_valid(range)) return fail(ctx, EG_ERR_INVALID_ARG, "invalid range decomposition");
+    if (!valid_label(label)) return fail(ctx, EG_ERR_INVALID_ARG, "transcript label must be 1..255 bytes");
+    if (n == 0) return EG_SUCCESS;
+    const uint32_t R = range->n_rings, T = (uint32_t)range_rings_size(*range);
+    if (!values || !wide_rand || !cts || !rings || (R > 1 && !partials)) return fail(ctx, EG_ERR_INVALID_ARG, "null pointer");
+    const uint64_t ub = range_upper_bound(*range);
+    for (size_t i = 0; i < n; i++)
+        if (values[i] >= ub) return fail(ctx, EG_ERR_INVALID_ARG, "a value is outside the range");
+    const size_t draws = (size_t)R + T, ring_stride = 32 * (1 + (size_t)T), part_stride = 64 * (size_t)(R - 1);
+    const size_t chunk = std::max<size_t>(256, default_chunk(ctx) * 8 / (T + R)), cm = std::min(chunk, n);
+    TRY(ensure(ctx, ctx->in[0], cm * 8));
+    TRY(ensure(ctx, ctx->in[1], cm * draws * 64));
+    TRY(ensure(ctx, ctx->in[2], cm * 64));
+    TRY(ensure(ctx, ctx->in[3], cm * ring_stride));
+    TRY(ensure(ctx, ctx->misc, std::max<size_t>(cm * part_stride, 4096)));
+    TRY(ensure(ctx, ctx->pts, cm * 2 * R * 128));
+    TRY(ensure(ctx, ctx->enc, cm * 2 * R * 32));
+    TRY(ensure(ctx, ctx->commit, cm * 2 * R * 32));
+    TRY(ensure(ctx, ctx->res_big, cm * 2 * R * 32));
+    TRY(ensure(ctx, ctx->chal, cm * 32));
+    rprove_params P;
+    memset(&P, 0, sizeof P);
+    range_prover_shape(P, *range);
+    range_prover_prefix(P.prefix, *range, label, ctx->key);
+    P.values = (const uint64_t *)ctx->in[0].p; P.value_stride = 1;
+    P.wide = (const uint8_t *)ctx->in[1].p; P.wide_stride = draws * 64;
+    P.ct_out = (uint8_t *)ctx->in[2].p; P.ct_stride = 64;
+    P.partial_out = (uint8_t *)ctx->misc.p; P.partial_stride = part_stride;
+    P.ring_out = (uint8_t *)ctx->in[3].p; P.ring_stride = ring_stride;
+    P.pts = (uint32_t *)ctx->pts.p; P.enc = (uint32_t *)ctx->enc.p; P.sec = (uint32_t *)ctx->res_big.p;
+    P.commit = (uint32_t *)ctx->commit.p; P.chal = (uint32_t *)ctx->chal.p;
+    P.table_g = ctx->d_table_g; P.table_k = ctx->d_table_k;
+    for (size_t off = 0; off < n; off += chunk) {
+        const size_t k = std::min(chunk, n - off);
+        P.n = k;
+        CU(cudaMemcpyAsync(ctx->in[0].p, values + off, k * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->in[1].p, wide_rand + off * draws * 64, k * draws * 64, cudaMemcpyHostToDevice, ctx->stream));
+        TRY(launch_rprove(ctx, P));
+        CU(cudaMemcpyAsync(cts + off * 64, ctx->in[2].p, k * 64, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(rings + off * ring_stride, ctx->in[3].p, k * ring_stride, cudaMemcpyDeviceToHost, ctx->stream));
+        if (R > 1) CU(cudaMemcpyAsync(partials + off * part_stride, ctx->misc.p, k * part_stride, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    return finish_call(ctx);
+}
+
 // =================================================================== wire format (serde.rs:19-80)
 
 static bool b64_shape(b64_params &P, size_t n, size_t bytes_per_item) {
@@ -2209,7 +2351,6 @@ extern "C" eg_status eg_base64url_encode_batch(eg_ctx *ctx, size_t n, size_t byt
 
 // =================================================================== CommitmentEquivalenceProof::verify
 
-static bool valid_label(const char *label) { return label && strlen(label) > 0 && strlen(label) < 256; }
 
 static void sigma_set_msg(sigma_msg &g, uint8_t kind, const char *label, uint32_t index, uint32_t count) {
     memset(&g, 0, sizeof g);

@@ -616,6 +616,214 @@ EG_HD void prove_ring2_body(const prove_params &P, size_t item, uint32_t k, uint
     store32_bytes(resp + 32, s.v);
 }
 
+// ------------------------------------------------------------------ proving side: RangeProof::new (general rings)
+//
+// PublicKey::encrypt_range (keys/impls.rs:121-141) = RangeProof::new (range.rs:462-473): encrypt the value, decompose it
+// over the rings of the RangeDecomposition (range.rs decompose), encrypt every partial value but the last one
+// (RingProofBuilder::add_value ring.rs:460-469), derive the last partial ciphertext from the others (range.rs:520-529),
+// and close all rings with a common challenge.  Caller-supplied randomness, one 64-byte block per draw, in the
+// reference's order:
+//   block 0                      r of the main ciphertext (CiphertextWithValue::new)
+//   then per ring k, in order:   [r_k unless k is the last ring]  x_k  s_{k,eq} for eq = vi_k+1 .. size_k-1   (Ring::new)
+//   then per ring k, in order:   s_{k,eq} for eq = 0 .. vi_k-1                                               (Ring::finalize)
+// n_rings + sum(size_k) blocks per item.  The last ring's ciphertext is ([r_last]G, [v_last]G + [r_last]K) with
+// r_last = r - sum r_k: the same group elements as `ciphertext - sum partial` (ExtendedCiphertext arithmetic tracks the
+// randomness, encryption.rs:329-357), computed without touching the other rings' points.
+struct rprove_params {
+    size_t n;
+    uint32_t n_rings, total;                 // total = sum of ring sizes
+    uint16_t sizes[EG_MAX_RINGS], starts[EG_MAX_RINGS];
+    uint64_t steps[EG_MAX_RINGS];
+    const uint64_t *values; size_t value_stride;     // value of item i = values[i * value_stride]
+    const uint8_t *wide; size_t wide_stride;         // bytes between the first blocks of consecutive items
+    uint8_t *ct_out; size_t ct_stride;               // 64 B per item
+    uint8_t *partial_out; size_t partial_stride;     // 64 (n_rings - 1) B per item
+    uint8_t *ring_out; size_t ring_stride;           // 32 (1 + total) B per item: common challenge | responses
+    transcript prefix;                               // Transcript::new(label) + "encryption_range_proof" + "range" + initialize_transcript
+    uint32_t *pts, *enc, *sec, *commit, *chal;       // planar scratch; ring k: pts / enc / commit 2k, 2k+1; sec 2k = r_k, 2k+1 = x_k
+    uint32_t *ct_sec;                                // optional planar scalar (index 0): r of the main ciphertext
+    const uint32_t *table_g, *table_k;
+};
+
+EG_HD void rprove_draw(sc &out, const rprove_params &P, size_t item, uint32_t pos) {
+    uint32_t w[16];
+    const uint8_t *b = P.wide + item * P.wide_stride + (size_t)pos * 64;
+    load32_bytes(w, b);
+    load32_bytes(w + 8, b + 32);
+    sc_from_wide_words(out, w);
+}
+
+// value index of ring k and the positions of its first phase-0 / phase-2 draws (RangeDecomposition::decompose)
+struct rprove_pos { uint32_t vi, pos0, pos2; };
+
+EG_HD rprove_pos rprove_layout(const rprove_params &P, uint64_t value, uint32_t k) {
+    rprove_pos out = {0, 0, 0};
+    uint32_t p0 = 1, fin_before = 0;
+    for (uint32_t i = 0; i < P.n_rings; i++) {
+        uint64_t idx = value / P.steps[i];
+        if (idx > (uint64_t)P.sizes[i] - 1) idx = (uint64_t)P.sizes[i] - 1;
+        value -= idx * P.steps[i];
+        if (i == k) { out.vi = (uint32_t)idx; out.pos0 = p0; out.pos2 = fin_before; }
+        p0 += (i + 1 < P.n_rings ? 1u : 0u) + 1u + (P.sizes[i] - 1u - (uint32_t)idx);
+        if (i < k) fin_before += (uint32_t)idx;
+    }
+    out.pos2 += p0;         // finalize draws start after every ring's Ring::new draws
+    return out;
+}
+
+// out = ([r]G, [v]G + [r]K) as points and encodings
+EG_HD void rprove_encrypt(ge_ext &R, ge_ext &B, uint32_t enc_ct[16], const sc &r, uint64_t v, const uint32_t *tab_g, const uint32_t *tab_k) {
+    sc hr, hv;
+    sc_half(hr, r);
+    sc_half(hv, sc_from_u64(v));
+    ge_ext qr, qb;
+    ge_eval64(qr, nullptr, hr, 1, tab_g, hr, tab_g, hr);
+    ge_eval64(qb, nullptr, hr, v ? 2 : 1, tab_k, hr, tab_g, hv);
+    ge_double_compress2(enc_ct, enc_ct + 8, qr, qb);
+    ge_dbl(R, qr);
+    ge_dbl(B, qb);
+}
+
+// forged equation with admissible value [a]G: (cg, ck) = ([s]G - [e]R, [s]K - [e](B - [a]G)), window tables prebuilt
+EG_HD void rprove_forge(uint32_t cg[8], uint32_t ck[8], const uint32_t *tab_r, const uint32_t *tab_b, const sc &e, const sc &s, uint64_t a,
+                        const uint32_t *tab_g, const uint32_t *tab_k) {
+    sc ne, hne, hs, hea;
+    sc_neg(ne, e);
+    sc_half(hne, ne);
+    sc_half(hs, s);
+    ge_ext qg, qk;
+    ge_eval64(qg, tab_r, hne, 1, tab_g, hs, tab_g, hs);
+    if (a) {
+        sc ea;
+        sc_mul(ea, e, sc_from_u64(a));
+        sc_half(hea, ea);
+        ge_eval64(qk, tab_b, hne, 2, tab_k, hs, tab_g, hea);
+    } else {
+        ge_eval64(qk, tab_b, hne, 1, tab_k, hs, tab_k, hs);
+    }
+    ge_double_compress2(cg, ck, qg, qk);
+}
+
+// phase 0, one thread per (item, slot): slot < n_rings = ring `slot` (ciphertext + Ring::new); slot == n_rings = main ciphertext
+EG_HD void rprove_ring1_body(const rprove_params &P, size_t item, uint32_t slot, uint32_t *scratch, const uint32_t *tab_g, const uint32_t *tab_k) {
+    const uint64_t value = P.values[item * P.value_stride];
+    const uint32_t Rn = P.n_rings;
+    uint32_t enc_ct[16];
+    ge_ext R, B;
+    if (slot == Rn) {
+        sc r;
+        rprove_draw(r, P, item, 0);
+        rprove_encrypt(R, B, enc_ct, r, value, tab_g, tab_k);
+        uint8_t *o = P.ct_out + item * P.ct_stride;
+        store32_bytes(o, enc_ct);
+        store32_bytes(o + 32, enc_ct + 8);
+        if (P.ct_sec) planar_store_words(P.ct_sec, P.n, 0, 8, item, r.v);
+        return;
+    }
+    const uint32_t k = slot, m = P.sizes[k];
+    const rprove_pos L = rprove_layout(P, value, k);
+    const bool last = (k + 1 == Rn);
+    sc r, x;
+    if (!last) {
+        rprove_draw(r, P, item, L.pos0);
+    } else {
+        // r_last = r_ct - sum of the other rings' r (range.rs:520-521)
+        rprove_draw(r, P, item, 0);
+#pragma unroll 1
+        for (uint32_t i = 0; i + 1 < Rn; i++) {
+            sc ri;
+            rprove_draw(ri, P, item, rprove_layout(P, value, i).pos0);
+            sc_sub(r, r, ri);
+        }
+    }
+    rprove_encrypt(R, B, enc_ct, r, (uint64_t)L.vi * P.steps[k], tab_g, tab_k);
+    if (!last) {
+        uint8_t *o = P.partial_out + item * P.partial_stride + 64 * (size_t)k;
+        store32_bytes(o, enc_ct);
+        store32_bytes(o + 32, enc_ct + 8);
+    }
+    const uint32_t xpos = L.pos0 + (last ? 0u : 1u);
+    rprove_draw(x, P, item, xpos);
+    planar_store_words(P.enc, P.n, 2 * k, 8, item, enc_ct);
+    planar_store_words(P.enc, P.n, 2 * k + 1, 8, item, enc_ct + 8);
+    planar_store_point(P.pts, P.n, 2 * k, item, R);
+    planar_store_point(P.pts, P.n, 2 * k + 1, item, B);
+    planar_store_words(P.sec, P.n, 2 * k, 8, item, r.v);
+    planar_store_words(P.sec, P.n, 2 * k + 1, 8, item, x.v);
+    // Ring::new (ring.rs:97-131): commitments of the real equation, then the forged equations above it
+    uint32_t cg[8], ck[8];
+    prove_commit_pair(cg, ck, x, tab_g, tab_k);
+    if (L.vi + 1 < m) {
+        uint32_t *tab_r = scratch, *tab_b = scratch + EG_VTAB_WORDS;
+        ge_vtab_build(tab_r, R);
+        ge_vtab_build(tab_b, B);
+        transcript rt;
+        ring_transcript_start(rt, P.prefix, enc_ct, k);
+        uint8_t *resp = P.ring_out + item * P.ring_stride + 32 * (1 + (size_t)P.starts[k]);
+#pragma unroll 1
+        for (uint32_t eq = L.vi + 1; eq < m; eq++) {
+            sc e, s_;
+            ring_next_challenge(e, rt, eq - 1, cg, ck);
+            rprove_draw(s_, P, item, xpos + (eq - L.vi));
+            store32_bytes(resp + 32 * (size_t)eq, s_.v);
+            rprove_forge(cg, ck, tab_r, tab_b, e, s_, (uint64_t)eq * P.steps[k], tab_g, tab_k);
+        }
+    }
+    planar_store_words(P.commit, P.n, 2 * k, 8, item, cg);
+    planar_store_words(P.commit, P.n, 2 * k + 1, 8, item, ck);
+}
+
+// phase 1, one thread per item: common challenge (Ring::aggregate ring.rs:138-160)
+EG_HD void rprove_common_body(const rprove_params &P, size_t item) {
+    transcript t = P.prefix;
+    uint32_t w[8];
+#pragma unroll 1
+    for (uint32_t k = 0; k < P.n_rings; k++) {
+        planar_load_words(w, P.commit, P.n, 2 * k, 8, item);
+        merlin_append_words(t, EG_LBL("R_G"), w, 8);
+        planar_load_words(w, P.commit, P.n, 2 * k + 1, 8, item);
+        merlin_append_words(t, EG_LBL("R_K"), w, 8);
+    }
+    sc e0;
+    merlin_challenge_scalar(t, EG_LBL("c"), e0);
+    planar_store_words(P.chal, P.n, 0, 8, item, e0.v);
+    store32_bytes(P.ring_out + item * P.ring_stride, e0.v);
+}
+
+// phase 2, one thread per (item, ring k): Ring::finalize (ring.rs:162-195)
+EG_HD void rprove_ring2_body(const rprove_params &P, size_t item, uint32_t k, uint32_t *scratch, const uint32_t *tab_g, const uint32_t *tab_k) {
+    const uint64_t value = P.values[item * P.value_stride];
+    const rprove_pos L = rprove_layout(P, value, k);
+    sc e, r, x, s;
+    planar_load_words(e.v, P.chal, P.n, 0, 8, item);
+    planar_load_words(r.v, P.sec, P.n, 2 * k, 8, item);
+    planar_load_words(x.v, P.sec, P.n, 2 * k + 1, 8, item);
+    uint8_t *resp = P.ring_out + item * P.ring_stride + 32 * (1 + (size_t)P.starts[k]);
+    if (L.vi > 0) {
+        ge_ext R, B;
+        planar_load_point(R, P.pts, P.n, 2 * k, item);
+        planar_load_point(B, P.pts, P.n, 2 * k + 1, item);
+        uint32_t *tab_r = scratch, *tab_b = scratch + EG_VTAB_WORDS;
+        ge_vtab_build(tab_r, R);
+        ge_vtab_build(tab_b, B);
+        uint32_t enc_ct[16], cg[8], ck[8];
+        planar_load_words(enc_ct, P.enc, P.n, 2 * k, 8, item);
+        planar_load_words(enc_ct + 8, P.enc, P.n, 2 * k + 1, 8, item);
+        transcript rt;
+        ring_transcript_start(rt, P.prefix, enc_ct, k);
+#pragma unroll 1
+        for (uint32_t eq = 0; eq < L.vi; eq++) {
+            sc s_;
+            rprove_draw(s_, P, item, L.pos2 + eq);
+            store32_bytes(resp + 32 * (size_t)eq, s_.v);
+            rprove_forge(cg, ck, tab_r, tab_b, e, s_, (uint64_t)eq * P.steps[k], tab_g, tab_k);
+            ring_next_challenge(e, rt, eq, cg, ck);
+        }
+    }
+    sc_muladd(s, e, r, x);
+    store32_bytes(resp + 32 * (size_t)L.vi, s.v);
+}
+
 // Outer transcript: absorb every ring's terminal commitments, compare with the common challenge (ring.rs:364-373)
 struct ring_final_params {
     in_bufs in;

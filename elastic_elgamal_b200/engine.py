@@ -230,6 +230,18 @@ class Engine:
                                                    _addr(partials) if rng.n_rings > 1 else None, _addr(rings), _addr(v)))
         return v
 
+    def encrypt_range(self, rng, label, values, wide_rand):
+        values = np.ascontiguousarray(values, dtype=np.uint64).reshape(-1)
+        n = values.shape[0]
+        draws = self.lib.eg_range_prover_draws(C.byref(rng))
+        wide_rand = _u8(wide_rand, (n, draws, 64))
+        cts = np.empty((n, 64), np.uint8)
+        partials = np.empty((n, max(0, rng.n_rings - 1), 64), np.uint8)
+        rings = np.empty((n, 1 + rng.rings_size, 32), np.uint8)
+        self._check(self.lib.eg_encrypt_range_batch(self.h, C.byref(rng), label.encode(), n, _addr(values), _addr(wide_rand),
+                                                    _addr(cts), _addr(partials) if rng.n_rings > 1 else None, _addr(rings)))
+        return cts, partials, rings
+
     # ---- QuadraticVotingBallot
     def qv_params(self, options, credits):
         p = _ffi.QvParams()

@@ -229,6 +229,19 @@ eg_status eg_encrypt_choice_batch(eg_ctx *ctx, size_t n, uint32_t options, int s
                                   const uint8_t *wide_rand /* n*(3*options+single)*64 */, uint8_t *choices /* n*options*64 */,
                                   uint8_t *ring_proofs /* n*(1+2*options)*32 */, uint8_t *sum_proofs /* n*64 */);
 
+/* PublicKey::encrypt_range (src/keys/impls.rs:121-141) = RangeProof::new (src/proofs/range.rs:462-534) with
+ * `Transcript::new(label)`.  Item i consumes eg_range_prover_draws(range) = n_rings + sum(ring sizes) blocks in the
+ * reference's draw order: r of the ciphertext; per ring, in order: r of the partial ciphertext (not for the last ring,
+ * which is derived, range.rs:520-529), the ring's nonce, the forged responses above the value's index (ring.rs:97-131);
+ * then per ring, in order, the forged responses below it (Ring::finalize ring.rs:162-195).  values[i] must be below the
+ * range's upper bound (the reference panics, range.rs:365-369): EG_ERR_INVALID_ARG otherwise.
+ * Outputs use the layouts eg_verify_range_batch reads. */
+size_t    eg_range_prover_draws(const eg_range *range);
+eg_status eg_encrypt_range_batch(eg_ctx *ctx, const eg_range *range, const char *transcript_label, size_t n,
+                                 const uint64_t *values /* n */, const uint8_t *wide_rand /* n*draws*64 */,
+                                 uint8_t *cts /* n*64 */, uint8_t *partials /* n*(n_rings-1)*64 */,
+                                 uint8_t *ring_proofs /* n*(1+sum sizes)*32 */);
+
 /* ---- device-pointer variants (inputs already resident in HBM; same semantics) ------------------- */
 eg_status eg_verify_bool_batch_dev(eg_ctx *ctx, size_t n, const uint8_t *d_cts, const uint8_t *d_proofs, uint8_t *d_verdicts);
 eg_status eg_verify_choice_batch_dev(eg_ctx *ctx, size_t n, uint32_t options, int single, const uint8_t *d_choices,

@@ -525,3 +525,49 @@ def check_base64url(e, n=200):
         if valid_sc is not None:
             assert e.scalars_validate(raw).tolist() == [valid_sc]
     assert e.base64url_decode(np.zeros((0, 43), np.uint8), 32)[0].shape == (0, 32)
+
+
+# ---------------------------------------------------------------- RangeProof::new on the GPU
+
+def check_encrypt_range(e, pk, upper_bound, n=12, label="ciphertext_range", seed=W.SEED_CHOICE):
+    """Same ChaCha blocks as the oracle's prover (item i: stream i << 20) => byte-identical ciphertexts, partial
+    ciphertexts and ring proofs; the GPU verifier accepts them."""
+    spec = O.range_optimal(upper_bound)
+    espec = to_engine_range(e, spec)
+    rnd = random.Random(upper_bound)
+    values = [0, upper_bound - 1] + [rnd.randrange(upper_bound) for _ in range(max(0, n - 2))]
+    values = np.array(values[:n], np.uint64)
+    cts, partials, rings = O.gen_range_batch(pk, spec, label, seed, values)
+    draws = e.lib.eg_range_prover_draws(O.C.byref(espec))
+    assert draws == spec.n_rings + spec.rings_size
+    wide = np.frombuffer(b"".join(item_blocks(seed, i, draws) for i in range(n)), np.uint8).reshape(n, draws, 64)
+    g_cts, g_partials, g_rings = e.encrypt_range(espec, label, values, wide)
+    assert (g_cts == cts).all()
+    assert (g_partials == partials).all()
+    assert (g_rings == rings).all()
+    assert (e.verify_range(espec, label, g_cts, g_partials, g_rings) == 0).all()
+    from elastic_elgamal_b200 import EngineError, _ffi
+    try:
+        e.encrypt_range(espec, label, np.array([upper_bound], np.uint64), wide[:1])
+        raise AssertionError("out-of-range value accepted")
+    except EngineError as exc:
+        assert exc.status == _ffi.ERR_INVALID_ARG
+
+
+def check_encrypt_range_reference_snapshot(e):
+    """tests/snapshots.rs:96-109: encrypt_range(optimal(100), 42) from seed 12345, byte for byte."""
+    import json
+    import pathlib
+    gold = json.loads((pathlib.Path(__file__).parent / "golden" / "ristretto_snapshots.json").read_text())["range-encryption"]
+    rng = O.rng_from_u64(12345)
+    sk, pk = O.keypair(rng)
+    e.set_receiver(pk)
+    espec = e.range_optimal(100)
+    draws = e.lib.eg_range_prover_draws(O.C.byref(espec))
+    wide = np.frombuffer(b"".join(O.rng_block(rng) for _ in range(draws)), np.uint8).reshape(1, draws, 64)
+    cts, partials, rings = e.encrypt_range(espec, "ciphertext_range", np.array([42], np.uint64), wide)
+    hx = bytes.fromhex
+    assert bytes(cts[0]) == hx(gold["ciphertext"]["random_element"]) + hx(gold["ciphertext"]["blinded_element"])
+    pr = gold["proof"]
+    assert bytes(partials[0].reshape(-1)) == b"".join(hx(c["random_element"]) + hx(c["blinded_element"]) for c in pr["partial_ciphertexts"])
+    assert bytes(rings[0].reshape(-1)) == hx(pr["common_challenge"]) + b"".join(hx(x) for x in pr["ring_responses"])

@@ -202,3 +202,15 @@ def test_proof_of_possession(env, k):
 
 def test_base64url_wire_format(env):
     PC.check_base64url(env[0], n=3000)
+
+
+@pytest.mark.parametrize("ub", [2, 5, 16, 21, 100, 1000, 65536])
+def test_encrypt_range(env, ub):
+    PC.check_encrypt_range(env[0], env[2], ub, n=40)
+
+
+def test_encrypt_range_reference_snapshot(env):
+    try:
+        PC.check_encrypt_range_reference_snapshot(env[0])
+    finally:
+        env[0].set_receiver(env[2])
