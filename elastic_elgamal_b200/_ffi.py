@@ -80,6 +80,8 @@ PROTOTYPES = {
     "eg_encrypt_choice_batch": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_uint32, C.c_int, P8, P8, P8, P8, P8]),
     "eg_range_prover_draws": (C.c_size_t, [C.POINTER(Range)]),
     "eg_encrypt_range_batch": (C.c_int32, [C.c_void_p, C.POINTER(Range), C.c_char_p, C.c_size_t, P8, P8, P8, P8, P8]),
+    "eg_qv_prover_draws": (C.c_size_t, [C.POINTER(QvParams)]),
+    "eg_encrypt_qv_batch": (C.c_int32, [C.c_void_p, C.POINTER(QvParams), C.c_size_t, P8, P8, P8]),
     "eg_kernel_launch_count": (C.c_uint64, [C.c_void_p]),
     "eg_last_timings": (C.c_int32, [C.c_void_p, C.POINTER(C.c_float * 5)]),
     "eg_ctx_stream": (C.c_void_p, [C.c_void_p]),

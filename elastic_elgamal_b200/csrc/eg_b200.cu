@@ -131,6 +131,19 @@ __global__ void __launch_bounds__(EG_RING_THREADS, EG_RING_MINBLOCKS) k_rprove(c
     }
 }
 
+// SumOfSquaresProof::new, one thread per item; persistent grid, chunked fixed-base tables in shared memory
+__global__ void __launch_bounds__(EG_RING_THREADS, EG_RING_MINBLOCKS) k_sumsq_prove(const sumsq_prove_params P) {
+    extern __shared__ __align__(16) uint32_t s_rtab[];
+    for (int k = threadIdx.x; k < EG_FCHUNK_TABLE_WORDS; k += blockDim.x) {
+        s_rtab[k] = P.table_g[k];
+        s_rtab[EG_FCHUNK_TABLE_WORDS + k] = P.table_k[k];
+    }
+    __syncthreads();
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x; tid < P.n; tid += stride)
+        sumsq_prove_body(P, tid, s_rtab, s_rtab + EG_FCHUNK_TABLE_WORDS);
+}
+
 __global__ void __launch_bounds__(128) k_ring_hash(const ring_hash_params P) {
     size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= P.n * (size_t)P.n_slots) return;
@@ -396,6 +409,7 @@ struct eg_ctx {
     int ring_grid = 0;        // resident CTAs of k_ring (queried once)
     int prove_grid[3] = {0, 0, 0};
     int rprove_grid[3] = {0, 0, 0};
+    int sumsq_prove_grid = 0;
     dev_buf ring_scratch;
 };
 
@@ -601,6 +615,26 @@ static eg_status launch_rprove(eg_ctx *ctx, const rprove_params &P) {
     TRY(launch_rprove_phase<1>(ctx, P, ctx->rprove_grid[1]));
     TRY(launch_rprove_phase<2>(ctx, P, ctx->rprove_grid[2]));
 #endif
+    return EG_SUCCESS;
+}
+
+static eg_status launch_sumsq_prove(eg_ctx *ctx, const sumsq_prove_params &P) {
+#ifdef EG_HOSTSIM
+    EG_FOR_HOST(P.n, sumsq_prove_body(P, tid, P.table_g, P.table_k))
+#else
+    const size_t smem = 2 * EG_FCHUNK_TABLE_WORDS * 4;
+    if (ctx->sumsq_prove_grid == 0) {
+        CU(cudaFuncSetAttribute(k_sumsq_prove, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0, sms = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sumsq_prove, EG_RING_THREADS, smem));
+        CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+        if (per_sm < 1) return fail(ctx, EG_ERR_CUDA, "k_sumsq_prove does not fit on an SM");
+        ctx->sumsq_prove_grid = per_sm * sms;
+    }
+    const unsigned grid = (unsigned)std::min<size_t>((size_t)ctx->sumsq_prove_grid, (P.n + EG_RING_THREADS - 1) / EG_RING_THREADS);
+    k_sumsq_prove<<<grid, EG_RING_THREADS, smem, ctx->stream>>>(P);
+#endif
+    ctx->launches++;
     return EG_SUCCESS;
 }
 
@@ -2261,6 +2295,111 @@ extern "C" eg_status eg_encrypt_range_batch(eg_ctx *ctx, const eg_range *range, 
         CU(cudaMemcpyAsync(cts + off * 64, ctx->in[2].p, k * 64, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaMemcpyAsync(rings + off * ring_stride, ctx->in[3].p, k * ring_stride, cudaMemcpyDeviceToHost, ctx->stream));
         if (R > 1) CU(cudaMemcpyAsync(partials + off * part_stride, ctx->misc.p, k * part_stride, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    return finish_call(ctx);
+}
+
+// =================================================================== QuadraticVotingBallot::new
+
+extern "C" size_t eg_qv_prover_draws(const eg_qv_params *p) {
+    if (!p) return 0;
+    return (size_t)p->options * eg_range_prover_draws(&p->vote_range) + eg_range_prover_draws(&p->credit_range) + 1 + 2 * (size_t)p->options;
+}
+
+// quadratic_voting.rs:234-284: per option RangeProof::new over the vote range ("quadratic_voting_variant"), RangeProof::new
+// of credit = sum votes^2 over the credit range ("quadratic_voting_credit_range"), SumOfSquaresProof::new
+// ("quadratic_voting_credit_equiv"); randomness is consumed in that order.  A vote or a credit outside its range makes the
+// reference panic (range.rs:365-369): EG_ERR_INVALID_ARG here.
+extern "C" eg_status eg_encrypt_qv_batch(eg_ctx *ctx, const eg_qv_params *params, size_t n, const uint64_t *votes, const uint8_t *wide_rand,
+                                         uint8_t *ballots) {
+    TRY(begin_call(ctx));
+    if (!params || params->options == 0 || params->options >= EG_MSM_MAXV || !range_valid(&params->vote_range) ||
+        !range_valid(&params->credit_range))
+        return fail(ctx, EG_ERR_INVALID_ARG, "invalid quadratic voting parameters (options must be in 1..15)");
+    if (n == 0) return EG_SUCCESS;
+    if (!votes || !wide_rand || !ballots) return fail(ctx, EG_ERR_INVALID_ARG, "null pointer");
+    const eg_qv_params &qp = *params;
+    const uint32_t m = qp.options, Rv = qp.vote_range.n_rings, Rc = qp.credit_range.n_rings;
+    const uint32_t Tv = (uint32_t)range_rings_size(qp.vote_range), Tc = (uint32_t)range_rings_size(qp.credit_range);
+    const size_t vsz = range_item_size(qp.vote_range), csz = range_item_size(qp.credit_range), bsz = eg_qv_ballot_size(&qp);
+    const size_t Dv = (size_t)Rv + Tv, Dc = (size_t)Rc + Tc, D = m * Dv + Dc + 1 + 2 * (size_t)m;
+    const uint64_t ub_v = range_upper_bound(qp.vote_range), ub_c = range_upper_bound(qp.credit_range);
+    std::vector<uint64_t> credits(n);
+    for (size_t i = 0; i < n; i++) {
+        uint64_t credit = 0;
+        for (uint32_t o = 0; o < m; o++) {
+            const uint64_t v = votes[i * m + o];
+            if (v >= ub_v) return fail(ctx, EG_ERR_INVALID_ARG, "a vote is outside the vote range");
+            credit += v * v;
+        }
+        if (credit >= ub_c) return fail(ctx, EG_ERR_INVALID_ARG, "the credit of a ballot is outside the credit range");
+        credits[i] = credit;
+    }
+    const size_t chunk = std::max<size_t>(256, default_chunk(ctx) / 8), cm = std::min(chunk, n);
+    const uint32_t Rmax = std::max(Rv, Rc);
+    TRY(ensure(ctx, ctx->in[0], cm * m * 8));
+    TRY(ensure(ctx, ctx->in[1], cm * D * 64));
+    TRY(ensure(ctx, ctx->in[2], cm * bsz));
+    TRY(ensure(ctx, ctx->in[3], cm * 8));
+    TRY(ensure(ctx, ctx->pts, cm * m * 2 * Rmax * 128));
+    TRY(ensure(ctx, ctx->enc, cm * m * 2 * Rmax * 32));
+    TRY(ensure(ctx, ctx->commit, cm * m * 2 * Rmax * 32));
+    TRY(ensure(ctx, ctx->res_big, cm * m * 2 * Rmax * 32));
+    TRY(ensure(ctx, ctx->chal, cm * m * 32));
+    TRY(ensure(ctx, ctx->res[1], cm * m * 32));
+    TRY(ensure(ctx, ctx->res[2], cm * 32));
+    for (size_t off = 0; off < n; off += chunk) {
+        const size_t k = std::min(chunk, n - off);
+        CU(cudaMemcpyAsync(ctx->in[0].p, votes + off * m, k * m * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->in[1].p, wide_rand + off * D * 64, k * D * 64, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->in[3].p, credits.data() + off, k * 8, cudaMemcpyHostToDevice, ctx->stream));
+        uint8_t *d_ballots = (uint8_t *)ctx->in[2].p;
+        const uint8_t *d_wide = (const uint8_t *)ctx->in[1].p;
+        rprove_params P;
+        // ---- votes: items = (ballot, option)
+        memset(&P, 0, sizeof P);
+        range_prover_shape(P, qp.vote_range);
+        range_prover_prefix(P.prefix, qp.vote_range, "quadratic_voting_variant", ctx->key);       // quadratic_voting.rs:253
+        P.n = k * m; P.group = m; P.wide_inner = Dv * 64; P.out_inner = vsz;
+        P.values = (const uint64_t *)ctx->in[0].p; P.value_stride = 1;
+        P.wide = d_wide; P.wide_stride = D * 64;
+        P.ct_out = d_ballots; P.ct_stride = bsz;
+        P.partial_out = d_ballots + 64; P.partial_stride = bsz;
+        P.ring_out = d_ballots + 64 + 64 * (size_t)(Rv - 1); P.ring_stride = bsz;
+        P.pts = (uint32_t *)ctx->pts.p; P.enc = (uint32_t *)ctx->enc.p; P.sec = (uint32_t *)ctx->res_big.p;
+        P.commit = (uint32_t *)ctx->commit.p; P.chal = (uint32_t *)ctx->chal.p; P.ct_sec = (uint32_t *)ctx->res[1].p;
+        P.table_g = ctx->d_table_g; P.table_k = ctx->d_table_k;
+        TRY(launch_rprove(ctx, P));
+        // ---- credit
+        memset(&P, 0, sizeof P);
+        range_prover_shape(P, qp.credit_range);
+        range_prover_prefix(P.prefix, qp.credit_range, "quadratic_voting_credit_range", ctx->key);   // quadratic_voting.rs:263
+        P.n = k; P.group = 0;
+        P.values = (const uint64_t *)ctx->in[3].p; P.value_stride = 1;
+        P.wide = d_wide + m * Dv * 64; P.wide_stride = D * 64;
+        P.ct_out = d_ballots + m * vsz; P.ct_stride = bsz;
+        P.partial_out = d_ballots + m * vsz + 64; P.partial_stride = bsz;
+        P.ring_out = d_ballots + m * vsz + 64 + 64 * (size_t)(Rc - 1); P.ring_stride = bsz;
+        P.pts = (uint32_t *)ctx->pts.p; P.enc = (uint32_t *)ctx->enc.p; P.sec = (uint32_t *)ctx->res_big.p;
+        P.commit = (uint32_t *)ctx->commit.p; P.chal = (uint32_t *)ctx->chal.p; P.ct_sec = (uint32_t *)ctx->res[2].p;
+        P.table_g = ctx->d_table_g; P.table_k = ctx->d_table_k;
+        TRY(launch_rprove(ctx, P));
+        // ---- credit equivalence
+        sumsq_prove_params S;
+        memset(&S, 0, sizeof S);
+        S.n = k; S.m = m; S.values = (const uint64_t *)ctx->in[0].p;
+        S.wide = d_wide + (m * Dv + Dc) * 64; S.wide_stride = D * 64;
+        S.cts = d_ballots; S.ct_stride = bsz; S.ct_inner = vsz;
+        S.sum_ct = d_ballots + m * vsz;
+        S.proof = d_ballots + m * vsz + csz; S.proof_stride = bsz;
+        S.r_cts = (const uint32_t *)ctx->res[1].p; S.r_sum = (const uint32_t *)ctx->res[2].p;
+        merlin_new(S.prefix, EG_LBL("quadratic_voting_credit_equiv"));                               // quadratic_voting.rs:272
+        merlin_append_message(S.prefix, EG_LBL("dom-sep"), (const uint8_t *)"sum_of_squares", 14);   // mul.rs:96-99
+        merlin_append_message(S.prefix, EG_LBL("K"), ctx->key, 32);
+        S.table_g = ctx->d_table_g; S.table_k = ctx->d_table_k;
+        TRY(launch_sumsq_prove(ctx, S));
+        CU(cudaMemcpyAsync(ballots + off * bsz, d_ballots, k * bsz, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
     }
     return finish_call(ctx);

@@ -635,7 +635,11 @@ struct rprove_params {
     uint16_t sizes[EG_MAX_RINGS], starts[EG_MAX_RINGS];
     uint64_t steps[EG_MAX_RINGS];
     const uint64_t *values; size_t value_stride;     // value of item i = values[i * value_stride]
-    const uint8_t *wide; size_t wide_stride;         // bytes between the first blocks of consecutive items
+    // Items may be grouped into records (QuadraticVotingBallot: item = (ballot, option)): with group > 1 the address of
+    // item i's data is base + (i / group) * stride + (i % group) * inner; group <= 1 is the flat base + i * stride.
+    uint32_t group;
+    size_t wide_inner, out_inner;
+    const uint8_t *wide; size_t wide_stride;         // first randomness block of the item
     uint8_t *ct_out; size_t ct_stride;               // 64 B per item
     uint8_t *partial_out; size_t partial_stride;     // 64 (n_rings - 1) B per item
     uint8_t *ring_out; size_t ring_stride;           // 32 (1 + total) B per item: common challenge | responses
@@ -645,9 +649,13 @@ struct rprove_params {
     const uint32_t *table_g, *table_k;
 };
 
+EG_HD size_t rprove_off(const rprove_params &P, size_t item, size_t stride, size_t inner) {
+    return P.group > 1 ? (item / P.group) * stride + (item % P.group) * inner : item * stride;
+}
+
 EG_HD void rprove_draw(sc &out, const rprove_params &P, size_t item, uint32_t pos) {
     uint32_t w[16];
-    const uint8_t *b = P.wide + item * P.wide_stride + (size_t)pos * 64;
+    const uint8_t *b = P.wide + rprove_off(P, item, P.wide_stride, P.wide_inner) + (size_t)pos * 64;
     load32_bytes(w, b);
     load32_bytes(w + 8, b + 32);
     sc_from_wide_words(out, w);
@@ -714,7 +722,7 @@ EG_HD void rprove_ring1_body(const rprove_params &P, size_t item, uint32_t slot,
         sc r;
         rprove_draw(r, P, item, 0);
         rprove_encrypt(R, B, enc_ct, r, value, tab_g, tab_k);
-        uint8_t *o = P.ct_out + item * P.ct_stride;
+        uint8_t *o = P.ct_out + rprove_off(P, item, P.ct_stride, P.out_inner);
         store32_bytes(o, enc_ct);
         store32_bytes(o + 32, enc_ct + 8);
         if (P.ct_sec) planar_store_words(P.ct_sec, P.n, 0, 8, item, r.v);
@@ -738,7 +746,7 @@ EG_HD void rprove_ring1_body(const rprove_params &P, size_t item, uint32_t slot,
     }
     rprove_encrypt(R, B, enc_ct, r, (uint64_t)L.vi * P.steps[k], tab_g, tab_k);
     if (!last) {
-        uint8_t *o = P.partial_out + item * P.partial_stride + 64 * (size_t)k;
+        uint8_t *o = P.partial_out + rprove_off(P, item, P.partial_stride, P.out_inner) + 64 * (size_t)k;
         store32_bytes(o, enc_ct);
         store32_bytes(o + 32, enc_ct + 8);
     }
@@ -759,7 +767,7 @@ EG_HD void rprove_ring1_body(const rprove_params &P, size_t item, uint32_t slot,
         ge_vtab_build(tab_b, B);
         transcript rt;
         ring_transcript_start(rt, P.prefix, enc_ct, k);
-        uint8_t *resp = P.ring_out + item * P.ring_stride + 32 * (1 + (size_t)P.starts[k]);
+        uint8_t *resp = P.ring_out + rprove_off(P, item, P.ring_stride, P.out_inner) + 32 * (1 + (size_t)P.starts[k]);
 #pragma unroll 1
         for (uint32_t eq = L.vi + 1; eq < m; eq++) {
             sc e, s_;
@@ -787,7 +795,7 @@ EG_HD void rprove_common_body(const rprove_params &P, size_t item) {
     sc e0;
     merlin_challenge_scalar(t, EG_LBL("c"), e0);
     planar_store_words(P.chal, P.n, 0, 8, item, e0.v);
-    store32_bytes(P.ring_out + item * P.ring_stride, e0.v);
+    store32_bytes(P.ring_out + rprove_off(P, item, P.ring_stride, P.out_inner), e0.v);
 }
 
 // phase 2, one thread per (item, ring k): Ring::finalize (ring.rs:162-195)
@@ -798,7 +806,7 @@ EG_HD void rprove_ring2_body(const rprove_params &P, size_t item, uint32_t k, ui
     planar_load_words(e.v, P.chal, P.n, 0, 8, item);
     planar_load_words(r.v, P.sec, P.n, 2 * k, 8, item);
     planar_load_words(x.v, P.sec, P.n, 2 * k + 1, 8, item);
-    uint8_t *resp = P.ring_out + item * P.ring_stride + 32 * (1 + (size_t)P.starts[k]);
+    uint8_t *resp = P.ring_out + rprove_off(P, item, P.ring_stride, P.out_inner) + 32 * (1 + (size_t)P.starts[k]);
     if (L.vi > 0) {
         ge_ext R, B;
         planar_load_point(R, P.pts, P.n, 2 * k, item);
@@ -822,6 +830,99 @@ EG_HD void rprove_ring2_body(const rprove_params &P, size_t item, uint32_t k, ui
     }
     sc_muladd(s, e, r, x);
     store32_bytes(resp + 32 * (size_t)L.vi, s.v);
+}
+
+// ------------------------------------------------------------------ proving side: SumOfSquaresProof::new (mul.rs:107-181)
+//
+// The prover knows the value x_i and randomness r_i of every ciphertext (R_i, X_i) = ([r_i]G, [x_i]G + [r_i]K), so each
+// commitment is a fixed-base expression:
+//   [e_r,i]G ; [e_x,i]G + [e_r,i]K ; sum [e_x,i]R_i + [e_z]G = [sum e_x,i r_i + e_z]G ;
+//   sum [e_x,i]X_i + [e_z]K = [sum e_x,i x_i]G + [sum e_x,i r_i + e_z]K
+// (the same group elements as the reference's multi_mul over R_i / X_i).  Draw order: e_z, then (e_r,i, e_x,i) per
+// ciphertext.  One thread per ballot.  Used by QuadraticVotingBallot::new (quadratic_voting.rs:268-276).
+struct sumsq_prove_params {
+    size_t n;
+    uint32_t m;                          // ciphertexts per item
+    const uint64_t *values;              // n * m
+    const uint8_t *wide; size_t wide_stride;   // first block of the proof's randomness
+    const uint8_t *cts; size_t ct_stride, ct_inner;   // ciphertext i of item b at cts + b * ct_stride + i * ct_inner (64 B)
+    const uint8_t *sum_ct;               // + b * ct_stride: the sum-of-squares ciphertext (64 B)
+    uint8_t *proof; size_t proof_stride; // 32 (2m + 2) B: challenge | (r_resp, x_resp) * m | sum_resp
+    const uint32_t *r_cts;               // planar scalars over n * m items (item b * m + i): r_i
+    const uint32_t *r_sum;               // planar scalars over n items: randomness of the sum ciphertext
+    transcript prefix;                   // Transcript::new(label) + start_proof("sum_of_squares") + "K"
+    const uint32_t *table_g, *table_k;
+};
+
+EG_HD void sumsq_prove_body(const sumsq_prove_params &P, size_t item, const uint32_t *tab_g, const uint32_t *tab_k) {
+    transcript t = P.prefix;
+    uint32_t w[16], c0[8], c1[8];
+    const uint8_t *wide = P.wide + item * P.wide_stride;
+    sc e_z, e_r[EG_MSM_MAXV], e_x[EG_MSM_MAXV];
+    load32_bytes(w, wide); load32_bytes(w + 8, wide + 32);
+    sc_from_wide_words(e_z, w);
+    sc acc_r = e_z, acc_x = sc_zero();       // sum e_x,i r_i + e_z ; sum e_x,i x_i
+    sc sum_random;                            // r_z - sum x_i r_i   (mul.rs:117,132-133)
+    planar_load_words(sum_random.v, P.r_sum, P.n, 0, 8, item);
+#pragma unroll 1
+    for (uint32_t i = 0; i < P.m; i++) {
+        const uint8_t *ct = P.cts + item * P.ct_stride + i * P.ct_inner;
+        load32_bytes(w, ct);
+        merlin_append_words(t, EG_LBL("R_x"), w, 8);
+        load32_bytes(w, ct + 32);
+        merlin_append_words(t, EG_LBL("X"), w, 8);
+        const uint8_t *b = wide + 64 * (size_t)(1 + 2 * i);
+        load32_bytes(w, b); load32_bytes(w + 8, b + 32);
+        sc_from_wide_words(e_r[i], w);
+        load32_bytes(w, b + 64); load32_bytes(w + 8, b + 96);
+        sc_from_wide_words(e_x[i], w);
+        sc her, hex_;
+        sc_half(her, e_r[i]);
+        sc_half(hex_, e_x[i]);
+        ge_ext q0, q1;
+        ge_eval64(q0, nullptr, her, 1, tab_g, her, tab_g, her);
+        ge_eval64(q1, nullptr, her, 2, tab_k, her, tab_g, hex_);
+        ge_double_compress2(c0, c1, q0, q1);
+        merlin_append_words(t, EG_LBL("[e_r]G"), c0, 8);
+        merlin_append_words(t, EG_LBL("[e_x]G + [e_r]K"), c1, 8);
+        sc r_i, x_i = sc_from_u64(P.values[item * P.m + i]), tmp;
+        planar_load_words(r_i.v, P.r_cts, P.n * P.m, 0, 8, item * P.m + i);
+        sc_muladd(acc_r, e_x[i], r_i, acc_r);
+        sc_muladd(acc_x, e_x[i], x_i, acc_x);
+        sc_mul(tmp, x_i, r_i);
+        sc_sub(sum_random, sum_random, tmp);
+    }
+    {
+        sc ha, hx;
+        sc_half(ha, acc_r);
+        sc_half(hx, acc_x);
+        ge_ext q0, q1;
+        ge_eval64(q0, nullptr, ha, 1, tab_g, ha, tab_g, ha);
+        ge_eval64(q1, nullptr, ha, 2, tab_k, ha, tab_g, hx);
+        ge_double_compress2(c0, c1, q0, q1);
+    }
+    const uint8_t *zct = P.sum_ct + item * P.ct_stride;
+    load32_bytes(w, zct);
+    merlin_append_words(t, EG_LBL("R_z"), w, 8);
+    load32_bytes(w, zct + 32);
+    merlin_append_words(t, EG_LBL("Z"), w, 8);
+    merlin_append_words(t, EG_LBL("[e_x]R_x + [e_z]G"), c0, 8);
+    merlin_append_words(t, EG_LBL("[e_x]X + [e_z]K"), c1, 8);
+    sc c, s;
+    merlin_challenge_scalar(t, EG_LBL("c"), c);
+    uint8_t *out = P.proof + item * P.proof_stride;
+    store32_bytes(out, c.v);
+#pragma unroll 1
+    for (uint32_t i = 0; i < P.m; i++) {
+        sc r_i, x_i = sc_from_u64(P.values[item * P.m + i]);
+        planar_load_words(r_i.v, P.r_cts, P.n * P.m, 0, 8, item * P.m + i);
+        sc_muladd(s, c, r_i, e_r[i]);
+        store32_bytes(out + 32 * (size_t)(1 + 2 * i), s.v);
+        sc_muladd(s, c, x_i, e_x[i]);
+        store32_bytes(out + 32 * (size_t)(2 + 2 * i), s.v);
+    }
+    sc_muladd(s, c, sum_random, e_z);
+    store32_bytes(out + 32 * (size_t)(1 + 2 * P.m), s.v);
 }
 
 // Outer transcript: absorb every ring's terminal commitments, compare with the common challenge (ring.rs:364-373)

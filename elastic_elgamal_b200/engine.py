@@ -260,6 +260,15 @@ class Engine:
         self._check(self.lib.eg_verify_qv_batch(self.h, C.byref(p), n, _addr(ballots), _addr(v), _addr(t)))
         return v, t
 
+    def encrypt_qv(self, p, votes, wide_rand):
+        votes = np.ascontiguousarray(votes, dtype=np.uint64).reshape(-1, p.options)
+        n = votes.shape[0]
+        draws = self.lib.eg_qv_prover_draws(C.byref(p))
+        wide_rand = _u8(wide_rand, (n, draws, 64))
+        ballots = np.empty((n, self.qv_ballot_size(p)), np.uint8)
+        self._check(self.lib.eg_encrypt_qv_batch(self.h, C.byref(p), n, _addr(votes), _addr(wide_rand), _addr(ballots)))
+        return ballots
+
     # ---- threshold decryption
     def verify_shares(self, keyset, indexes, cts, shares, proofs):
         s = len(indexes)

@@ -242,6 +242,15 @@ eg_status eg_encrypt_range_batch(eg_ctx *ctx, const eg_range *range, const char 
                                  uint8_t *cts /* n*64 */, uint8_t *partials /* n*(n_rings-1)*64 */,
                                  uint8_t *ring_proofs /* n*(1+sum sizes)*32 */);
 
+/* QuadraticVotingBallot::new (src/app/quadratic_voting.rs:234-284).  votes[i*options + k] = votes of ballot i for
+ * option k.  Item i consumes eg_qv_prover_draws(params) blocks: one RangeProof::new per option over the vote range, one for
+ * credit = sum votes^2 over the credit range, then SumOfSquaresProof::new (src/proofs/mul.rs:107-181: e_z, then e_r, e_x per
+ * option).  A vote or credit outside its range (a panic in the reference) is EG_ERR_INVALID_ARG.
+ * Ballots use the layout eg_verify_qv_batch reads. */
+size_t    eg_qv_prover_draws(const eg_qv_params *params);
+eg_status eg_encrypt_qv_batch(eg_ctx *ctx, const eg_qv_params *params, size_t n, const uint64_t *votes /* n*options */,
+                              const uint8_t *wide_rand /* n*draws*64 */, uint8_t *ballots /* n*eg_qv_ballot_size */);
+
 /* ---- device-pointer variants (inputs already resident in HBM; same semantics) ------------------- */
 eg_status eg_verify_bool_batch_dev(eg_ctx *ctx, size_t n, const uint8_t *d_cts, const uint8_t *d_proofs, uint8_t *d_verdicts);
 eg_status eg_verify_choice_batch_dev(eg_ctx *ctx, size_t n, uint32_t options, int single, const uint8_t *d_choices,

@@ -571,3 +571,67 @@ def check_encrypt_range_reference_snapshot(e):
     pr = gold["proof"]
     assert bytes(partials[0].reshape(-1)) == b"".join(hx(c["random_element"]) + hx(c["blinded_element"]) for c in pr["partial_ciphertexts"])
     assert bytes(rings[0].reshape(-1)) == hx(pr["common_challenge"]) + b"".join(hx(x) for x in pr["ring_responses"])
+
+
+# ---------------------------------------------------------------- QuadraticVotingBallot::new on the GPU
+
+def check_encrypt_qv(e, pk, sk=None, n=8, options=5, credits=20, seed=W.SEED_QV):
+    p, ep = O.qv_params(options, credits), e.qv_params(options, credits)
+    rnd = random.Random(n * options + credits)
+    if options == 5 and credits == 20:
+        votes = [QV_VOTES[i % 4] for i in range(n)]
+    else:
+        mv = int(O.lib().eo_isqrt(credits))
+        votes = []
+        for _ in range(n):
+            while True:
+                v = [rnd.randrange(mv + 1) for _ in range(options)]
+                if sum(x * x for x in v) <= credits:
+                    break
+            votes.append(v)
+    votes = np.array(votes, np.uint64)
+    ballots = O.gen_qv_batch(pk, p, seed, votes)
+    draws = e.lib.eg_qv_prover_draws(O.C.byref(ep))
+    wide = np.frombuffer(b"".join(item_blocks(seed, i, draws) for i in range(n)), np.uint8).reshape(n, draws, 64)
+    got = e.encrypt_qv(ep, votes, wide)
+    assert got.shape == ballots.shape
+    bad = np.nonzero((got != ballots).any(axis=1))[0]
+    assert bad.size == 0, (bad[:4], np.nonzero(got[bad[0]] != ballots[bad[0]])[0][:8])
+    v, t = e.verify_qv(ep, got)
+    assert (v == 0).all()
+    if sk is not None:
+        table = O.DlogTable(0, 8 * n + 1)
+        assert [table.get(O.decrypt_to_element(sk, bytes(t[k]))) for k in range(options)] == votes.sum(axis=0).tolist()
+    from elastic_elgamal_b200 import EngineError, _ffi
+    too_many = votes[:1].copy()
+    too_many[0, 0] = 1000
+    try:
+        e.encrypt_qv(ep, too_many, wide[:1])
+        raise AssertionError("out-of-range vote accepted")
+    except EngineError as exc:
+        assert exc.status == _ffi.ERR_INVALID_ARG
+
+
+def check_encrypt_qv_reference_snapshot(e):
+    """tests/snapshots.rs:153-161: QuadraticVotingBallot::new(params(pk, 5, 15), [3, 0, 1, 0, 2]) from seed 12345."""
+    import json
+    import pathlib
+    gold = json.loads((pathlib.Path(__file__).parent / "golden" / "ristretto_snapshots.json").read_text())["qv-ballot"]
+    rng = O.rng_from_u64(12345)
+    sk, pk = O.keypair(rng)
+    e.set_receiver(pk)
+    ep = e.qv_params(5, 15)
+    draws = e.lib.eg_qv_prover_draws(O.C.byref(ep))
+    wide = np.frombuffer(b"".join(O.rng_block(rng) for _ in range(draws)), np.uint8).reshape(1, draws, 64)
+    ballot = bytes(e.encrypt_qv(ep, np.array([[3, 0, 1, 0, 2]], np.uint64), wide)[0])
+    hx = bytes.fromhex
+
+    def rp(d):     # CiphertextWithRangeProof -> ct | partial ciphertexts | common challenge | responses
+        pr = d["range_proof"]
+        return (hx(d["ciphertext"]["random_element"]) + hx(d["ciphertext"]["blinded_element"])
+                + b"".join(hx(c["random_element"]) + hx(c["blinded_element"]) for c in pr["partial_ciphertexts"])
+                + hx(pr["common_challenge"]) + b"".join(hx(x) for x in pr["ring_responses"]))
+    ce = gold["credit_equivalence_proof"]
+    expected = (b"".join(rp(v) for v in gold["votes"]) + rp(gold["credit"]) + hx(ce["challenge"])
+                + b"".join(hx(x) for x in ce["ciphertext_responses"]) + hx(ce["sum_response"]))
+    assert ballot == expected

@@ -214,3 +214,15 @@ def test_encrypt_range_reference_snapshot(env):
         PC.check_encrypt_range_reference_snapshot(env[0])
     finally:
         env[0].set_receiver(env[2])
+
+
+def test_encrypt_qv(env):
+    PC.check_encrypt_qv(env[0], env[2], env[1], n=48)
+    PC.check_encrypt_qv(env[0], env[2], env[1], n=12, options=3, credits=15)
+
+
+def test_encrypt_qv_reference_snapshot(env):
+    try:
+        PC.check_encrypt_qv_reference_snapshot(env[0])
+    finally:
+        env[0].set_receiver(env[2])

@@ -119,8 +119,16 @@ def config3(e, pk, sk, n, unique, steps, warmup, threads):
         assert table.get(O.decrypt_to_element(sk, bytes(t[k]))) == int(vt[ev == 0, k].sum())
     s1, sa = cpu_rates(lambda: O.verify_qv_batch(pk, p, ballots[:32], threads=1), 32,
                        lambda: O.verify_qv_batch(pk, p, ballots, threads=threads), unique)
+    # the creation side (QuadraticVotingBallot::new) on a quarter of the count, accepted by the GPU verifier
+    ne = max(64, n // 4)
+    draws = e.lib.eg_qv_prover_draws(O.C.byref(ep))
+    wide = np.random.RandomState(3).randint(0, 256, (ne, draws, 64)).astype(np.uint8)
+    dt_enc, made = timed(lambda: e.encrypt_qv(ep, vt[:ne], wide), 1, 1)
+    assert (e.verify_qv(ep, made)[0] == 0).all()
+    t0 = time.perf_counter(); O.gen_qv_batch(pk, p, W.SEED_QV, votes, threads=threads); cpu_enc = unique / (time.perf_counter() - t0)
     return {"unit": "verified QV ballots/s", "bytes_per_item": int(bsz), "gpu_e2e": n / dt, "cpu_1t": s1, "cpu_all": sa,
-            "rejected": int((ov != 0).sum())}
+            "rejected": int((ov != 0).sum()), "gpu_encrypt_qv_e2e": ne / dt_enc, "cpu_all_encrypt_qv": cpu_enc,
+            "prover_randomness_bytes_per_item": int(draws * 64)}
 
 
 def config4(e, pk, sk, n, unique, steps, warmup, threads):
@@ -136,8 +144,17 @@ def config4(e, pk, sk, n, unique, steps, warmup, threads):
     assert (v == tile(ov, n)).all()
     s1, sa = cpu_rates(lambda: O.verify_range_batch(pk, spec, "ciphertext_range", cts[:32], partials[:32], rings[:32], threads=1), 32,
                        lambda: O.verify_range_batch(pk, spec, "ciphertext_range", cts, partials, rings, threads=threads), unique)
+    # the creation side (encrypt_range = RangeProof::new) on a quarter of the count, accepted by the GPU verifier
+    ne = max(64, n // 4)
+    draws = e.lib.eg_range_prover_draws(O.C.byref(espec))
+    wide = np.random.RandomState(4).randint(0, 256, (ne, draws, 64)).astype(np.uint8)
+    ev = (np.arange(ne, dtype=np.uint64) * 40503) % 65536
+    dt_enc, (c2, p2, r2) = timed(lambda: e.encrypt_range(espec, "ciphertext_range", ev, wide), 1, 1)
+    assert (e.verify_range(espec, "ciphertext_range", c2, p2, r2) == 0).all()
+    t0 = time.perf_counter(); O.gen_range_batch(pk, spec, "ciphertext_range", W.SEED_CHOICE, values, threads=threads); cpu_enc = unique / (time.perf_counter() - t0)
     return {"unit": "verified range proofs/s", "bytes_per_item": 1568, "gpu_e2e": n / dt, "cpu_1t": s1, "cpu_all": sa,
-            "rejected": int((ov != 0).sum()), "decomposition": O.range_display(spec)}
+            "rejected": int((ov != 0).sum()), "decomposition": O.range_display(spec), "gpu_encrypt_range_e2e": ne / dt_enc,
+            "cpu_all_encrypt_range": cpu_enc, "prover_randomness_bytes_per_item": int(draws * 64)}
 
 
 def config5(e, pk, sk, n, unique, steps, warmup, threads):
