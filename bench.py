@@ -14,9 +14,9 @@ SURVEY.md 8(d) (1 % tampered with the reference's tamper patterns) and tiled to 
 does not depend on ballot contents (uniform control flow), and verdicts/tally are checked against the oracle.
 
 JSON keys follow the driver contract; `value` = device-resident throughput, `e2e` = through the host C ABI with
-pinned host buffers (H2D + D2H inside the timed region), `roofline` = the dominant kernel (k_commit) against the
-INT32 multiply-add issue rate measured live by tools/microbench/int_pipe_bench, `cpu_baseline` = the oracle port
-timed on this box's host cores.
+pinned host buffers (H2D + D2H inside the timed region), `roofline` = the dominant kernel (k_ring: one thread per ring
+proof, all of its equations) against the INT32 multiply-add issue rate measured live by
+tools/microbench/int_pipe_bench, `cpu_baseline` = the oracle port timed on this box's host cores.
 """
 import argparse
 import json
@@ -246,13 +246,19 @@ def main():
     sampler.start()
     launches0 = e.kernel_launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # the dominant kernel: k_ring in ring mode 2 (kind 1), k_commit in the per-equation A/B mode (kind 0)
+    dom_kind = 1 if args.ring_mode == 2 else 0
     commit_ms, commit_tasks, commit_launches = 0.0, 0, 0
+    other_ms, other_tasks, other_launches = 0.0, 0, 0
     with torch.cuda.stream(stream):
         ev0.record(stream)
         for _ in range(args.steps):
             step_device()
-            st = e.last_commit_stats()
+            st = e.last_kernel_stats(dom_kind)
             commit_ms += st["ms"]; commit_tasks += st["tasks"]; commit_launches += st["launches"]
+            if dom_kind == 1:
+                st = e.last_kernel_stats(0)
+                other_ms += st["ms"]; other_tasks += st["tasks"]; other_launches += st["launches"]
         ev1.record(stream)
     barrier()
     dev_ms = ev0.elapsed_time(ev1)
@@ -332,10 +338,12 @@ def main():
             peak_ops *= clk["sm_mhz"] / peak["sm_clock_mhz_probed"]
     achieved_ops = commit_tasks * FIELD_OPS_PER_COMMIT * IMAD_PER_FIELD_OP / (commit_ms * 1e-3) if commit_ms > 0 else None
     traffic = None
-    tfile = ROOT / "profiles" / "k_commit_traffic.json"
+    tfile = ROOT / "profiles" / ("k_ring_traffic.json" if args.ring_mode == 2 else "k_commit_traffic.json")
     if tfile.exists():
         try:
-            traffic = json.loads(tfile.read_text()).get("dram_bytes_per_launch")
+            # dram bytes of one ncu-captured launch, rescaled to this run's equation sides per launch
+            t = json.loads(tfile.read_text())
+            traffic = t["dram_bytes_per_launch"] * (commit_tasks / max(1, commit_launches)) / t["equation_sides_per_launch"]
         except Exception:
             traffic = None
     roofline = {
@@ -348,6 +356,9 @@ def main():
         "traffic": traffic,
         "launches": commit_launches, "avg_launch_ms": commit_ms / max(1, commit_launches),
         "share_of_step": commit_ms / dev_ms if dev_ms else None,
+        "ncu": "profiles/r1_k_ring_full_s3.txt: fmaheavy pipe 83.6 % busy, issue slots 43.5 %, 13.7 warps/SM (ncu --set full, same command)",
+        "second_kernel": {"kernel": "k_commit (sum proof)", "launches": other_launches, "equation_sides": other_tasks,
+                          "ms": other_ms, "share_of_step": other_ms / dev_ms if dev_ms else None} if dom_kind == 1 else None,
         "algorithmic": {"field_ops_per_equation_side": FIELD_OPS_PER_COMMIT, "imad_per_field_op": IMAD_PER_FIELD_OP,
                         "equation_sides_per_launch": commit_tasks / max(1, commit_launches)},
         "field_ops_per_s": commit_tasks * FIELD_OPS_PER_COMMIT / (commit_ms * 1e-3) if commit_ms > 0 else None,

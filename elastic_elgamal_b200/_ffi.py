@@ -76,6 +76,9 @@ PROTOTYPES = {
     "eg_dlog_table_create": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_void_p)]),
     "eg_dlog_table_destroy": (None, [C.c_void_p]),
     "eg_combine_decrypt_batch": (C.c_int32, [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.c_size_t, C.c_uint32, P8, P8, C.c_void_p, P8, P8]),
+    "eg_multi_mul_batch": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_uint32, P8, P8, P8, P8]),
+    "eg_encrypt_batch": (C.c_int32, [C.c_void_p, C.c_size_t, P8, P8, P8]),
+    "eg_encrypt_zero_batch": (C.c_int32, [C.c_void_p, C.c_size_t, P8, P8, P8]),
     "eg_encrypt_bool_batch": (C.c_int32, [C.c_void_p, C.c_size_t, P8, P8, P8, P8]),
     "eg_encrypt_choice_batch": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_uint32, C.c_int, P8, P8, P8, P8, P8]),
     "eg_range_prover_draws": (C.c_size_t, [C.POINTER(Range)]),
@@ -86,6 +89,7 @@ PROTOTYPES = {
     "eg_last_timings": (C.c_int32, [C.c_void_p, C.POINTER(C.c_float * 5)]),
     "eg_ctx_stream": (C.c_void_p, [C.c_void_p]),
     "eg_last_commit_stats": (C.c_int32, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_float)]),
+    "eg_last_kernel_stats": (C.c_int32, [C.c_void_p, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_float)]),
     "eg_selftest_field": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_uint64, C.POINTER(C.c_uint64)]),
     "eg_ctx_set_chunk_items": (C.c_int32, [C.c_void_p, C.c_size_t]),
     "eg_ctx_set_ring_mode": (C.c_int32, [C.c_void_p, C.c_int]),

@@ -131,6 +131,19 @@ __global__ void __launch_bounds__(EG_RING_THREADS, EG_RING_MINBLOCKS) k_rprove(c
     }
 }
 
+// PublicKey::encrypt / encrypt_zero, one thread per item; persistent grid, chunked fixed-base tables in shared memory
+__global__ void __launch_bounds__(EG_RING_THREADS, EG_RING_MINBLOCKS) k_encrypt(const encrypt_params P) {
+    extern __shared__ __align__(16) uint32_t s_rtab[];
+    for (int k = threadIdx.x; k < EG_FCHUNK_TABLE_WORDS; k += blockDim.x) {
+        s_rtab[k] = P.table_g[k];
+        s_rtab[EG_FCHUNK_TABLE_WORDS + k] = P.table_k[k];
+    }
+    __syncthreads();
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x; tid < P.n; tid += stride)
+        encrypt_body(P, tid, s_rtab, s_rtab + EG_FCHUNK_TABLE_WORDS);
+}
+
 // SumOfSquaresProof::new, one thread per item; persistent grid, chunked fixed-base tables in shared memory
 __global__ void __launch_bounds__(EG_RING_THREADS, EG_RING_MINBLOCKS) k_sumsq_prove(const sumsq_prove_params P) {
     extern __shared__ __align__(16) uint32_t s_rtab[];
@@ -266,6 +279,11 @@ __global__ void __launch_bounds__(256) k_scalars_validate(const uint8_t *s, size
     if (i < n) scalars_validate_body(i, s, ok);
 }
 
+__global__ void __launch_bounds__(256) k_unpack(const unpack_params P) {
+    size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid < P.n) unpack_body(P, tid);
+}
+
 template <int ENCODE>
 __global__ void __launch_bounds__(256) k_b64url(const b64_params P) {
     size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -397,9 +415,12 @@ struct eg_ctx {
     uint64_t launches = 0, commit_launches = 0, commit_tasks = 0;
     float timings[5] = {0, 0, 0, 0, 0};
     cudaEvent_t ev[8];
-    std::vector<cudaEvent_t> commit_ev;     // pairs (start, stop) around every k_commit launch of the current call
+    std::vector<cudaEvent_t> commit_ev;     // pairs (start, stop) around every k_commit / k_ring launch of the current call
+    std::vector<uint8_t> commit_ev_kind;    // per pair: 0 = k_commit, 1 = k_ring
     size_t commit_ev_used = 0;
     uint64_t call_commit_tasks = 0, call_commit_launches = 0;
+    uint64_t kind_tasks[2] = {0, 0}, kind_launches[2] = {0, 0};   // per kind, current call
+    float kind_ms[2] = {0, 0};
     // grow-only scratch
     dev_buf pts, enc, commit, chal, flags, res[3], in[4], verdicts, partial, running, adm, misc, slots, consts, res_big;
     size_t adm_used = 0;      // cached points in `adm` (32 words each); entries 0,1 = the [O, G] pair
@@ -409,7 +430,7 @@ struct eg_ctx {
     int ring_grid = 0;        // resident CTAs of k_ring (queried once)
     int prove_grid[3] = {0, 0, 0};
     int rprove_grid[3] = {0, 0, 0};
-    int sumsq_prove_grid = 0;
+    int sumsq_prove_grid = 0, encrypt_grid = 0;
     dev_buf ring_scratch;
 };
 
@@ -486,6 +507,9 @@ static void launch_commit(eg_ctx *ctx, const commit_params &P) {
         ctx->commit_ev.push_back(a); ctx->commit_ev.push_back(b);
     }
     cudaEvent_t e_start = ctx->commit_ev[ctx->commit_ev_used], e_stop = ctx->commit_ev[ctx->commit_ev_used + 1];
+    if (ctx->commit_ev_kind.size() < ctx->commit_ev.size() / 2) ctx->commit_ev_kind.resize(ctx->commit_ev.size() / 2);
+    ctx->commit_ev_kind[ctx->commit_ev_used / 2] = 0;
+    ctx->kind_tasks[0] += total; ctx->kind_launches[0]++;
     ctx->commit_ev_used += 2;
     cudaEventRecord(e_start, ctx->stream);
 #ifdef EG_HOSTSIM
@@ -512,6 +536,9 @@ static eg_status launch_ring(eg_ctx *ctx, ring_params &P) {
         ctx->commit_ev.push_back(a); ctx->commit_ev.push_back(b);
     }
     cudaEvent_t e_start = ctx->commit_ev[ctx->commit_ev_used], e_stop = ctx->commit_ev[ctx->commit_ev_used + 1];
+    if (ctx->commit_ev_kind.size() < ctx->commit_ev.size() / 2) ctx->commit_ev_kind.resize(ctx->commit_ev.size() / 2);
+    ctx->commit_ev_kind[ctx->commit_ev_used / 2] = 1;
+    ctx->kind_tasks[1] += sides; ctx->kind_launches[1]++;
     ctx->commit_ev_used += 2;
     const size_t total = P.n * (size_t)P.n_rings;
 #ifdef EG_HOSTSIM
@@ -615,6 +642,26 @@ static eg_status launch_rprove(eg_ctx *ctx, const rprove_params &P) {
     TRY(launch_rprove_phase<1>(ctx, P, ctx->rprove_grid[1]));
     TRY(launch_rprove_phase<2>(ctx, P, ctx->rprove_grid[2]));
 #endif
+    return EG_SUCCESS;
+}
+
+static eg_status launch_encrypt(eg_ctx *ctx, const encrypt_params &P) {
+#ifdef EG_HOSTSIM
+    EG_FOR_HOST(P.n, encrypt_body(P, tid, P.table_g, P.table_k))
+#else
+    const size_t smem = 2 * EG_FCHUNK_TABLE_WORDS * 4;
+    if (ctx->encrypt_grid == 0) {
+        CU(cudaFuncSetAttribute(k_encrypt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0, sms = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_encrypt, EG_RING_THREADS, smem));
+        CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+        if (per_sm < 1) return fail(ctx, EG_ERR_CUDA, "k_encrypt does not fit on an SM");
+        ctx->encrypt_grid = per_sm * sms;
+    }
+    const unsigned grid = (unsigned)std::min<size_t>((size_t)ctx->encrypt_grid, (P.n + EG_RING_THREADS - 1) / EG_RING_THREADS);
+    k_encrypt<<<grid, EG_RING_THREADS, smem, ctx->stream>>>(P);
+#endif
+    ctx->launches++;
     return EG_SUCCESS;
 }
 
@@ -765,6 +812,15 @@ static void launch_scalars_validate(eg_ctx *ctx, const uint8_t *sc_in, size_t n,
     ctx->launches++;
 }
 
+static void launch_unpack(eg_ctx *ctx, const unpack_params &P) {
+#ifdef EG_HOSTSIM
+    EG_FOR_HOST(P.n, unpack_body(P, tid))
+#else
+    k_unpack<<<grid_for(P.n, 256), 256, 0, ctx->stream>>>(P);
+#endif
+    ctx->launches++;
+}
+
 static void launch_b64url(eg_ctx *ctx, const b64_params &P, bool encode) {
     const size_t total = P.n * (size_t)P.groups;
 #ifdef EG_HOSTSIM
@@ -874,6 +930,15 @@ extern "C" eg_status eg_last_commit_stats(const eg_ctx *ctx, uint64_t *launches,
     if (launches) *launches = ctx->call_commit_launches;
     if (tasks) *tasks = ctx->call_commit_tasks;
     if (ms) *ms = ctx->timings[2];
+    return EG_SUCCESS;
+}
+
+// kind 0: k_commit launches of the last call, kind 1: k_ring launches (tasks = equation sides)
+extern "C" eg_status eg_last_kernel_stats(const eg_ctx *ctx, int kind, uint64_t *launches, uint64_t *tasks, float *ms) {
+    if (!ctx || kind < 0 || kind > 1) return EG_ERR_INVALID_ARG;
+    if (launches) *launches = ctx->kind_launches[kind];
+    if (tasks) *tasks = ctx->kind_tasks[kind];
+    if (ms) *ms = ctx->kind_ms[kind];
     return EG_SUCCESS;
 }
 
@@ -1143,7 +1208,7 @@ static eg_status begin_call(eg_ctx *ctx) {
     ctx->err.clear();
     ctx->commit_ev_used = 0;
     ctx->call_commit_tasks = 0;
-    ctx->call_commit_launches = 0;
+    ctx->call_commit_launches = 0; ctx->kind_tasks[0] = ctx->kind_tasks[1] = 0; ctx->kind_launches[0] = ctx->kind_launches[1] = 0;
     return EG_SUCCESS;
 }
 
@@ -1151,9 +1216,13 @@ static eg_status finish_call(eg_ctx *ctx) {
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaGetLastError());
     float commit_ms = 0;
+    ctx->kind_ms[0] = ctx->kind_ms[1] = 0;
     for (size_t k = 0; k + 1 < ctx->commit_ev_used; k += 2) {
         float ms = 0;
-        if (cudaEventElapsedTime(&ms, ctx->commit_ev[k], ctx->commit_ev[k + 1]) == cudaSuccess) commit_ms += ms;
+        if (cudaEventElapsedTime(&ms, ctx->commit_ev[k], ctx->commit_ev[k + 1]) == cudaSuccess) {
+            commit_ms += ms;
+            ctx->kind_ms[ctx->commit_ev_kind[k / 2] ? 1 : 0] += ms;
+        }
     }
     ctx->timings[2] = commit_ms;
     return EG_SUCCESS;
@@ -2104,7 +2173,7 @@ extern "C" eg_status eg_verify_shares_batch(eg_ctx *ctx, const eg_keyset *ks, si
                                             const uint8_t *cts, const uint8_t *shares, const uint8_t *proofs, uint8_t *verdicts) {
     if (!ctx) return EG_ERR_INVALID_ARG;
     CU(cudaSetDevice(ctx->device));
-    ctx->err.clear(); ctx->commit_ev_used = 0; ctx->call_commit_tasks = 0; ctx->call_commit_launches = 0;
+    ctx->err.clear(); ctx->commit_ev_used = 0; ctx->call_commit_tasks = 0; ctx->call_commit_launches = 0; ctx->kind_tasks[0] = ctx->kind_tasks[1] = 0; ctx->kind_launches[0] = ctx->kind_launches[1] = 0;
     if (!ks || !indexes || n_shares == 0 || n_shares > 8 || ks->shares == 0 || ks->shares > 64 || ks->threshold == 0 || ks->threshold > ks->shares)
         return fail(ctx, EG_ERR_INVALID_ARG, "invalid key set / share count (at most 8 shares per call)");
     for (uint32_t j = 0; j < n_shares; j++)
@@ -2405,6 +2474,117 @@ extern "C" eg_status eg_encrypt_qv_batch(eg_ctx *ctx, const eg_qv_params *params
     return finish_call(ctx);
 }
 
+// =================================================================== PublicKey::encrypt / encrypt_zero
+
+static eg_status encrypt_batch(eg_ctx *ctx, size_t n, const uint64_t *values, const uint8_t *wide, uint8_t *cts, uint8_t *proofs) {
+    TRY(begin_call(ctx));
+    const bool zero = values == nullptr;
+    if (n == 0) return EG_SUCCESS;
+    if (!wide || !cts || (zero && !proofs)) return fail(ctx, EG_ERR_INVALID_ARG, "null pointer");
+    const size_t draws = zero ? 2 : 1;
+    const size_t chunk = (size_t)1 << 20, cm = std::min(chunk, n);
+    TRY(ensure(ctx, ctx->in[0], cm * 8));
+    TRY(ensure(ctx, ctx->in[1], cm * draws * 64));
+    TRY(ensure(ctx, ctx->in[2], cm * 64));
+    TRY(ensure(ctx, ctx->in[3], cm * 64));
+    encrypt_params P;
+    memset(&P, 0, sizeof P);
+    P.with_zero_proof = zero ? 1 : 0;
+    P.values = (const uint64_t *)ctx->in[0].p; P.wide = (const uint8_t *)ctx->in[1].p;
+    P.cts = (uint8_t *)ctx->in[2].p; P.proofs = (uint8_t *)ctx->in[3].p;
+    P.table_g = ctx->d_table_g; P.table_k = ctx->d_table_k;
+    if (zero) {
+        merlin_new(P.prefix, EG_LBL("zero_encryption"));                  // keys/impls.rs:47
+        merlin_append_message(P.prefix, EG_LBL("dom-sep"), (const uint8_t *)"log_eq", 6);
+        merlin_append_message(P.prefix, EG_LBL("K"), ctx->key, 32);
+    }
+    for (size_t off = 0; off < n; off += chunk) {
+        const size_t k = std::min(chunk, n - off);
+        P.n = k;
+        if (!zero) CU(cudaMemcpyAsync(ctx->in[0].p, values + off, k * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->in[1].p, wide + off * draws * 64, k * draws * 64, cudaMemcpyHostToDevice, ctx->stream));
+        TRY(launch_encrypt(ctx, P));
+        CU(cudaMemcpyAsync(cts + off * 64, ctx->in[2].p, k * 64, cudaMemcpyDeviceToHost, ctx->stream));
+        if (zero) CU(cudaMemcpyAsync(proofs + off * 64, ctx->in[3].p, k * 64, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    return finish_call(ctx);
+}
+
+extern "C" eg_status eg_encrypt_batch(eg_ctx *ctx, size_t n, const uint64_t *values, const uint8_t *wide_rand, uint8_t *cts) {
+    if (ctx && n && !values) return fail(ctx, EG_ERR_INVALID_ARG, "null pointer");
+    static const uint64_t dummy = 0;
+    return encrypt_batch(ctx, n, values ? values : &dummy, wide_rand, cts, nullptr);
+}
+
+extern "C" eg_status eg_encrypt_zero_batch(eg_ctx *ctx, size_t n, const uint8_t *wide_rand, uint8_t *cts, uint8_t *proofs) {
+    return encrypt_batch(ctx, n, nullptr, wide_rand, cts, proofs);
+}
+
+// =================================================================== Group::vartime_multi_mul over a batch
+
+// ristretto.rs:139-146: out[i] = sum_j [scalars[i][j]] points[i][j], `terms` <= 16 per item.  ok[i] = 0 (identity
+// encoding) when a point does not decode or a scalar is not canonical.
+extern "C" eg_status eg_multi_mul_batch(eg_ctx *ctx, size_t n, uint32_t terms, const uint8_t *scalars, const uint8_t *points, uint8_t *out,
+                                        uint8_t *ok) {
+    if (!ctx) return EG_ERR_INVALID_ARG;
+    CU(cudaSetDevice(ctx->device));
+    ctx->err.clear(); ctx->commit_ev_used = 0; ctx->call_commit_tasks = 0; ctx->call_commit_launches = 0; ctx->kind_tasks[0] = ctx->kind_tasks[1] = 0; ctx->kind_launches[0] = ctx->kind_launches[1] = 0;
+    if (terms == 0 || terms > EG_MSM_MAXV) return fail(ctx, EG_ERR_INVALID_ARG, "terms must be in 1..16");
+    if (n == 0) return EG_SUCCESS;
+    if (!scalars || !points || !out || !ok) return fail(ctx, EG_ERR_INVALID_ARG, "null pointer");
+    const uint32_t T = terms;
+    const size_t chunk = std::max<size_t>(1024, default_chunk(ctx) * 2 / T), cm = std::min(chunk, n);
+    TRY(ensure(ctx, ctx->in[0], cm * 32 * T));
+    TRY(ensure(ctx, ctx->in[1], cm * 32 * T));
+    TRY(ensure(ctx, ctx->in[2], cm * 32));
+    TRY(ensure(ctx, ctx->verdicts, cm));
+    TRY(ensure(ctx, ctx->pts, cm * T * 128));
+    TRY(ensure(ctx, ctx->commit, cm * 32));
+    TRY(ensure(ctx, ctx->flags, cm * 4));
+    for (size_t off = 0; off < n; off += chunk) {
+        const size_t k = std::min(chunk, n - off);
+        CU(cudaMemcpyAsync(ctx->in[0].p, scalars + off * 32 * T, k * 32 * T, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->in[1].p, points + off * 32 * T, k * 32 * T, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemsetAsync(ctx->flags.p, 0, k * 4, ctx->stream));
+        in_bufs in;
+        memset(&in, 0, sizeof in);
+        in.buf[0] = (const uint8_t *)ctx->in[0].p; in.stride[0] = 32 * T;
+        in.buf[1] = (const uint8_t *)ctx->in[1].p; in.stride[1] = 32 * T;
+        decode_params dp;
+        memset(&dp, 0, sizeof dp);
+        dp.in = in; dp.n = k; dp.n_slots = (int)T;
+        for (uint32_t q = 0; q < T; q++) { dp.slots[q].buf = 1; dp.slots[q].offset = 32 * q; dp.slots[q].p_index = q; }
+        dp.pts = (uint32_t *)ctx->pts.p; dp.enc = nullptr; dp.flags = (uint32_t *)ctx->flags.p;
+        launch_decode(ctx, dp);
+        scalars_params sp;
+        memset(&sp, 0, sizeof sp);
+        sp.in = in; sp.n = k; sp.n_slots = 1; sp.slots[0].buf = 0; sp.slots[0].offset = 0; sp.slots[0].count = T;
+        sp.flags = (uint32_t *)ctx->flags.p;
+        launch_scalars(ctx, sp);
+        std::vector<msm_slot> slots(1);
+        msm_slot &z = slots[0];
+        memset(&z, 0, sizeof z);
+        z.nv = (uint8_t)T; z.nf = 0; z.out_enc = 1; z.out_index = 0;
+        for (uint32_t j = 0; j < T; j++) { z.p_index[j] = j; z.vs[j] = src_in(0, 32 * j, false); }
+        TRY(upload_slots(ctx, slots));
+        msm_params mp;
+        memset(&mp, 0, sizeof mp);
+        mp.in = in; mp.n = k; mp.n_slots = 1; mp.slots = (const msm_slot *)ctx->slots.p;
+        mp.pts = (const uint32_t *)ctx->pts.p; mp.commit = (uint32_t *)ctx->commit.p; mp.pts_out = (uint32_t *)ctx->pts.p;
+        mp.table_g = ctx->d_table_g; mp.table_k = ctx->has_receiver ? ctx->d_table_k : ctx->d_table_g;
+        launch_msm(ctx, mp);
+        unpack_params up;
+        up.n = k; up.commit = (const uint32_t *)ctx->commit.p; up.flags = (const uint32_t *)ctx->flags.p;
+        up.out = (uint8_t *)ctx->in[2].p; up.ok = (uint8_t *)ctx->verdicts.p;
+        launch_unpack(ctx, up);
+        CU(cudaMemcpyAsync(out + off * 32, ctx->in[2].p, k * 32, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(ok + off, ctx->verdicts.p, k, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    return finish_call(ctx);
+}
+
 // =================================================================== wire format (serde.rs:19-80)
 
 static bool b64_shape(b64_params &P, size_t n, size_t bytes_per_item) {
@@ -2599,7 +2779,7 @@ extern "C" eg_status eg_verify_possession_batch(eg_ctx *ctx, const char *label, 
                                                 const uint8_t *proofs, uint8_t *verdicts) {
     if (!ctx) return EG_ERR_INVALID_ARG;
     CU(cudaSetDevice(ctx->device));
-    ctx->err.clear(); ctx->commit_ev_used = 0; ctx->call_commit_tasks = 0; ctx->call_commit_launches = 0;
+    ctx->err.clear(); ctx->commit_ev_used = 0; ctx->call_commit_tasks = 0; ctx->call_commit_launches = 0; ctx->kind_tasks[0] = ctx->kind_tasks[1] = 0; ctx->kind_launches[0] = ctx->kind_launches[1] = 0;
     if (!valid_label(label)) return fail(ctx, EG_ERR_INVALID_ARG, "transcript label must be 1..255 bytes");
     const uint32_t K = keys_per_proof;
     if (K == 0 || K > EG_MAX_RINGS) return fail(ctx, EG_ERR_INVALID_ARG, "keys_per_proof must be in 1..64");
@@ -2719,7 +2899,7 @@ extern "C" eg_status eg_combine_decrypt_batch(eg_ctx *ctx, uint32_t threshold, c
                                               uint8_t *found) {
     if (!ctx) return EG_ERR_INVALID_ARG;
     CU(cudaSetDevice(ctx->device));
-    ctx->err.clear(); ctx->commit_ev_used = 0; ctx->call_commit_tasks = 0; ctx->call_commit_launches = 0;
+    ctx->err.clear(); ctx->commit_ev_used = 0; ctx->call_commit_tasks = 0; ctx->call_commit_launches = 0; ctx->kind_tasks[0] = ctx->kind_tasks[1] = 0; ctx->kind_launches[0] = ctx->kind_launches[1] = 0;
     if (!indexes || !table || threshold == 0 || threshold > EG_MSM_MAXV || share_stride < threshold)
         return fail(ctx, EG_ERR_INVALID_ARG, "invalid threshold / share layout");
     if (n == 0) return EG_SUCCESS;

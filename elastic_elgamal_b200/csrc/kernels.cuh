@@ -832,6 +832,49 @@ EG_HD void rprove_ring2_body(const rprove_params &P, size_t item, uint32_t k, ui
     store32_bytes(resp + 32 * (size_t)L.vi, s.v);
 }
 
+// ------------------------------------------------------------------ PublicKey::encrypt / encrypt_zero (keys/impls.rs:16-53)
+//
+// encrypt: one draw r per item, (R, B) = ([r]G, [v]G + [r]K) (ExtendedCiphertext::new encryption.rs:310-327).
+// encrypt_zero: r, then the LogEqualityProof::new nonce x (log_equality.rs:114-143); proof = c | c r + x.
+struct encrypt_params {
+    size_t n;
+    uint8_t with_zero_proof;             // 0: encrypt(values[i]); 1: encrypt_zero + proof
+    const uint64_t *values;              // mode 0
+    const uint8_t *wide;                 // n * (1 + with_zero_proof) * 64
+    uint8_t *cts;                        // n * 64
+    uint8_t *proofs;                     // mode 1: n * 64
+    transcript prefix;                   // mode 1: Transcript::new("zero_encryption") + start_proof("log_eq") + "K"
+    const uint32_t *table_g, *table_k;
+};
+
+EG_HD void encrypt_body(const encrypt_params &P, size_t item, const uint32_t *tab_g, const uint32_t *tab_k) {
+    const uint32_t draws = 1 + P.with_zero_proof;
+    uint32_t w[16], enc_ct[16];
+    const uint8_t *b = P.wide + item * draws * 64;
+    sc r;
+    load32_bytes(w, b); load32_bytes(w + 8, b + 32);
+    sc_from_wide_words(r, w);
+    ge_ext R, B;
+    rprove_encrypt(R, B, enc_ct, r, P.with_zero_proof ? 0 : P.values[item], tab_g, tab_k);
+    store32_bytes(P.cts + item * 64, enc_ct);
+    store32_bytes(P.cts + item * 64 + 32, enc_ct + 8);
+    if (!P.with_zero_proof) return;
+    sc x, c, s_;
+    load32_bytes(w, b + 64); load32_bytes(w + 8, b + 96);
+    sc_from_wide_words(x, w);
+    uint32_t c0[8], c1[8];
+    prove_commit_pair(c0, c1, x, tab_g, tab_k);
+    transcript t = P.prefix;
+    merlin_append_words(t, EG_LBL("[r]G"), enc_ct, 8);
+    merlin_append_words(t, EG_LBL("[r]K"), enc_ct + 8, 8);
+    merlin_append_words(t, EG_LBL("[x]G"), c0, 8);
+    merlin_append_words(t, EG_LBL("[x]K"), c1, 8);
+    merlin_challenge_scalar(t, EG_LBL("c"), c);
+    sc_muladd(s_, c, r, x);
+    store32_bytes(P.proofs + item * 64, c.v);
+    store32_bytes(P.proofs + item * 64 + 32, s_.v);
+}
+
 // ------------------------------------------------------------------ proving side: SumOfSquaresProof::new (mul.rs:107-181)
 //
 // The prover knows the value x_i and randomness r_i of every ciphertext (R_i, X_i) = ([r_i]G, [x_i]G + [r_i]K), so each
@@ -1179,6 +1222,18 @@ EG_HD void scalars_validate_body(size_t i, const uint8_t *s, uint8_t *ok) {
     uint32_t w[8];
     load32_bytes(w, s + 32 * i);
     ok[i] = sc_is_canonical_words(w) ? 1 : 0;
+}
+
+// planar encoding 0 of every item -> 32-byte records; ok = 0 and the identity encoding for flagged (malformed) items
+struct unpack_params { size_t n; const uint32_t *commit; const uint32_t *flags; uint8_t *out; uint8_t *ok; };
+
+EG_HD void unpack_body(const unpack_params &P, size_t item) {
+    uint32_t w[8];
+    const bool bad = (P.flags[item] & 1u) != 0;
+    planar_load_words(w, P.commit, P.n, 0, 8, item);
+    if (bad) for (int k = 0; k < 8; k++) w[k] = 0;
+    store32_bytes(P.out + 32 * item, w);
+    P.ok[item] = bad ? 0 : 1;
 }
 
 // ------------------------------------------------------------------ wire format: Base64UrlUnpadded (serde.rs:19-80)

@@ -64,6 +64,12 @@ class Engine:
         self._check(self.lib.eg_last_commit_stats(self.h, C.byref(launches), C.byref(tasks), C.byref(ms)))
         return {"launches": launches.value, "tasks": tasks.value, "ms": ms.value}
 
+    def last_kernel_stats(self, kind):
+        """kind 0: k_commit, 1: k_ring -- launches, equation sides and summed device ms in the last batch call."""
+        launches, tasks, ms = C.c_uint64(0), C.c_uint64(0), C.c_float(0)
+        self._check(self.lib.eg_last_kernel_stats(self.h, kind, C.byref(launches), C.byref(tasks), C.byref(ms)))
+        return {"launches": launches.value, "tasks": tasks.value, "ms": ms.value}
+
     def selftest_field(self, n=1 << 16, seed=1):
         m = C.c_uint64(0)
         self._check(self.lib.eg_selftest_field(self.h, n, seed, C.byref(m)))
@@ -135,6 +141,14 @@ class Engine:
         self._check(self.lib.eg_mul_generator_batch(self.h, n, _addr(k), _addr(out), _addr(ok)))
         return out, ok.astype(bool)
 
+    def multi_mul(self, scalars, points):
+        scalars = _u8(scalars)
+        n, t = scalars.shape[0], scalars.shape[1]
+        scalars, points = scalars.reshape(n, t, 32), _u8(points, (n, t, 32))
+        out, ok = np.empty((n, 32), np.uint8), np.empty(n, np.uint8)
+        self._check(self.lib.eg_multi_mul_batch(self.h, n, t, _addr(scalars), _addr(points), _addr(out), _addr(ok)))
+        return out, ok.astype(bool)
+
     def ciphertexts_sum(self, parts):
         parts = _u8(parts)
         n_parts, n_cts = parts.shape[0], parts.shape[1]
@@ -190,6 +204,21 @@ class Engine:
         return v
 
     # ---- encryption side (randomness supplied by the caller as 64-byte blocks in the reference's draw order)
+    def encrypt(self, values, wide_rand):
+        values = np.ascontiguousarray(values, dtype=np.uint64).reshape(-1)
+        n = values.shape[0]
+        wide_rand = _u8(wide_rand, (n, 64))
+        cts = np.empty((n, 64), np.uint8)
+        self._check(self.lib.eg_encrypt_batch(self.h, n, _addr(values), _addr(wide_rand), _addr(cts)))
+        return cts
+
+    def encrypt_zero(self, wide_rand):
+        wide_rand = _u8(wide_rand, (-1, 2, 64))
+        n = wide_rand.shape[0]
+        cts, proofs = np.empty((n, 64), np.uint8), np.empty((n, 64), np.uint8)
+        self._check(self.lib.eg_encrypt_zero_batch(self.h, n, _addr(wide_rand), _addr(cts), _addr(proofs)))
+        return cts, proofs
+
     def encrypt_bool(self, values, wide_rand):
         values = _u8(values, (-1,))
         n = values.shape[0]

@@ -96,6 +96,10 @@ eg_status eg_double_mul_generator_batch(eg_ctx *ctx, size_t n, const uint8_t *a 
                                         const uint8_t *b /* n*32 */, uint8_t *out /* n*32 */, uint8_t *ok /* n */);
 /* Group::mul_generator :105-107 over a batch: out[i] = [k_i]G */
 eg_status eg_mul_generator_batch(eg_ctx *ctx, size_t n, const uint8_t *k /* n*32 */, uint8_t *out /* n*32 */, uint8_t *ok);
+/* Group::vartime_multi_mul :139-146 over a batch: out[i] = sum_j [scalars[i][j]] points[i][j], 1 <= terms <= 16.
+ * ok[i] = 0 (and out[i] = identity encoding) if a point does not decode or a scalar is not canonical. */
+eg_status eg_multi_mul_batch(eg_ctx *ctx, size_t n, uint32_t terms, const uint8_t *scalars /* n*terms*32 */,
+                             const uint8_t *points /* n*terms*32 */, uint8_t *out /* n*32 */, uint8_t *ok /* n */);
 /* Ciphertext + Ciphertext folded over a batch (src/encryption.rs:163-172): out = sum of the n_parts rows,
  * each row = n_cts ciphertexts.  Used to combine per-GPU partial tallies. ok = 0 if any element is malformed. */
 eg_status eg_ciphertexts_sum(eg_ctx *ctx, size_t n_parts, size_t n_cts, const uint8_t *parts /* n_parts*n_cts*64 */,
@@ -215,6 +219,14 @@ eg_status eg_combine_decrypt_batch(eg_ctx *ctx, uint32_t threshold, const uint32
 
 /* ---- encryption side (encrypt_* drop-ins with caller-supplied randomness) ----------------------- */
 
+/* PublicKey::encrypt (src/keys/impls.rs:16-23 -> ExtendedCiphertext::new src/encryption.rs:310-327): one block per item
+ * (the randomness r); cts[i] = ([r]G, [values[i]]G + [r]K). */
+eg_status eg_encrypt_batch(eg_ctx *ctx, size_t n, const uint64_t *values /* n */, const uint8_t *wide_rand /* n*64 */,
+                           uint8_t *cts /* n*64 */);
+/* PublicKey::encrypt_zero (src/keys/impls.rs:30-53): two blocks per item (r, then the LogEqualityProof::new nonce,
+ * src/proofs/log_equality.rs:114-143); proofs[i] = challenge | response as LogEqualityProof::to_bytes. */
+eg_status eg_encrypt_zero_batch(eg_ctx *ctx, size_t n, const uint8_t *wide_rand /* n*2*64 */, uint8_t *cts /* n*64 */,
+                                uint8_t *proofs /* n*64 */);
 /* PublicKey::encrypt_bool (src/keys/impls.rs:77-89).  The reference draws from a CryptoRng; here the caller supplies the
  * randomness: item i consumes three 64-byte blocks in the reference's draw order (r, x, forged
  * response), each reduced mod l as Ristretto::generate_scalar does (src/group/ristretto.rs:28-32).  With blocks taken
@@ -271,9 +283,11 @@ uint64_t  eg_kernel_launch_count(const eg_ctx *ctx);
  * [0] decode + derived ciphertexts, [1] commitments + transcripts + verdicts, [2] the k_commit launches alone
  * (one event pair per launch), [3] tally, [4] total of [0]+[1]+[3]. */
 eg_status eg_last_timings(const eg_ctx *ctx, float out_ms[5]);
-/* The dominant kernel (k_commit, one thread per verification-equation side) in the last batch call: number of
- * launches, number of equation sides evaluated, summed device time of those launches. */
+/* The equation-evaluation kernels (k_ring + k_commit) in the last batch call: number of launches, number of
+ * verification-equation sides evaluated, summed device time of those launches (one CUDA event pair per launch). */
 eg_status eg_last_commit_stats(const eg_ctx *ctx, uint64_t *launches, uint64_t *tasks, float *ms);
+/* The same split by kernel: kind 0 = k_commit (single-use equation sides), kind 1 = k_ring (one thread per ring). */
+eg_status eg_last_kernel_stats(const eg_ctx *ctx, int kind, uint64_t *launches, uint64_t *tasks, float *ms);
 /* On-device self-test of the tuned GF(2^255-19) multiply / square / add / sub against the portable formulation on
  * n pseudo-random and edge-case operands; *mismatches must come back 0. */
 eg_status eg_selftest_field(eg_ctx *ctx, size_t n, uint64_t seed, uint64_t *mismatches);

@@ -635,3 +635,73 @@ def check_encrypt_qv_reference_snapshot(e):
     expected = (b"".join(rp(v) for v in gold["votes"]) + rp(gold["credit"]) + hx(ce["challenge"])
                 + b"".join(hx(x) for x in ce["ciphertext_responses"]) + hx(ce["sum_response"]))
     assert ballot == expected
+
+
+# ---------------------------------------------------------------- encrypt / encrypt_zero / vartime_multi_mul
+
+def check_encrypt_plain_and_zero(e, pk, sk, n=20):
+    """Same ChaCha blocks as the oracle (one sequential stream) => identical ciphertexts and zero proofs; includes the
+    reference's `ciphertext` and `zero-encryption` snapshots (tests/snapshots.rs:31-71)."""
+    rng = O.rng_from_seed(bytes([6] * 32))
+    rng2 = O.rng_from_seed(bytes([6] * 32))
+    values = [0, 1, 2**32 + 5, 2**63] + list(range(100, 100 + n - 4))
+    expected = [O.encrypt(pk, v, rng) for v in values]
+    wide = np.frombuffer(b"".join(O.rng_block(rng2) for _ in range(n)), np.uint8).reshape(n, 64)
+    got = e.encrypt(np.array(values, np.uint64), wide)
+    assert [bytes(g) for g in got] == expected
+    table = O.DlogTable(0, 200)
+    assert table.get(O.decrypt_to_element(sk, bytes(got[5]))) == 101
+    expected = [O.encrypt_zero(pk, rng) for _ in range(n)]
+    wide = np.frombuffer(b"".join(O.rng_block(rng2) for _ in range(2 * n)), np.uint8).reshape(n, 2, 64)
+    cts, proofs = e.encrypt_zero(wide)
+    assert [(bytes(c), bytes(p)) for c, p in zip(cts, proofs)] == expected
+    assert (e.verify_zero(cts, proofs) == 0).all()
+    assert e.encrypt(np.zeros(0, np.uint64), np.zeros((0, 64), np.uint8)).shape == (0, 64)
+
+
+def check_encrypt_plain_and_zero_snapshots(e):
+    import json
+    import pathlib
+    gold = json.loads((pathlib.Path(__file__).parent / "golden" / "ristretto_snapshots.json").read_text())
+    hx = bytes.fromhex
+    for name in ("ciphertext", "zero-encryption"):
+        rng = O.rng_from_u64(12345)
+        sk, pk = O.keypair(rng)
+        e.set_receiver(pk)
+        if name == "ciphertext":
+            wide = np.frombuffer(O.rng_block(rng), np.uint8).reshape(1, 64)
+            ct = bytes(e.encrypt(np.array([42], np.uint64), wide)[0])
+            assert ct == hx(gold[name]["random_element"]) + hx(gold[name]["blinded_element"]) == hx(gold["ciphertext-bin"])
+        else:
+            wide = np.frombuffer(O.rng_block(rng) + O.rng_block(rng), np.uint8).reshape(1, 2, 64)
+            cts, proofs = e.encrypt_zero(wide)
+            g = gold[name]
+            assert bytes(cts[0]) == hx(g["ciphertext"]["random_element"]) + hx(g["ciphertext"]["blinded_element"])
+            assert bytes(proofs[0]) == hx(g["proof"]["challenge"]) + hx(g["proof"]["response"]) == hx(gold["zero-encryption-bin"])
+
+
+def check_multi_mul(e, n=12):
+    rnd = random.Random(17)
+    rng = O.rng_from_seed(bytes([8] * 32))
+    for terms in (1, 2, 3, 7, 16):
+        scalars = np.zeros((n, terms, 32), np.uint8)
+        points = np.zeros((n, terms, 32), np.uint8)
+        expected = []
+        for i in range(n):
+            acc = bytes(32)
+            for j in range(terms):
+                s_ = O.scalar_reduce_wide(O.rng_block(rng)) if (i + j) % 5 else sc(rnd.choice([0, 1, W.L - 1]))
+                p_ = O.point_mul_generator(O.scalar_reduce_wide(O.rng_block(rng))) if (i * j) % 7 != 3 else bytes(32)
+                scalars[i, j] = np.frombuffer(s_, np.uint8)
+                points[i, j] = np.frombuffer(p_, np.uint8)
+                acc = O.point_add(acc, O.point_mul(s_, p_))
+            expected.append(acc)
+        if n >= 4:
+            points[1, terms - 1] = np.frombuffer(W.BAD_POINT, np.uint8)
+            scalars[2, 0] = np.frombuffer(W.BAD_SCALAR, np.uint8)
+        out, ok = e.multi_mul(scalars, points)
+        for i in range(n):
+            if n >= 4 and i in (1, 2):
+                assert not ok[i] and bytes(out[i]) == bytes(32)
+            else:
+                assert ok[i] and bytes(out[i]) == expected[i], (terms, i)

@@ -226,3 +226,15 @@ def test_encrypt_qv_reference_snapshot(env):
         PC.check_encrypt_qv_reference_snapshot(env[0])
     finally:
         env[0].set_receiver(env[2])
+
+
+def test_encrypt_plain_and_zero(env):
+    PC.check_encrypt_plain_and_zero(env[0], env[2], env[1], n=64)
+    try:
+        PC.check_encrypt_plain_and_zero_snapshots(env[0])
+    finally:
+        env[0].set_receiver(env[2])
+
+
+def test_multi_mul(env):
+    PC.check_multi_mul(env[0], n=64)
