@@ -108,6 +108,43 @@ extern "C" {
                                      d_cts: *const u8, d_partial_cts: *const u8, d_ring_proofs: *const u8,
                                      d_verdicts: *mut u8) -> eg_status;
 
+    pub fn eg_ctx_set_blinding_base(ctx: *mut eg_ctx, base: *const u8) -> eg_status;
+    pub fn eg_ctx_set_ring_mode(ctx: *mut eg_ctx, mode: c_int) -> eg_status;
+
+    pub fn eg_multi_mul_batch(ctx: *mut eg_ctx, n: usize, terms: u32, scalars: *const u8, points: *const u8, out: *mut u8,
+                              ok: *mut u8) -> eg_status;
+    pub fn eg_ciphertexts_sum_dev(ctx: *mut eg_ctx, n_parts: usize, n_cts: usize, d_parts: *const u8, d_out: *mut u8,
+                                  d_bad: *mut u32) -> eg_status;
+
+    pub fn eg_base64url_chars(bytes_per_item: usize) -> usize;
+    pub fn eg_base64url_decode_batch(ctx: *mut eg_ctx, n: usize, bytes_per_item: usize, text: *const c_char, raw: *mut u8,
+                                     ok: *mut u8) -> eg_status;
+    pub fn eg_base64url_encode_batch(ctx: *mut eg_ctx, n: usize, bytes_per_item: usize, raw: *const u8, text: *mut c_char) -> eg_status;
+    pub fn eg_base64url_decode_batch_dev(ctx: *mut eg_ctx, n: usize, bytes_per_item: usize, d_text: *const c_char,
+                                         d_raw: *mut u8, d_ok: *mut u8) -> eg_status;
+    pub fn eg_base64url_encode_batch_dev(ctx: *mut eg_ctx, n: usize, bytes_per_item: usize, d_raw: *const u8,
+                                         d_text: *mut c_char) -> eg_status;
+
+    pub fn eg_verify_commitment_equiv_batch(ctx: *mut eg_ctx, transcript_label: *const c_char, n: usize, cts: *const u8,
+                                            commitments: *const u8, proofs: *const u8, verdicts: *mut u8) -> eg_status;
+    pub fn eg_verify_possession_batch(ctx: *mut eg_ctx, transcript_label: *const c_char, keys_per_proof: u32, n: usize,
+                                      keys: *const u8, proofs: *const u8, verdicts: *mut u8) -> eg_status;
+
+    pub fn eg_encrypt_batch(ctx: *mut eg_ctx, n: usize, values: *const u64, wide_rand: *const u8, cts: *mut u8) -> eg_status;
+    pub fn eg_encrypt_zero_batch(ctx: *mut eg_ctx, n: usize, wide_rand: *const u8, cts: *mut u8, proofs: *mut u8) -> eg_status;
+    pub fn eg_encrypt_bool_batch(ctx: *mut eg_ctx, n: usize, values: *const u8, wide_rand: *const u8, cts: *mut u8,
+                                 proofs: *mut u8) -> eg_status;
+    pub fn eg_encrypt_choice_batch(ctx: *mut eg_ctx, n: usize, options: u32, single: c_int, values: *const u8,
+                                   wide_rand: *const u8, choices: *mut u8, ring_proofs: *mut u8, sum_proofs: *mut u8) -> eg_status;
+    pub fn eg_range_prover_draws(range: *const eg_range) -> usize;
+    pub fn eg_encrypt_range_batch(ctx: *mut eg_ctx, range: *const eg_range, transcript_label: *const c_char, n: usize,
+                                  values: *const u64, wide_rand: *const u8, cts: *mut u8, partials: *mut u8,
+                                  ring_proofs: *mut u8) -> eg_status;
+    pub fn eg_qv_prover_draws(params: *const eg_qv_params) -> usize;
+    pub fn eg_encrypt_qv_batch(ctx: *mut eg_ctx, params: *const eg_qv_params, n: usize, votes: *const u64,
+                               wide_rand: *const u8, ballots: *mut u8) -> eg_status;
+
+    pub fn eg_last_kernel_stats(ctx: *const eg_ctx, kind: c_int, launches: *mut u64, tasks: *mut u64, ms: *mut f32) -> eg_status;
     pub fn eg_kernel_launch_count(ctx: *const eg_ctx) -> u64;
     pub fn eg_last_timings(ctx: *const eg_ctx, out_ms: *mut f32) -> eg_status;
     pub fn eg_last_commit_stats(ctx: *const eg_ctx, launches: *mut u64, tasks: *mut u64, ms: *mut f32) -> eg_status;

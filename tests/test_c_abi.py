@@ -24,6 +24,15 @@ def test_exports_every_declared_symbol():
     assert names <= set(_ffi.PROTOTYPES), sorted(names - set(_ffi.PROTOTYPES))
 
 
+def test_rust_sys_crate_declares_every_symbol():
+    """rust/elastic-elgamal-b200-sys is source-only here (no rustc): keep its extern block in step with the header."""
+    header = re.sub(r"/\*.*?\*/", "", (ROOT / "include" / "eg_b200.h").read_text(), flags=re.S)
+    names = set(re.findall(r"\b(eg_[a-z0-9_]+)\s*\(", header))
+    rust = (ROOT / "rust" / "elastic-elgamal-b200-sys" / "src" / "lib.rs").read_text()
+    declared = set(re.findall(r"pub fn (eg_[a-z0-9_]+)\(", rust))
+    assert names <= declared, sorted(names - declared)
+
+
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():
