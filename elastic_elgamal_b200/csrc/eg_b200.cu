@@ -68,11 +68,15 @@ __global__ void __launch_bounds__(EG_COMMIT_THREADS, EG_COMMIT_MINBLOCKS) k_comm
 // v2 ring engine: persistent grid (one CTA slot per resident CTA), each thread walks (item, ring) pairs with a fixed
 // 8 KB scratch region for the window tables of its current ring.  Both 48 KB chunked fixed-base tables live in shared
 // memory (dynamic, 96 KB per CTA).
+// Launch shape: ONE CTA of 640 threads per SM (20 warps = 5 per scheduler, <= 102 registers).  Measured on B200
+// (profiles/r1_ab_launch_shapes.txt): 2 x 256 threads 1.784 M ballots/s, 1 x 512 1.823 M, 1 x 640 1.866 M, 1 x 768 1.833 M;
+// warp counts that do not divide by the 4 schedulers (576, 704) lose 8-10 %.  One CTA per SM also leaves 132 KB instead
+// of 36 KB of the unified L1 to the per-thread window tables.
 #ifndef EG_RING_THREADS
-#define EG_RING_THREADS 256
+#define EG_RING_THREADS 640
 #endif
 #ifndef EG_RING_MINBLOCKS
-#define EG_RING_MINBLOCKS 2
+#define EG_RING_MINBLOCKS 1
 #endif
 __global__ void __launch_bounds__(EG_RING_THREADS, EG_RING_MINBLOCKS) k_ring(const ring_params P) {
     extern __shared__ __align__(16) uint32_t s_rtab[];
