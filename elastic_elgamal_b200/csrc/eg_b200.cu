@@ -68,17 +68,28 @@ __global__ void __launch_bounds__(EG_COMMIT_THREADS, EG_COMMIT_MINBLOCKS) k_comm
 // v2 ring engine: persistent grid (one CTA slot per resident CTA), each thread walks (item, ring) pairs with a fixed
 // 8 KB scratch region for the window tables of its current ring.  Both 48 KB chunked fixed-base tables live in shared
 // memory (dynamic, 96 KB per CTA).
-// Launch shape: ONE CTA of 640 threads per SM (20 warps = 5 per scheduler, <= 102 registers).  Measured on B200
-// (profiles/r1_ab_launch_shapes.txt): 2 x 256 threads 1.784 M ballots/s, 1 x 512 1.823 M, 1 x 640 1.866 M, 1 x 768 1.833 M;
-// warp counts that do not divide by the 4 schedulers (576, 704) lose 8-10 %.  One CTA per SM also leaves 132 KB instead
-// of 36 KB of the unified L1 to the per-thread window tables.
+// Two launch shapes, chosen per job by the ring sizes (measured on B200, profiles/r1_ab_launch_shapes.txt):
+//   * rings of two equations (bool / choice): ONE CTA of 640 threads per SM (20 warps = 5 per scheduler, <= 102 registers):
+//     2 x 256 threads 1.784 M ballots/s, 1 x 512 1.823 M, 1 x 640 1.866 M, 1 x 768 1.833 M; warp counts that do not divide
+//     by the 4 schedulers (576, 704) lose 8-10 %.  One CTA per SM also leaves 132 KB instead of 36 KB of the unified L1
+//     to the per-thread window tables.
+//   * longer rings (range proofs, QV ballots): 2 CTAs of 256 threads (128 registers): 643 k range proofs/s vs 600 k with
+//     1 x 640 -- the longer equation loop suffers from the extra spills of the 102-register build.
+// EG_RING_THREADS / EG_RING_MINBLOCKS is the shape of the long-ring variant and of the prover kernels.
 #ifndef EG_RING_THREADS
-#define EG_RING_THREADS 640
+#define EG_RING_THREADS 256
 #endif
 #ifndef EG_RING_MINBLOCKS
-#define EG_RING_MINBLOCKS 1
+#define EG_RING_MINBLOCKS 2
 #endif
-__global__ void __launch_bounds__(EG_RING_THREADS, EG_RING_MINBLOCKS) k_ring(const ring_params P) {
+#ifndef EG_RING2_THREADS
+#define EG_RING2_THREADS 640
+#endif
+#ifndef EG_RING2_MINBLOCKS
+#define EG_RING2_MINBLOCKS 1
+#endif
+template <int THREADS, int MINBLOCKS>
+__global__ void __launch_bounds__(THREADS, MINBLOCKS) k_ring(const ring_params P) {
     extern __shared__ __align__(16) uint32_t s_rtab[];
     for (int k = threadIdx.x; k < EG_FCHUNK_TABLE_WORDS; k += blockDim.x) {
         s_rtab[k] = P.table_g[k];
@@ -431,7 +442,7 @@ struct eg_ctx {
     std::map<std::string, std::vector<uint64_t>> adm_cache_key;
     size_t chunk_items = 0;   // 0 = default
     int ring_mode = 2;        // 2: k_ring (one thread per ring, chunked tables); 1: k_commit / k_ring_hash launches per equation
-    int ring_grid = 0;        // resident CTAs of k_ring (queried once)
+    int ring_grid[2] = {0, 0};   // resident CTAs of the two k_ring shapes (queried once)
     int prove_grid[3] = {0, 0, 0};
     int rprove_grid[3] = {0, 0, 0};
     int sumsq_prove_grid = 0, encrypt_grid = 0;
@@ -552,19 +563,30 @@ static eg_status launch_ring(eg_ctx *ctx, ring_params &P) {
     EG_FOR_HOST(total, ring_body(P, tid % P.n, (uint32_t)(tid / P.n), P.scratch, P.table_g, P.table_k))
 #else
     const size_t smem = 2 * EG_FCHUNK_TABLE_WORDS * 4;
-    if (ctx->ring_grid == 0) {
-        CU(cudaFuncSetAttribute(k_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    bool short_rings = true;
+    for (uint32_t r = 0; r < P.n_rings; r++) short_rings = short_rings && P.sizes[r] <= 2;
+    const int shape = short_rings ? 1 : 0;
+    const int threads = shape ? EG_RING2_THREADS : EG_RING_THREADS;
+    if (ctx->ring_grid[shape] == 0) {
         int per_sm = 0, sms = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ring, EG_RING_THREADS, smem));
+        if (shape) {
+            CU(cudaFuncSetAttribute(k_ring<EG_RING2_THREADS, EG_RING2_MINBLOCKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ring<EG_RING2_THREADS, EG_RING2_MINBLOCKS>, threads, smem));
+        } else {
+            CU(cudaFuncSetAttribute(k_ring<EG_RING_THREADS, EG_RING_MINBLOCKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ring<EG_RING_THREADS, EG_RING_MINBLOCKS>, threads, smem));
+        }
         CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
         if (per_sm < 1) return fail(ctx, EG_ERR_CUDA, "k_ring does not fit on an SM");
-        ctx->ring_grid = per_sm * sms;
+        ctx->ring_grid[shape] = per_sm * sms;
     }
-    const unsigned grid = (unsigned)std::min<size_t>((size_t)ctx->ring_grid, (total + EG_RING_THREADS - 1) / EG_RING_THREADS);
-    TRY(ensure(ctx, ctx->ring_scratch, (size_t)ctx->ring_grid * EG_RING_THREADS * 2 * EG_VTAB_WORDS * 4));
+    const size_t resident = (size_t)ctx->ring_grid[shape];
+    const unsigned grid = (unsigned)std::min<size_t>(resident, (total + threads - 1) / threads);
+    TRY(ensure(ctx, ctx->ring_scratch, resident * threads * 2 * EG_VTAB_WORDS * 4));
     P.scratch = (uint32_t *)ctx->ring_scratch.p;
     cudaEventRecord(e_start, ctx->stream);
-    k_ring<<<grid, EG_RING_THREADS, smem, ctx->stream>>>(P);
+    if (shape) k_ring<EG_RING2_THREADS, EG_RING2_MINBLOCKS><<<grid, threads, smem, ctx->stream>>>(P);
+    else k_ring<EG_RING_THREADS, EG_RING_MINBLOCKS><<<grid, threads, smem, ctx->stream>>>(P);
 #endif
     cudaEventRecord(e_stop, ctx->stream);
     ctx->launches++;
