@@ -167,6 +167,9 @@ def int32_peak():
     """Measured INT32 multiply-add issue rate (lane-ops / s) of this GPU: tools/microbench/int_pipe_bench."""
     exe = ROOT / "tools" / "microbench" / "int_pipe_bench"
     try:
+        if not exe.exists():      # built by __graft_entry__.build(); rebuilt here if the binary did not travel
+            subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-o", str(exe),
+                            str(exe) + ".cu"], check=True, timeout=600)
         out = subprocess.run([str(exe), "8192"], check=True, stdout=subprocess.PIPE, text=True, timeout=120).stdout
         data = json.loads(out.strip().splitlines()[-1])
         return data
@@ -185,9 +188,20 @@ def main():
 
     import oracle as O
     from elastic_elgamal_b200 import Engine
+    from elastic_elgamal_b200 import build as eg_build
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not eg_build.LIB.exists() and "EG_B200_LIB" not in os.environ:
+        # the CUDA library normally travels with the repo snapshot; compile it (nvcc, sm_100a) if it did not.  Rank 0
+        # of a node builds, the others wait for the file.  There is no other implementation to fall back to.
+        if local_rank == 0:
+            eg_build.build()
+        else:
+            for _ in range(1200):
+                if eg_build.LIB.exists():
+                    break
+                time.sleep(0.5)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
