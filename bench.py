@@ -39,6 +39,9 @@ BALLOT_BYTES = OPTIONS * 64 + (1 + 2 * OPTIONS) * 32 + 64        # 736, SURVEY.m
 # instructions per field operation.
 FIELD_OPS_PER_COMMIT = 4956 / 2 + 280
 FIELD_OPS_PER_BALLOT = 4956 * 11 + 280 * (34 + 10)               # 66 836
+# What k_ring actually executes per equation side of a two-equation ring: (2 x 1603 table build +
+# 4 x 1139 evaluation + 224 for the [e a]G term + 2 x 304 encoding) / 4 sides, counted from the formulas in ge.cuh.
+EXECUTED_FIELD_OPS_PER_RING_SIDE = (2 * 1603 + 4 * 1139 + 224 + 2 * 304) / 4      # 2148.5
 IMAD_PER_FIELD_OP = 144
 METRIC = "verified ballots/sec (5-option choice)"
 
@@ -375,6 +378,11 @@ def main():
                           "ms": other_ms, "share_of_step": other_ms / dev_ms if dev_ms else None} if dom_kind == 1 else None,
         "algorithmic": {"field_ops_per_equation_side": FIELD_OPS_PER_COMMIT, "imad_per_field_op": IMAD_PER_FIELD_OP,
                         "equation_sides_per_launch": commit_tasks / max(1, commit_launches)},
+        # `achieved` counts the reference's algorithm; the engine does less work per side (shared doublings,
+        # chunked tables, inversion-only encoding), so the fraction of the pipe it really keeps busy is the lower one:
+        "executed": ({"field_ops_per_equation_side": EXECUTED_FIELD_OPS_PER_RING_SIDE,
+                      "frac": achieved_ops * EXECUTED_FIELD_OPS_PER_RING_SIDE / FIELD_OPS_PER_COMMIT / peak_ops}
+                     if achieved_ops and peak_ops and dom_kind == 1 else None),
         "field_ops_per_s": commit_tasks * FIELD_OPS_PER_COMMIT / (commit_ms * 1e-3) if commit_ms > 0 else None,
         "hbm": {"achieved_gbs": world * B * (BALLOT_BYTES + 1) * args.steps / (dev_ms_max * 1e-3) / 1e9,
                 "note": "input streaming only; <1% of the measured HBM copy bandwidth, the path is integer-pipe bound"},
