@@ -6,8 +6,9 @@ import json,sys
 for line in sys.stdin:
     line=line.strip()
     if line.startswith('{'):
-        d=json.loads(line); r=d['roofline']
-        print('$lib', 'value=%.0f' % d['value'], 'e2e=%.0f' % d['e2e']['value'], 'kernel_ms=%.2f' % r['avg_launch_ms'], 'share=%.3f' % r['share_of_step'], 'frac=%.3f' % r['frac'])
+        d=json.loads(line); r=d['roofline']; k2=r.get('second_kernel') or {}
+        print('$lib', 'value=%.0f' % d['value'], 'e2e=%.0f' % d['e2e']['value'], 'kernel_ms=%.2f' % r['avg_launch_ms'], 'share=%.3f' % r['share_of_step'], 'frac=%.3f' % r['frac'],
+              'k_commit_ms=%.2f' % (k2.get('ms', 0) / max(1, k2.get('launches', 1))))
     elif line: print('$lib', line[:200])
 "
 done
