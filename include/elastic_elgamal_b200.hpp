@@ -31,6 +31,12 @@ struct Ciphertext { Element random_element, blinded_element; };                 
 struct LogEqualityProof { Scalar challenge, response; };                              // to_bytes: c || s
 struct RingProof { Scalar common_challenge; std::vector<Scalar> ring_responses; };    // to_bytes: e0 || s...
 struct PublicKey { Element bytes; };
+// src/proofs/commitment.rs:126-135 (serde only in the reference; bytes = struct field order)
+struct CommitmentEquivalenceProof { Scalar challenge, randomness_response, value_response, commitment_response; };
+// src/proofs/possession.rs:71-76
+struct ProofOfPossession { Scalar challenge; std::vector<Scalar> responses; };
+// src/proofs/range.rs:446-450 + the ciphertext it speaks about
+struct RangeProof { std::vector<Ciphertext> partial_ciphertexts; RingProof inner; };
 
 struct ChoiceParams { PublicKey receiver; uint32_t options_count; bool single; };     // ChoiceParams::{single, multi}
 struct EncryptedChoice { std::vector<Ciphertext> choices; RingProof range_proof; LogEqualityProof sum_proof; };
@@ -85,6 +91,57 @@ class Engine {
             std::copy(t.begin() + 64 * k + 32, t.begin() + 64 * k + 64, out.tally[k].blinded_element.begin());
         }
         return out;
+    }
+
+    // proofs.iter().map(|(ct, proof)| receiver.verify_range(&range, ct, proof))   (keys/impls.rs:143-151)
+    std::vector<Verdict> verify_range_batch(const eg_range &range, const std::vector<Ciphertext> &cts, const std::vector<RangeProof> &proofs,
+                                            const std::string &label = "ciphertext_range") {
+        if (cts.size() != proofs.size()) throw Error(EG_ERR_LEN_MISMATCH, "ciphertexts / proofs size mismatch");
+        size_t total = 0;
+        for (uint32_t r = 0; r < range.n_rings; r++) total += range.size[r];
+        std::vector<uint8_t> c, pc, r, v(cts.size());
+        for (size_t i = 0; i < cts.size(); i++) {
+            if (proofs[i].partial_ciphertexts.size() + 1 != range.n_rings) throw Error(EG_ERR_LEN_MISMATCH, "number of rings");  // range.rs:555-559
+            if (proofs[i].inner.ring_responses.size() != total) throw Error(EG_ERR_LEN_MISMATCH, "items in all rings");
+            append(c, cts[i]);
+            for (const auto &ct : proofs[i].partial_ciphertexts) append(pc, ct);
+            append(r, proofs[i].inner);
+        }
+        check(eg_verify_range_batch(ctx_, &range, label.c_str(), cts.size(), c.data(), range.n_rings > 1 ? pc.data() : nullptr, r.data(), v.data()));
+        return to_verdicts(v);
+    }
+
+    // CommitmentEquivalenceProof::verify over a batch (commitment.rs:198-248); `blinding_base` = H
+    void set_blinding_base(const Element &base) { check(eg_ctx_set_blinding_base(ctx_, base.data())); }
+    std::vector<Verdict> verify_commitment_equivalence_batch(const std::vector<Ciphertext> &cts, const std::vector<Element> &commitments,
+                                                             const std::vector<CommitmentEquivalenceProof> &proofs, const std::string &label) {
+        if (cts.size() != proofs.size() || cts.size() != commitments.size()) throw Error(EG_ERR_LEN_MISMATCH, "batch size mismatch");
+        std::vector<uint8_t> c, k, p, v(cts.size());
+        for (size_t i = 0; i < cts.size(); i++) {
+            append(c, cts[i]);
+            k.insert(k.end(), commitments[i].begin(), commitments[i].end());
+            for (const Scalar *s : {&proofs[i].challenge, &proofs[i].randomness_response, &proofs[i].value_response, &proofs[i].commitment_response})
+                p.insert(p.end(), s->begin(), s->end());
+        }
+        check(eg_verify_commitment_equiv_batch(ctx_, label.c_str(), cts.size(), c.data(), k.data(), p.data(), v.data()));
+        return to_verdicts(v);
+    }
+
+    // ProofOfPossession::verify over a batch of proofs for `keys_per_proof` keys each (possession.rs:137-163)
+    std::vector<Verdict> verify_possession_batch(const std::vector<std::vector<PublicKey>> &keys, const std::vector<ProofOfPossession> &proofs,
+                                                 const std::string &label) {
+        if (keys.size() != proofs.size()) throw Error(EG_ERR_LEN_MISMATCH, "batch size mismatch");
+        if (keys.empty()) return {};
+        const size_t kpp = keys[0].size();
+        std::vector<uint8_t> k, p, v(keys.size());
+        for (size_t i = 0; i < keys.size(); i++) {
+            if (keys[i].size() != kpp || proofs[i].responses.size() != kpp) throw Error(EG_ERR_LEN_MISMATCH, "public keys");   // possession.rs:147
+            for (const auto &key : keys[i]) k.insert(k.end(), key.bytes.begin(), key.bytes.end());
+            p.insert(p.end(), proofs[i].challenge.begin(), proofs[i].challenge.end());
+            for (const auto &s : proofs[i].responses) p.insert(p.end(), s.begin(), s.end());
+        }
+        check(eg_verify_possession_batch(ctx_, label.c_str(), (uint32_t)kpp, keys.size(), k.data(), p.data(), v.data()));
+        return to_verdicts(v);
     }
 
     eg_ctx *raw() { return ctx_; }

@@ -33,6 +33,17 @@ def test_rust_sys_crate_declares_every_symbol():
     assert names <= declared, sorted(names - declared)
 
 
+def test_headers_compile_as_c99_and_cxx17(tmp_path):
+    """include/eg_b200.h is plain C (what cgo / bindgen / ctypes consume); the .hpp mirror is header-only C++17."""
+    import subprocess
+    c = tmp_path / "t.c"
+    c.write_text('#include "eg_b200.h"\nint main(void) { return eg_version() == 0; }\n')
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", str(ROOT / "include"), "-fsyntax-only", str(c)], check=True)
+    cpp = tmp_path / "t.cpp"
+    cpp.write_text('#include "elastic_elgamal_b200.hpp"\nint main() { return 0; }\n')
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-I", str(ROOT / "include"), "-fsyntax-only", str(cpp)], check=True)
+
+
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():
