@@ -437,6 +437,9 @@ struct eg_ctx {
     uint64_t kind_tasks[2] = {0, 0}, kind_launches[2] = {0, 0};   // per kind, current call
     float kind_ms[2] = {0, 0};
     // grow-only scratch
+    cudaStream_t copy_stream = nullptr;     // host -> device prefetch of the next chunk
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr};
+    dev_buf in2[3];
     dev_buf pts, enc, commit, chal, flags, res[3], in[4], verdicts, partial, running, adm, misc, slots, consts, res_big;
     size_t adm_used = 0;      // cached points in `adm` (32 words each); entries 0,1 = the [O, G] pair
     std::map<std::string, std::vector<uint64_t>> adm_cache_key;
@@ -1022,6 +1025,8 @@ extern "C" eg_status eg_ctx_create(int device_id, eg_ctx **out) {
     if (cudaSetDevice(device_id) != cudaSuccess) return bail(EG_ERR_NO_DEVICE);
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(EG_ERR_CUDA);
     for (auto &e : ctx->ev) if (cudaEventCreate(&e) != cudaSuccess) return bail(EG_ERR_CUDA);
+    if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(EG_ERR_CUDA);
+    for (auto &e : ctx->ev_h2d) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return bail(EG_ERR_CUDA);
     if (cudaMalloc(&ctx->d_table_g, EG_FCHUNK_TABLE_WORDS * 4) != cudaSuccess) return bail(EG_ERR_OUT_OF_MEMORY);
     if (cudaMalloc(&ctx->d_table_k, EG_FCHUNK_TABLE_WORDS * 4) != cudaSuccess) return bail(EG_ERR_OUT_OF_MEMORY);
     if (cudaMalloc(&ctx->d_status, 1024) != cudaSuccess) return bail(EG_ERR_OUT_OF_MEMORY);
@@ -1036,7 +1041,8 @@ extern "C" void eg_ctx_destroy(eg_ctx *ctx) {
     cudaSetDevice(ctx->device);
     dev_buf *bufs[] = {&ctx->pts, &ctx->enc, &ctx->commit, &ctx->chal, &ctx->flags, &ctx->res[0], &ctx->res[1], &ctx->res[2],
                        &ctx->in[0], &ctx->in[1], &ctx->in[2], &ctx->in[3], &ctx->verdicts, &ctx->partial, &ctx->running,
-                       &ctx->adm, &ctx->misc, &ctx->slots, &ctx->consts, &ctx->res_big, &ctx->ring_scratch};
+                       &ctx->adm, &ctx->misc, &ctx->slots, &ctx->consts, &ctx->res_big, &ctx->ring_scratch,
+                       &ctx->in2[0], &ctx->in2[1], &ctx->in2[2]};
     for (dev_buf *b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->d_table_g) cudaFree(ctx->d_table_g);
     if (ctx->d_table_k) cudaFree(ctx->d_table_k);
@@ -1044,6 +1050,8 @@ extern "C" void eg_ctx_destroy(eg_ctx *ctx) {
     if (ctx->d_status) cudaFree(ctx->d_status);
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
     for (auto &e : ctx->commit_ev) if (e) cudaEventDestroy(e);
+    for (auto &e : ctx->ev_h2d) if (e) cudaEventDestroy(e);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -1570,16 +1578,36 @@ extern "C" eg_status eg_verify_choice_batch(eg_ctx *ctx, size_t n, uint32_t opti
     TRY(ensure(ctx, ctx->misc, 64 * (size_t)options));
     TRY(ensure(ctx, ctx->partial, (size_t)2 * options * EG_TALLY_BLOCKS * 128));
     TRY(ensure(ctx, ctx->running, (size_t)2 * options * 128));
+    // Double-buffered input staging: while chunk k is verified on the compute stream, chunk k + 1 is copied host -> device
+    // on the copy stream into the other buffer (its previous reader, chunk k - 1, finished before the end-of-chunk
+    // synchronisation of the previous iteration).  With pinned host memory the copies disappear behind the kernels.
+    dev_buf *bufs[2][3] = {{&ctx->in[0], &ctx->in[1], &ctx->in[2]}, {&ctx->in2[0], &ctx->in2[1], &ctx->in2[2]}};
+    const bool two = n > chunk;
+    if (two) {
+        TRY(ensure(ctx, ctx->in2[0], cm * 64 * options));
+        TRY(ensure(ctx, ctx->in2[1], cm * ring_stride));
+        TRY(ensure(ctx, ctx->in2[2], cm * 64));
+    }
+    auto prefetch = [&](size_t off, int b) -> eg_status {
+        const size_t m = std::min(chunk, n - off);
+        cudaStream_t cs = two ? ctx->copy_stream : ctx->stream;
+        CU(cudaMemcpyAsync(bufs[b][0]->p, choices + 64 * options * off, m * 64 * options, cudaMemcpyHostToDevice, cs));
+        CU(cudaMemcpyAsync(bufs[b][1]->p, rings + ring_stride * off, m * ring_stride, cudaMemcpyHostToDevice, cs));
+        if (single) CU(cudaMemcpyAsync(bufs[b][2]->p, sums + 64 * off, m * 64, cudaMemcpyHostToDevice, cs));
+        if (two) CU(cudaEventRecord(ctx->ev_h2d[b], cs));
+        return EG_SUCCESS;
+    };
     bool first = true;
-    for (size_t off = 0; off < n; off += chunk) {
+    int b = 0;
+    if (n) TRY(prefetch(0, 0));
+    for (size_t off = 0; off < n; off += chunk, b ^= 1) {
         size_t m = std::min(chunk, n - off);
-        CU(cudaMemcpyAsync(ctx->in[0].p, choices + 64 * options * off, m * 64 * options, cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemcpyAsync(ctx->in[1].p, rings + ring_stride * off, m * ring_stride, cudaMemcpyHostToDevice, ctx->stream));
-        if (single) CU(cudaMemcpyAsync(ctx->in[2].p, sums + 64 * off, m * 64, cudaMemcpyHostToDevice, ctx->stream));
-        TRY(verify_choice_chunk(ctx, m, options, single, (const uint8_t *)ctx->in[0].p, (const uint8_t *)ctx->in[1].p,
-                                single ? (const uint8_t *)ctx->in[2].p : nullptr, (uint8_t *)ctx->verdicts.p, tally != nullptr, first));
+        if (two) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[b], 0));
+        TRY(verify_choice_chunk(ctx, m, options, single, (const uint8_t *)bufs[b][0]->p, (const uint8_t *)bufs[b][1]->p,
+                                single ? (const uint8_t *)bufs[b][2]->p : nullptr, (uint8_t *)ctx->verdicts.p, tally != nullptr, first));
         first = false;
         CU(cudaMemcpyAsync(verdicts + off, ctx->verdicts.p, m, cudaMemcpyDeviceToHost, ctx->stream));
+        if (off + chunk < n) TRY(prefetch(off + chunk, b ^ 1));
         CU(cudaStreamSynchronize(ctx->stream));
         collect_timings(ctx, acc);
     }

@@ -705,3 +705,67 @@ def check_multi_mul(e, n=12):
                 assert not ok[i] and bytes(out[i]) == bytes(32)
             else:
                 assert ok[i] and bytes(out[i]) == expected[i], (terms, i)
+
+
+# ---------------------------------------------------------------- randomized differential tests
+
+def _flip_random(arrs, rnd, items, flips_per_item=1):
+    """Flips random bits at random byte positions of random items across the given (n, ...) uint8 arrays."""
+    flat = [a.reshape(a.shape[0], -1) for a in arrs]
+    sizes = [f.shape[1] for f in flat]
+    total = sum(sizes)
+    for i in items:
+        for _ in range(flips_per_item):
+            pos = rnd.randrange(total)
+            for f, sz in zip(flat, sizes):
+                if pos < sz:
+                    f[i, pos] ^= 1 << rnd.randrange(8)
+                    break
+                pos -= sz
+
+
+def check_fuzz_differential(e, pk, n=64, seed=1):
+    """Random single- and multi-bit corruption anywhere in the inputs (points, scalars, proofs): the GPU verdict must
+    equal the oracle's for every item -- malformed encodings, non-canonical scalars and plain mismatches alike."""
+    rnd = random.Random(seed)
+    half = list(range(0, n, 2))
+    # EncryptedChoice
+    cts, rings, sums = O.gen_choice_batch(pk, 3, W.SEED_CHOICE, n)
+    cts, rings, sums = cts.copy(), rings.copy(), sums.copy()
+    _flip_random([cts, rings, sums], rnd, half, flips_per_item=rnd.choice([1, 2, 5]))
+    ov, ot = O.verify_choice_batch(pk, 3, True, cts, rings, sums)
+    gv, gt = e.verify_choice(3, cts, rings, sums)
+    assert gv.tolist() == ov.tolist() and (gt == ot).all()
+    assert (ov[1::2] == 0).all() and (ov[half] != 0).sum() >= len(half) - 2
+    # bool
+    bc, bp = O.gen_bool_batch(pk, W.SEED_CHOICE, n)
+    bc, bp = bc.copy(), bp.copy()
+    _flip_random([bc, bp], rnd, half)
+    assert e.verify_bool(bc, bp).tolist() == O.verify_bool_batch(pk, bc, bp).tolist()
+    # RangeProof
+    spec = O.range_optimal(21)
+    espec = to_engine_range(e, spec)
+    values = np.array([rnd.randrange(21) for _ in range(n)], np.uint64)
+    rc, rp, rr = O.gen_range_batch(pk, spec, "ciphertext_range", W.SEED_CHOICE, values)
+    rc, rp, rr = rc.copy(), rp.copy(), rr.copy()
+    _flip_random([rc, rp, rr], rnd, half)
+    assert e.verify_range(espec, "ciphertext_range", rc, rp, rr).tolist() == O.verify_range_batch(pk, spec, "ciphertext_range", rc, rp, rr).tolist()
+    # QuadraticVotingBallot
+    p, ep = O.qv_params(3, 15), e.qv_params(3, 15)
+    votes = np.array([[rnd.randrange(3), rnd.randrange(3), rnd.randrange(2)] for _ in range(n // 2)], np.uint64)
+    ballots = O.gen_qv_batch(pk, p, W.SEED_QV, votes).copy()
+    _flip_random([ballots], rnd, list(range(0, n // 2, 2)))
+    ov, ot = O.verify_qv_batch(pk, p, ballots)
+    gv, gt = e.verify_qv(ep, ballots)
+    assert gv.tolist() == ov.tolist() and (gt == ot).all()
+    # CommitmentEquivalenceProof
+    e.set_blinding_base(BLINDING_BASE)
+    cc, cm, cp = O.gen_ceq_batch(pk, BLINDING_BASE, "fuzz", W.SEED_CHOICE, np.arange(n, dtype=np.uint64))
+    cc, cm, cp = cc.copy(), cm.copy(), cp.copy()
+    _flip_random([cc, cm, cp], rnd, half)
+    assert e.verify_commitment_equiv("fuzz", cc, cm, cp).tolist() == O.verify_ceq_batch(pk, BLINDING_BASE, "fuzz", cc, cm, cp).tolist()
+    # ProofOfPossession
+    keys, proofs = O.gen_pop_batch(3, "fuzz_pop", bytes([12] * 32), n)
+    keys, proofs = keys.copy(), proofs.copy()
+    _flip_random([keys, proofs], rnd, half)
+    assert e.verify_possession("fuzz_pop", keys, proofs).tolist() == O.verify_pop_batch("fuzz_pop", keys, proofs).tolist()

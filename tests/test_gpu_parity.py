@@ -238,3 +238,8 @@ def test_encrypt_plain_and_zero(env):
 
 def test_multi_mul(env):
     PC.check_multi_mul(env[0], n=64)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_fuzz_differential(env, seed):
+    PC.check_fuzz_differential(env[0], env[2], n=400, seed=seed)

@@ -157,3 +157,8 @@ def test_encrypt_plain_and_zero(env):
 
 def test_multi_mul(env):
     PC.check_multi_mul(env[0], n=6)
+
+
+@pytest.mark.parametrize("seed", [1])
+def test_fuzz_differential(env, seed):
+    PC.check_fuzz_differential(env[0], env[2], n=8, seed=seed)
