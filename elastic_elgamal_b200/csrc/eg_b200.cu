@@ -294,6 +294,11 @@ __global__ void __launch_bounds__(256) k_scalars_validate(const uint8_t *s, size
     if (i < n) scalars_validate_body(i, s, ok);
 }
 
+__global__ void __launch_bounds__(256) k_keyset_verdict(const keyset_verdict_params P) {
+    size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid < P.n) keyset_verdict_body(P, tid);
+}
+
 __global__ void __launch_bounds__(256) k_unpack(const unpack_params P) {
     size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid < P.n) unpack_body(P, tid);
@@ -837,6 +842,15 @@ static void launch_scalars_validate(eg_ctx *ctx, const uint8_t *sc_in, size_t n,
     EG_FOR_HOST(n, scalars_validate_body(tid, sc_in, ok))
 #else
     k_scalars_validate<<<grid_for(n, 256), 256, 0, ctx->stream>>>(sc_in, n, ok);
+#endif
+    ctx->launches++;
+}
+
+static void launch_keyset_verdict(eg_ctx *ctx, const keyset_verdict_params &P) {
+#ifdef EG_HOSTSIM
+    EG_FOR_HOST(P.n, keyset_verdict_body(P, tid))
+#else
+    k_keyset_verdict<<<grid_for(P.n, 256), 256, 0, ctx->stream>>>(P);
 #endif
     ctx->launches++;
 }
@@ -2634,6 +2648,119 @@ extern "C" eg_status eg_multi_mul_batch(eg_ctx *ctx, size_t n, uint32_t terms, c
         launch_unpack(ctx, up);
         CU(cudaMemcpyAsync(out + off * 32, ctx->in[2].p, k * 32, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaMemcpyAsync(ok + off, ctx->verdicts.p, k, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    return finish_call(ctx);
+}
+
+// =================================================================== PublicKeySet::from_participants
+
+// sharing/key_set.rs:87-144 for n_sets key sets of the same (shares, threshold): reconstruct the shared key from the
+// first `threshold` participant keys (Lagrange interpolation at 0) and check that every other participant key is the
+// interpolation of the same polynomial.  All coefficients depend only on (shares, threshold): computed once on the host
+// (lagrange_coefficients sharing/mod.rs:139-170, invert_scalars on 1..=n key_set.rs:106-110), with the common scale folded
+// into them ((sum c_i K_i) * s == sum (c_i s) K_i).  threshold <= 16.  No receiver key needed.
+extern "C" eg_status eg_keysets_validate_batch(eg_ctx *ctx, uint32_t shares, uint32_t threshold, size_t n_sets, const uint8_t *keys,
+                                               uint8_t *shared_keys, uint8_t *verdicts) {
+    if (!ctx) return EG_ERR_INVALID_ARG;
+    CU(cudaSetDevice(ctx->device));
+    ctx->err.clear(); ctx->commit_ev_used = 0; ctx->call_commit_tasks = 0; ctx->call_commit_launches = 0; ctx->kind_tasks[0] = ctx->kind_tasks[1] = 0; ctx->kind_launches[0] = ctx->kind_launches[1] = 0;
+    if (shares == 0 || shares > 64 || threshold == 0 || threshold > shares || threshold > EG_MSM_MAXV)
+        return fail(ctx, EG_ERR_INVALID_ARG, "need 1 <= threshold <= shares <= 64 and threshold <= 16");
+    if (n_sets == 0) return EG_SUCCESS;
+    if (!keys || !shared_keys || !verdicts) return fail(ctx, EG_ERR_INVALID_ARG, "null pointer");
+    const uint32_t N = shares, T = threshold, n_out = 1 + (N - T);
+    // ---- constants
+    std::vector<uint32_t> coeff((size_t)8 * T * n_out);
+    {
+        sc denom[EG_MSM_MAXV], scale = sc_from_u64(1), inv[64];
+        for (uint32_t a = 0; a < T; a++) {
+            bool sign = false;
+            sc mag = sc_from_u64(1);
+            for (uint32_t b2 = 0; b2 < T; b2++) {
+                sc e;
+                if (a > b2) { sign = !sign; e = sc_from_u64(a - b2); }
+                else if (a < b2) e = sc_from_u64(b2 - a);
+                else e = sc_from_u64((uint64_t)a + 1);
+                sc_mul(mag, mag, e);
+            }
+            if (sign) sc_neg(mag, mag);
+            sc_invert(denom[a], mag);
+            sc e = sc_from_u64((uint64_t)a + 1);
+            sc_mul(scale, scale, e);
+        }
+        for (uint32_t i = 0; i < N; i++) sc_invert(inv[i], sc_from_u64((uint64_t)i + 1));
+        for (uint32_t a = 0; a < T; a++) {
+            sc c;
+            sc_mul(c, denom[a], scale);
+            for (int w = 0; w < 8; w++) coeff[8 * a + w] = c.v[w];
+        }
+        for (uint32_t x = T; x < N; x++) {
+            sc key_scale = sc_from_u64(1);
+            for (uint32_t idx = 0; idx < T; idx++) sc_mul(key_scale, key_scale, sc_from_u64((uint64_t)(x - idx)));
+            if (T % 2 == 0) sc_neg(key_scale, key_scale);
+            for (uint32_t idx = 0; idx < T; idx++) {
+                sc c;
+                sc_mul(c, denom[idx], sc_from_u64((uint64_t)idx + 1));
+                sc_mul(c, c, inv[x - idx - 1]);
+                sc_mul(c, c, key_scale);
+                for (int w = 0; w < 8; w++) coeff[8 * ((size_t)T * (1 + x - T) + idx) + w] = c.v[w];
+            }
+        }
+    }
+    TRY(ensure(ctx, ctx->consts, 64 * 1024 + coeff.size() * 4));
+    uint32_t *d_coeff = (uint32_t *)((uint8_t *)ctx->consts.p + 64 * 1024);
+    CU(cudaMemcpyAsync(d_coeff, coeff.data(), coeff.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<msm_slot> slots(n_out);
+    for (uint32_t o = 0; o < n_out; o++) {
+        msm_slot &z = slots[o];
+        memset(&z, 0, sizeof z);
+        z.nv = (uint8_t)T; z.nf = 0; z.out_enc = 1; z.out_index = o;
+        for (uint32_t j = 0; j < T; j++) { z.p_index[j] = j; z.vs[j] = src_const(T * o + j); }
+    }
+    TRY(upload_slots(ctx, slots));
+    const size_t chunk = std::max<size_t>(256, default_chunk(ctx) / N), cm = std::min(chunk, n_sets);
+    TRY(ensure(ctx, ctx->in[0], cm * 32 * N));
+    TRY(ensure(ctx, ctx->in[1], cm * 32));
+    TRY(ensure(ctx, ctx->verdicts, cm));
+    TRY(ensure(ctx, ctx->pts, cm * N * 128));
+    TRY(ensure(ctx, ctx->commit, cm * n_out * 32));
+    TRY(ensure(ctx, ctx->flags, cm * 4));
+    for (size_t off = 0; off < n_sets; off += chunk) {
+        const size_t k = std::min(chunk, n_sets - off);
+        CU(cudaMemcpyAsync(ctx->in[0].p, keys + off * 32 * N, k * 32 * N, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemsetAsync(ctx->flags.p, 0, k * 4, ctx->stream));
+        in_bufs in;
+        memset(&in, 0, sizeof in);
+        in.buf[0] = (const uint8_t *)ctx->in[0].p; in.stride[0] = 32 * N;
+        for (uint32_t q0 = 0; q0 < N; q0 += EG_MAX_SLOTS) {
+            decode_params dp;
+            memset(&dp, 0, sizeof dp);
+            dp.in = in; dp.n = k;
+            int ns = 0;
+            for (uint32_t q = q0; q < N && ns < EG_MAX_SLOTS; q++, ns++) {
+                decode_slot &d = dp.slots[ns];
+                d.buf = 0; d.reject_identity = 1; d.offset = 32 * q; d.p_index = q;
+            }
+            dp.n_slots = ns;
+            dp.pts = (uint32_t *)ctx->pts.p; dp.enc = nullptr; dp.flags = (uint32_t *)ctx->flags.p;
+            launch_decode(ctx, dp);
+        }
+        msm_params mp;
+        memset(&mp, 0, sizeof mp);
+        mp.in = in; mp.n = k; mp.n_slots = (int)n_out; mp.slots = (const msm_slot *)ctx->slots.p;
+        mp.pts = (const uint32_t *)ctx->pts.p; mp.const_scalars = d_coeff; mp.commit = (uint32_t *)ctx->commit.p;
+        mp.pts_out = (uint32_t *)ctx->pts.p;
+        mp.table_g = ctx->d_table_g; mp.table_k = ctx->has_receiver ? ctx->d_table_k : ctx->d_table_g;
+        launch_msm(ctx, mp);
+        keyset_verdict_params vp;
+        memset(&vp, 0, sizeof vp);
+        vp.n = k; vp.shares = N; vp.threshold = T; vp.keys = (const uint8_t *)ctx->in[0].p;
+        vp.commit = (const uint32_t *)ctx->commit.p; vp.flags = (const uint32_t *)ctx->flags.p;
+        vp.shared_out = (uint8_t *)ctx->in[1].p; vp.verdicts = (uint8_t *)ctx->verdicts.p; vp.code_mismatch = EG_V_MALFORMED_PARTICIPANT_KEYS;
+        launch_keyset_verdict(ctx, vp);
+        CU(cudaMemcpyAsync(shared_keys + off * 32, ctx->in[1].p, k * 32, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(verdicts + off, ctx->verdicts.p, k, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
     }
     return finish_call(ctx);

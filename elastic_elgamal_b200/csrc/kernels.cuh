@@ -1236,6 +1236,38 @@ EG_HD void unpack_body(const unpack_params &P, size_t item) {
     P.ok[item] = bad ? 0 : 1;
 }
 
+// PublicKeySet::from_participants verdict (key_set.rs:128-140): interpolated key x (planar commit index 1 + (x - t)) must equal
+// participant key x byte for byte (both are canonical encodings); planar commit 0 is the reconstructed shared key.
+struct keyset_verdict_params {
+    size_t n;
+    uint32_t shares, threshold;
+    const uint8_t *keys;            // n * shares * 32
+    const uint32_t *commit;         // planar encodings
+    const uint32_t *flags;
+    uint8_t *shared_out;            // n * 32
+    uint8_t *verdicts;
+    uint8_t code_mismatch;
+};
+
+EG_HD void keyset_verdict_body(const keyset_verdict_params &P, size_t item) {
+    uint32_t w[8], k[8];
+    uint8_t v = 0;
+    if (P.flags[item] & 1u) v = 1;
+    else {
+        for (uint32_t x = P.threshold; x < P.shares; x++) {
+            planar_load_words(w, P.commit, P.n, 1 + (x - P.threshold), 8, item);
+            load32_bytes(k, P.keys + (item * P.shares + x) * 32);
+            bool same = true;
+            for (int q = 0; q < 8; q++) same = same && (w[q] == k[q]);
+            if (!same) { v = P.code_mismatch; break; }
+        }
+    }
+    planar_load_words(w, P.commit, P.n, 0, 8, item);
+    if (v) for (int q = 0; q < 8; q++) w[q] = 0;
+    store32_bytes(P.shared_out + 32 * item, w);
+    P.verdicts[item] = v;
+}
+
 // ------------------------------------------------------------------ wire format: Base64UrlUnpadded (serde.rs:19-80)
 //
 // Human-readable serde forms of every element / scalar / proof are unpadded base64url strings (serialize_bytes

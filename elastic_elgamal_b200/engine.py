@@ -309,6 +309,13 @@ class Engine:
         self._check(self.lib.eg_verify_shares_batch(self.h, C.byref(keyset), n, s, idx, _addr(cts), _addr(shares), _addr(proofs), _addr(v)))
         return v
 
+    def keysets_validate(self, shares, threshold, keys):
+        keys = _u8(keys, (-1, shares, 32))
+        n = keys.shape[0]
+        shared, v = np.empty((n, 32), np.uint8), np.empty(n, np.uint8)
+        self._check(self.lib.eg_keysets_validate_batch(self.h, shares, threshold, n, _addr(keys), _addr(shared), _addr(v)))
+        return shared, v
+
     def dlog_table(self, lo, hi):
         return DlogTable(self, lo, hi)
 

@@ -59,6 +59,7 @@ enum {
     EG_V_CHOICE_RANGE = 4,        /* ChoiceVerificationError::Range, src/app/choice.rs:379 */
     EG_V_QV_CREDIT_RANGE = 5,     /* QuadraticVotingError::CreditRange, src/app/quadratic_voting.rs:315-316 */
     EG_V_QV_CREDIT_EQUIV = 6,     /* QuadraticVotingError::CreditEquivalence, src/app/quadratic_voting.rs:325-326 */
+    EG_V_MALFORMED_PARTICIPANT_KEYS = 7,  /* sharing::Error::MalformedParticipantKeys, src/sharing/key_set.rs:137-139 */
     EG_V_QV_VARIANT_BASE = 16     /* + option index: QuadraticVotingError::Variant{index}, src/app/quadratic_voting.rs:305 */
 };
 
@@ -203,6 +204,15 @@ eg_status eg_verify_commitment_equiv_batch(eg_ctx *ctx, const char *transcript_l
 eg_status eg_verify_possession_batch(eg_ctx *ctx, const char *transcript_label, uint32_t keys_per_proof, size_t n,
                                      const uint8_t *keys /* n*keys_per_proof*32 */,
                                      const uint8_t *proofs /* n*(1+keys_per_proof)*32 */, uint8_t *verdicts /* n */);
+
+/* PublicKeySet::from_participants (src/sharing/key_set.rs:87-144) over n_sets key sets with the same (shares, threshold),
+ * threshold <= 16: reconstructs each shared key from the first `threshold` participant keys and checks that the other
+ * participant keys lie on the same polynomial.  verdicts: EG_V_OK (shared_keys[i] set), EG_V_MALFORMED (a key does not
+ * decode or is the identity), EG_V_MALFORMED_PARTICIPANT_KEYS.  `ParticipantCountMismatch` cannot occur in a fixed-stride
+ * batch.  Needs no receiver key. */
+eg_status eg_keysets_validate_batch(eg_ctx *ctx, uint32_t shares, uint32_t threshold, size_t n_sets,
+                                    const uint8_t *keys /* n_sets*shares*32 */, uint8_t *shared_keys /* n_sets*32 */,
+                                    uint8_t *verdicts /* n_sets */);
 
 /* DiscreteLogTable::new (src/encryption.rs:267-284) for the values lo..hi (exclusive); lives on the device */
 eg_status eg_dlog_table_create(eg_ctx *ctx, uint64_t lo, uint64_t hi, eg_dlog_table **out);

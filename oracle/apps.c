@@ -1044,3 +1044,48 @@ int eo_verify_pop_batch(uint32_t k, const char *label, size_t n, const uint8_t *
     parallel_for(verify_pop_item, &c, n, threads);
     return 0;
 }
+
+/* ================================================================== PublicKeySet::from_participants (sharing/key_set.rs:87-144)
+ * Returns 0 and the shared key when the participant keys are consistent, EO_MALFORMED when a key is not a valid
+ * PublicKey (keys/mod.rs:161-176), EO_MALFORMED_PARTICIPANT_KEYS (Error::MalformedParticipantKeys) otherwise;
+ * -1 for invalid parameters (ParticipantCountMismatch is the caller's framing: the batch has a fixed stride). */
+int eo_keyset_from_participants(uint32_t shares, uint32_t threshold, const uint8_t *keys, uint8_t shared_key[32]) {
+    if (shares == 0 || shares > 64 || threshold == 0 || threshold > shares) return -1;
+    eo_pk pk[64];
+    for (uint32_t i = 0; i < shares; i++)
+        if (eo_pk_from_bytes(&pk[i], keys + 32 * i)) return EO_MALFORMED;
+    uint32_t indexes[64];
+    for (uint32_t i = 0; i < threshold; i++) indexes[i] = i;
+    eo_sc denominators[64], scale;
+    lagrange(indexes, threshold, denominators, &scale);
+    eo_pt starting[64], acc, shared;
+    for (uint32_t i = 0; i < threshold; i++) starting[i] = pk[i].element;
+    eo_pt_multi_mul(&acc, denominators, starting, threshold);
+    eo_pt_mul(&shared, &scale, &acc);
+    eo_sc inverses[64];
+    for (uint32_t i = 0; i < shares; i++) {        /* invert_scalars on 1..=n (key_set.rs:106-110) */
+        eo_sc v;
+        eo_sc_from_u64(&v, (uint64_t)i + 1);
+        eo_sc_invert(&inverses[i], &v);
+    }
+    for (uint32_t x = threshold; x < shares; x++) {
+        eo_sc key_scale, kd[64], e;
+        eo_sc_from_u64(&key_scale, 1);
+        for (uint32_t idx = 0; idx < threshold; idx++) {
+            eo_sc_from_u64(&e, (uint64_t)(x - idx));
+            eo_sc_mul(&key_scale, &key_scale, &e);
+        }
+        for (uint32_t idx = 0; idx < threshold; idx++) {
+            eo_sc_from_u64(&e, (uint64_t)idx + 1);
+            eo_sc_mul(&kd[idx], &denominators[idx], &e);
+            eo_sc_mul(&kd[idx], &kd[idx], &inverses[x - idx - 1]);
+        }
+        if (threshold % 2 == 0) eo_sc_neg(&key_scale, &key_scale);
+        eo_pt interpolated, scaled;
+        eo_pt_multi_mul(&interpolated, kd, starting, threshold);
+        eo_pt_mul(&scaled, &key_scale, &interpolated);
+        if (!eo_pt_eq(&scaled, &pk[x].element)) return EO_MALFORMED_PARTICIPANT_KEYS;
+    }
+    eo_pt_encode(shared_key, &shared);
+    return 0;
+}

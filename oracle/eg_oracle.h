@@ -120,6 +120,7 @@ enum {
     EO_CHOICE_RANGE = 4,        /* ChoiceVerificationError::Range (choice.rs:379) */
     EO_QV_CREDIT_RANGE = 5,     /* QuadraticVotingError::CreditRange (quadratic_voting.rs:315-316) */
     EO_QV_CREDIT_EQUIV = 6,     /* QuadraticVotingError::CreditEquivalence (quadratic_voting.rs:325-326) */
+    EO_MALFORMED_PARTICIPANT_KEYS = 7,  /* sharing::Error::MalformedParticipantKeys (sharing/key_set.rs:137-139) */
     EO_QV_VARIANT_BASE = 16     /* + option index: QuadraticVotingError::Variant (quadratic_voting.rs:305) */
 };
 
@@ -265,6 +266,10 @@ int  eo_gen_pop_batch(uint32_t k, const char *label, const uint8_t seed[32], siz
                       uint8_t *proofs, int threads);
 int  eo_verify_pop_batch(uint32_t k, const char *label, size_t n, const uint8_t *keys, const uint8_t *proofs,
                          uint8_t *verdicts, int threads);
+/* PublicKeySet::from_participants sharing/key_set.rs:87-144: verdict (EO_OK / EO_MALFORMED /
+ * EO_MALFORMED_PARTICIPANT_KEYS) and, when OK, the reconstructed shared key; -1 for invalid (shares, threshold). */
+int  eo_keyset_from_participants(uint32_t shares, uint32_t threshold, const uint8_t *keys /* shares*32 */,
+                                 uint8_t shared_key[32]);
 int  eo_hw_threads(void);
 
 #ifdef __cplusplus

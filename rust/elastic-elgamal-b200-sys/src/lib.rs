@@ -33,6 +33,7 @@ pub const EG_V_CHOICE_SUM: u8 = 3;
 pub const EG_V_CHOICE_RANGE: u8 = 4;
 pub const EG_V_QV_CREDIT_RANGE: u8 = 5;
 pub const EG_V_QV_CREDIT_EQUIV: u8 = 6;
+pub const EG_V_MALFORMED_PARTICIPANT_KEYS: u8 = 7;
 pub const EG_V_QV_VARIANT_BASE: u8 = 16;
 
 #[repr(C)]
@@ -94,6 +95,8 @@ extern "C" {
     pub fn eg_verify_shares_batch(ctx: *mut eg_ctx, keyset: *const eg_keyset, n_tallies: usize, n_shares: u32,
                                   indexes: *const u32, cts: *const u8, shares: *const u8, proofs: *const u8,
                                   verdicts: *mut u8) -> eg_status;
+    pub fn eg_keysets_validate_batch(ctx: *mut eg_ctx, shares: u32, threshold: u32, n_sets: usize, keys: *const u8,
+                                     shared_keys: *mut u8, verdicts: *mut u8) -> eg_status;
     pub fn eg_dlog_table_create(ctx: *mut eg_ctx, lo: u64, hi: u64, out: *mut *mut eg_dlog_table) -> eg_status;
     pub fn eg_dlog_table_destroy(table: *mut eg_dlog_table);
     pub fn eg_combine_decrypt_batch(ctx: *mut eg_ctx, threshold: u32, indexes: *const u32, n_tallies: usize,

@@ -14,7 +14,7 @@ LIB_PATH = ORACLE_DIR / "liboracle.so"
 
 EO_MAX_RINGS = 64
 
-OK, MALFORMED, CHALLENGE_MISMATCH, CHOICE_SUM, CHOICE_RANGE, QV_CREDIT_RANGE, QV_CREDIT_EQUIV = range(7)
+OK, MALFORMED, CHALLENGE_MISMATCH, CHOICE_SUM, CHOICE_RANGE, QV_CREDIT_RANGE, QV_CREDIT_EQUIV, MALFORMED_PARTICIPANT_KEYS = range(8)
 QV_VARIANT_BASE = 16
 
 
@@ -511,6 +511,13 @@ def verify_pop_batch(label, keys, proofs, threads=0):
     keys, proofs = np.ascontiguousarray(keys), np.ascontiguousarray(proofs)
     assert lib().eo_verify_pop_batch(k, label.encode(), C.c_size_t(n), _ptr(keys), _ptr(proofs), _ptr(verdicts), threads) == 0
     return verdicts
+
+
+def keyset_from_participants(shares, threshold, keys):
+    """-> (verdict, shared_key or None)"""
+    out = buf(32)
+    rc = lib().eo_keyset_from_participants(shares, threshold, b"".join(bytes(k) for k in keys), out)
+    return rc, (raw(out) if rc == 0 else None)
 
 
 def hw_threads():

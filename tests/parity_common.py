@@ -769,3 +769,33 @@ def check_fuzz_differential(e, pk, n=64, seed=1):
     keys, proofs = keys.copy(), proofs.copy()
     _flip_random([keys, proofs], rnd, half)
     assert e.verify_possession("fuzz_pop", keys, proofs).tolist() == O.verify_pop_batch("fuzz_pop", keys, proofs).tolist()
+
+
+# ---------------------------------------------------------------- PublicKeySet::from_participants
+
+def check_keysets_validate(e, n_sets=8, shares=5, threshold=3, seed=13):
+    """key_set.rs:238-270: consistent sets restore the dealer's shared key; swapped / shifted keys are
+    MalformedParticipantKeys; undecodable or identity keys are malformed."""
+    rng = O.rng_from_seed(bytes([seed] * 32))
+    keys = np.zeros((n_sets, shares, 32), np.uint8)
+    shared_expected = []
+    for i in range(n_sets):
+        ks, _ = O.dealer_new(shares, threshold, rng)
+        for j in range(shares):
+            keys[i, j] = np.frombuffer(bytes(ks.participant_keys[j]), np.uint8)
+        shared_expected.append(bytes(ks.shared_key))
+    if n_sets >= 6 and shares > threshold and threshold > 1:
+        keys[1, [0, shares - 1]] = keys[1, [shares - 1, 0]]                                  # order of keys matters
+        keys[2, 1] = np.frombuffer(O.point_add(bytes(keys[2, 1]), W.G_ENC), np.uint8)        # one of the first t keys + G
+        keys[3, shares - 1] = np.frombuffer(O.point_add(bytes(keys[3, shares - 1]), W.G_ENC), np.uint8)
+        keys[4, 2] = np.frombuffer(W.BAD_POINT2, np.uint8)
+        keys[5, shares - 1] = 0                                                              # identity key
+    expected = [O.keyset_from_participants(shares, threshold, [bytes(k) for k in keys[i]]) for i in range(n_sets)]
+    shared, v = e.keysets_validate(shares, threshold, keys)
+    assert v.tolist() == [x[0] for x in expected], (v, expected)
+    for i in range(n_sets):
+        assert bytes(shared[i]) == (expected[i][1] if expected[i][0] == 0 else bytes(32))
+    assert expected[0] == (0, shared_expected[0])
+    if n_sets >= 6 and shares > threshold and threshold > 1:
+        assert [x[0] for x in expected[1:6]] == [O.MALFORMED_PARTICIPANT_KEYS] * 3 + [O.MALFORMED] * 2
+    assert e.keysets_validate(shares, threshold, keys[:0])[1].shape == (0,)

@@ -243,3 +243,8 @@ def test_multi_mul(env):
 @pytest.mark.parametrize("seed", [1, 2, 3])
 def test_fuzz_differential(env, seed):
     PC.check_fuzz_differential(env[0], env[2], n=400, seed=seed)
+
+
+@pytest.mark.parametrize("shares,threshold", [(5, 3), (10, 7), (4, 4), (3, 1), (6, 2), (40, 16), (64, 1)])
+def test_keysets_validate(env, shares, threshold):
+    PC.check_keysets_validate(env[0], n_sets=40, shares=shares, threshold=threshold)

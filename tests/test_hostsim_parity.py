@@ -162,3 +162,8 @@ def test_multi_mul(env):
 @pytest.mark.parametrize("seed", [1])
 def test_fuzz_differential(env, seed):
     PC.check_fuzz_differential(env[0], env[2], n=8, seed=seed)
+
+
+@pytest.mark.parametrize("shares,threshold", [(5, 3), (4, 4), (3, 1)])
+def test_keysets_validate(env, shares, threshold):
+    PC.check_keysets_validate(env[0], n_sets=6, shares=shares, threshold=threshold)
