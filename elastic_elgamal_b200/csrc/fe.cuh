@@ -205,8 +205,16 @@ namespace eg {
 static __device__ __noinline__ fe fe_mul_call(const fe a, const fe b) { fe r; fe_mul_portable(r, a, b); return r; }
 static __device__ __noinline__ fe fe_sq_call(const fe a) { fe r; fe_sq_portable(r, a); return r; }
 #else
-static __device__ __noinline__ fe fe_mul_call(const fe a, const fe b) { fe r; fe_mul_ptx(r, a, b); return r; }
-static __device__ __noinline__ fe fe_sq_call(const fe a) { fe r; fe_sq_ptx(r, a); return r; }
+#if defined(EG_FE_SHIFT_FOLD)
+// A/B variant: the 2^256 = 38 fold built from funnel shifts and add chains (ALU pipe) instead of 8 wide multiply-adds
+#define EG_FE_MUL_PTX fe_mul_ptx_sf
+#define EG_FE_SQ_PTX fe_sq_ptx_sf
+#else
+#define EG_FE_MUL_PTX fe_mul_ptx
+#define EG_FE_SQ_PTX fe_sq_ptx
+#endif
+static __device__ __noinline__ fe fe_mul_call(const fe a, const fe b) { fe r; EG_FE_MUL_PTX(r, a, b); return r; }
+static __device__ __noinline__ fe fe_sq_call(const fe a) { fe r; EG_FE_SQ_PTX(r, a); return r; }
 #endif
 #endif
 

@@ -64,6 +64,12 @@ class Prog:
                 v[dst] = t & M32
                 if op.endswith(".cc"):
                     cc = t >> 32
+            elif op == "shl":
+                v[dst] = (s[0] << s[1]) & M32
+            elif op == "shr":
+                v[dst] = s[0] >> s[1]
+            elif op == "shf.l":                       # funnel shift left: upper word of (hi:lo) << n
+                v[dst] = (((s[1] << 32) | s[0]) << s[2] >> 32) & M32
             else:
                 raise ValueError(op)
         return v
@@ -85,6 +91,12 @@ class Prog:
                 return str(x) if isinstance(x, int) else opmap.get(x, x)
             if op == "mov":
                 lines.append("mov.u32 %s, %s;" % (f(dst), f(src[0])))
+            elif op == "shl":
+                lines.append("shl.b32 %s, %s, %s;" % (f(dst), f(src[0]), f(src[1])))
+            elif op == "shr":
+                lines.append("shr.u32 %s, %s, %s;" % (f(dst), f(src[0]), f(src[1])))
+            elif op == "shf.l":
+                lines.append("shf.l.wrap.b32 %s, %s, %s, %s;" % (f(dst), f(src[0]), f(src[1]), f(src[2])))
             else:
                 lines.append("%s.u32 %s, %s;" % (op, f(dst), ", ".join(f(x) for x in src)))
         lines.append("}")
@@ -117,6 +129,41 @@ def fold(p, t, out):
     p.emit("mad.lo", out[0], c3, 38, r[0])  # wrapped value is tiny: stays inside limb 0
     for k in range(1, 8):
         p.emit("mov", out[k], r[k])
+
+
+def fold_shift(p, t, out):
+    """Same result as fold(), but 38 * t[8..15] = (h << 5) + (h << 2) + (h << 1) is built with funnel shifts and add
+    chains on the ALU pipe instead of eight wide multiply-adds on the (saturated) multiplier pipe."""
+    h = t[8:16]
+    r = [p.r("r%d" % i) for i in range(9)]
+    c3 = p.r("c3")
+    first = True
+    for sh in (5, 2, 1):
+        sv = [p.r("s%d_%d" % (sh, i)) for i in range(9)]
+        p.emit("shl", sv[0], h[0], sh)
+        for k in range(1, 8):
+            p.emit("shf.l", sv[k], h[k - 1], h[k], sh)
+        p.emit("shr", sv[8], h[7], 32 - sh)
+        base = t if first else r
+        p.emit("add.cc", r[0], base[0], sv[0])
+        for k in range(1, 8):
+            p.emit("addc.cc", r[k], base[k], sv[k])
+        if first:
+            p.emit("addc", r[8], sv[8], 0)
+        else:
+            p.emit("addc", r[8], r[8], sv[8])
+        first = False
+    # r[8] <= 31 + 3 + 1 + 3 carries: fold it once more (38 * r8 < 2^12)
+    p.emit("mad.lo.cc", r[0], r[8], 38, r[0])
+    for k in range(1, 8):
+        p.emit("addc.cc", r[k], r[k], 0)
+    p.emit("addc", c3, 0, 0)
+    p.emit("mad.lo", out[0], c3, 38, r[0])
+    for k in range(1, 8):
+        p.emit("mov", out[k], r[k])
+
+
+FOLD = fold
 
 
 def merge(p, e, o, t):
@@ -160,7 +207,7 @@ def gen_mul():
             chain(o, i - 1, [0, 2, 4, 6], b[i])
             chain(e, i + 1, [1, 3, 5, 7], b[i])
     merge(p, e, o, t)
-    fold(p, t, out)
+    FOLD(p, t, out)
     return p, a + b, out
 
 
@@ -200,7 +247,7 @@ def gen_sq():
     for i in range(8):
         p.emit("mad.lo.cc" if i == 0 else "madc.lo.cc", u[2 * i], a[i], a[i], u[2 * i])
         p.emit("madc.hi.cc" if i < 7 else "madc.hi", u[2 * i + 1], a[i], a[i], u[2 * i + 1])
-    fold(p, u, out)
+    FOLD(p, u, out)
     return p, a, out
 
 
@@ -259,7 +306,16 @@ def main():
             "// integers by the generator's PTX-subset interpreter and on the GPU against the oracle.\n"
             "#pragma once\nnamespace eg {\n\n")
     text += emit_function("fe_mul_ptx", pm, in_m, out_m, 2) + "\n"
-    text += emit_function("fe_sq_ptx", ps, in_s, out_s, 1) + "\n}  // namespace eg\n"
+    text += emit_function("fe_sq_ptx", ps, in_s, out_s, 1) + "\n"
+    # variant with the 2^256 = 38 fold on the ALU pipe (funnel shifts + add chains); selected by EG_FE_SHIFT_FOLD
+    global FOLD
+    FOLD = fold_shift
+    check(2000 if not args.check else 20000)
+    pm, in_m, out_m = gen_mul()
+    ps, in_s, out_s = gen_sq()
+    FOLD = fold
+    text += emit_function("fe_mul_ptx_sf", pm, in_m, out_m, 2) + "\n"
+    text += emit_function("fe_sq_ptx_sf", ps, in_s, out_s, 1) + "\n}  // namespace eg\n"
     pathlib.Path(args.out).write_text(text)
     print("wrote", args.out)
 

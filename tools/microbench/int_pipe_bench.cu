@@ -64,6 +64,25 @@ __global__ void __launch_bounds__(256) k_pipe(int iters, uint32_t a, uint32_t b,
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
 
+static __device__ __noinline__ eg::fe fe_mul_sf_call(const eg::fe a, const eg::fe b) {
+    eg::fe r;
+#if defined(__CUDA_ARCH__)
+    eg::fe_mul_ptx_sf(r, a, b);
+#else
+    eg::fe_mul_portable(r, a, b);
+#endif
+    return r;
+}
+static __device__ __noinline__ eg::fe fe_sq_sf_call(const eg::fe a) {
+    eg::fe r;
+#if defined(__CUDA_ARCH__)
+    eg::fe_sq_ptx_sf(r, a);
+#else
+    eg::fe_sq_portable(r, a);
+#endif
+    return r;
+}
+
 // dependent chain of field multiplications / squarings per thread (the unit of the library's roofline)
 template <int KIND>
 __global__ void __launch_bounds__(128) k_field(int iters, const uint32_t *seed, uint32_t *sink, long long *cycles) {
@@ -78,6 +97,8 @@ __global__ void __launch_bounds__(128) k_field(int iters, const uint32_t *seed, 
         if (KIND == 2) { eg::fe_mul_portable(x, x, y); eg::fe_mul_portable(y, y, x); }
         if (KIND == 3) { eg::fe_sq_portable(x, x); eg::fe_sq_portable(y, y); }
         if (KIND == 4) { eg::fe_add(x, x, y); eg::fe_sub(y, y, x); }
+        if (KIND == 5) { x = fe_mul_sf_call(x, y); y = fe_mul_sf_call(y, x); }
+        if (KIND == 6) { x = fe_sq_sf_call(x); y = fe_sq_sf_call(y); }
     }
     long long t1 = clock64();
     uint32_t acc = 0;
@@ -145,6 +166,12 @@ int main(int argc, char **argv) {
     FIELD(2, "fe_mul_portable_w16", 4);
     FIELD(3, "fe_sq_portable_w16", 4);
     FIELD(4, "fe_addsub_w16", 4);
+    FIELD(5, "fe_mul_shiftfold_w16", 4);
+    FIELD(6, "fe_sq_shiftfold_w16", 4);
+    FIELD(5, "fe_mul_shiftfold_w20", 5);
+    FIELD(6, "fe_sq_shiftfold_w20", 5);
+    FIELD(0, "fe_mul_ptx_w20", 5);
+    FIELD(1, "fe_sq_ptx_w20", 5);
     FIELD(0, "fe_mul_ptx_w8", 2);
     FIELD(1, "fe_sq_ptx_w8", 2);
     FIELD(0, "fe_mul_ptx_w32", 8);
