@@ -12,7 +12,7 @@ PKG = pathlib.Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libeg_b200.so"
 SOURCES = [CSRC / "eg_b200.cu"]
-HEADERS = sorted(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "eg_b200.h"]
+HEADERS = sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.inc")) + [PKG.parent / "include" / "eg_b200.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

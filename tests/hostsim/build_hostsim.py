@@ -10,7 +10,7 @@ LIB = HERE / "libeg_hostsim.so"
 
 
 def build(force=False):
-    deps = list(CSRC.glob("*.cuh")) + [CSRC / "eg_b200.cu", HERE / "hostsim_cuda.h", ROOT / "include" / "eg_b200.h"]
+    deps = list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.inc")) + [CSRC / "eg_b200.cu", HERE / "hostsim_cuda.h", ROOT / "include" / "eg_b200.h"]
     if not force and LIB.exists() and all(d.stat().st_mtime <= LIB.stat().st_mtime for d in deps):
         return LIB
     cmd = ["g++", "-x", "c++", "-std=c++17", "-O2", "-DEG_HOSTSIM", f"-I{HERE}", "-fPIC", "-shared", "-Wno-unknown-pragmas",

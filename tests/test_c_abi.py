@@ -56,6 +56,6 @@ def test_no_cpu_fallback():
 
 def test_package_never_imports_the_oracle():
     for f in (ROOT / "elastic_elgamal_b200").rglob("*"):
-        if f.suffix in (".py", ".cu", ".cuh", ".h", ".hpp") and f.is_file():
+        if f.suffix in (".py", ".cu", ".cuh", ".inc", ".h", ".hpp") and f.is_file():
             text = f.read_text()
             assert "import oracle" not in text and "liboracle" not in text and "eg_oracle.h" not in text, f
