@@ -228,6 +228,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
+        # NCCL prints its version banner (and anything NCCL_DEBUG asks for) to stdout by default: keep stdout for the one
+        # JSON line of the contract
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
