@@ -163,7 +163,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "ballots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(json.dumps(line))
 
 
 def hbm_roofline(sides, kernel_ms, traffic_per_launch, launches, step_stream_gbs):
@@ -197,8 +197,27 @@ def int32_peak():
         return {"error": repr(exc), "tests": {}}
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The one JSON line of the contract goes to the process's original stdout."""
+    data = (line + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line + "\n")
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
     args = parse_args()
+    # Libraries print to stdout behind our back (NCCL's version banner when NCCL_DEBUG=VERSION, for one): route file
+    # descriptor 1 to stderr for the whole run and keep the original stdout for the JSON line alone.
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
         return
@@ -228,9 +247,6 @@ def main():
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
-        # NCCL prints its version banner (and anything NCCL_DEBUG asks for) to stdout by default: keep stdout for the one
-        # JSON line of the contract
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -435,7 +451,7 @@ def main():
         "cpu_baseline": cpu,
         "reference_equivalent_field_ops_per_ballot": FIELD_OPS_PER_BALLOT,
     }
-    print(json.dumps(line))
+    emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
