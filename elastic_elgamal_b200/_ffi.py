@@ -100,7 +100,9 @@ PROTOTYPES = {
 
 def load(path=None):
     """Loads the C-ABI library.  Fails loudly when it has not been built: there is no fallback."""
-    # EG_B200_LIB selects another build of the same CUDA library (A/B tuning runs); there is still no CPU fallback
+    # EG_B200_LIB selects another build of the same CUDA library (A/B tuning runs); there is still no CPU fallback:
+    # only an explicit `path` (the test harness) may name the CPU-compiled hostsim library.
+    explicit = path is not None
     path = pathlib.Path(path) if path else pathlib.Path(os.environ.get("EG_B200_LIB", DEFAULT_LIB))
     if not path.exists():
         raise RuntimeError(f"{path} is missing: build it with `python -m elastic_elgamal_b200.build` "
@@ -117,4 +119,6 @@ def load(path=None):
         fn.argtypes = args
     if missing:
         raise RuntimeError(f"{path} does not export: {', '.join(missing)}")
+    if not explicit and b"sm_100a" not in lib.eg_version():
+        raise RuntimeError(f"{path} is not a CUDA sm_100a build ({lib.eg_version().decode()}): the engine has no CPU path")
     return lib

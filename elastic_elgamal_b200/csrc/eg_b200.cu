@@ -569,7 +569,11 @@ static void launch_dlog_lookup(eg_ctx *ctx, const dlog_lookup_params &P) {
     ctx->launches++;
 }
 
+#ifdef EG_HOSTSIM
+extern "C" const char *eg_version(void) { return "eg_b200 0.1.0 HOSTSIM test harness (not a product build)"; }
+#else
 extern "C" const char *eg_version(void) { return "eg_b200 0.1.0 sm_100a"; }
+#endif
 
 extern "C" const char *eg_last_error(const eg_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 

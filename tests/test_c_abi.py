@@ -54,6 +54,20 @@ def test_no_cpu_fallback():
     assert lib.eg_version().startswith(b"eg_b200")
 
 
+def test_hostsim_harness_is_not_loadable_as_the_product(monkeypatch):
+    """The CPU-compiled test harness identifies itself and the package refuses it unless a test names it explicitly."""
+    import pytest
+    from hostsim.build_hostsim import build as build_hostsim
+    from elastic_elgamal_b200 import _ffi
+    hs = build_hostsim()
+    assert b"HOSTSIM" in _ffi.load(hs).eg_version()                 # explicit path: allowed (tests only)
+    monkeypatch.setenv("EG_B200_LIB", str(hs))
+    with pytest.raises(RuntimeError):
+        _ffi.load()
+    monkeypatch.delenv("EG_B200_LIB")
+    assert b"sm_100a" in _ffi.load().eg_version()
+
+
 def test_package_never_imports_the_oracle():
     for f in (ROOT / "elastic_elgamal_b200").rglob("*"):
         if f.suffix in (".py", ".cu", ".cuh", ".inc", ".h", ".hpp") and f.is_file():
