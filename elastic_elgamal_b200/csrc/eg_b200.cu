@@ -179,7 +179,7 @@ static eg_status launch_ring(eg_ctx *ctx, ring_params &P) {
     cudaEventRecord(e_start, ctx->stream);
     EG_FOR_HOST(total, ring_body(P, tid % P.n, (uint32_t)(tid / P.n), P.scratch, P.table_g, P.table_k))
 #else
-    const size_t smem = 2 * EG_FCHUNK_TABLE_WORDS * 4;
+    const size_t smem = 0;
     bool short_rings = true;
     for (uint32_t r = 0; r < P.n_rings; r++) short_rings = short_rings && P.sizes[r] <= 2;
     const int shape = short_rings ? 1 : 0;
@@ -187,10 +187,8 @@ static eg_status launch_ring(eg_ctx *ctx, ring_params &P) {
     if (ctx->ring_grid[shape] == 0) {
         int per_sm = 0, sms = 0;
         if (shape) {
-            CU(cudaFuncSetAttribute(k_ring<EG_RING2_THREADS, EG_RING2_MINBLOCKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ring<EG_RING2_THREADS, EG_RING2_MINBLOCKS>, threads, smem));
         } else {
-            CU(cudaFuncSetAttribute(k_ring<EG_RING_THREADS, EG_RING_MINBLOCKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ring<EG_RING_THREADS, EG_RING_MINBLOCKS>, threads, smem));
         }
         CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
@@ -217,9 +215,8 @@ static eg_status launch_ring(eg_ctx *ctx, ring_params &P) {
 #ifndef EG_HOSTSIM
 template <int PHASE>
 static eg_status launch_prove_phase(eg_ctx *ctx, const prove_params &P, int &grid_cache) {
-    const size_t smem = 2 * EG_FCHUNK_TABLE_WORDS * 4;
+    const size_t smem = 0;
     if (grid_cache == 0) {
-        CU(cudaFuncSetAttribute(k_prove<PHASE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0, sms = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_prove<PHASE>, EG_RING_THREADS, smem));
         CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
@@ -254,9 +251,8 @@ static eg_status launch_prove(eg_ctx *ctx, const prove_params &P) {
 #ifndef EG_HOSTSIM
 template <int PHASE>
 static eg_status launch_rprove_phase(eg_ctx *ctx, const rprove_params &P, int &grid_cache) {
-    const size_t smem = PHASE == 1 ? 0 : 2 * EG_FCHUNK_TABLE_WORDS * 4;
+    const size_t smem = 0;
     if (grid_cache == 0) {
-        CU(cudaFuncSetAttribute(k_rprove<PHASE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0, sms = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rprove<PHASE>, EG_RING_THREADS, smem));
         CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
@@ -292,9 +288,8 @@ static eg_status launch_encrypt(eg_ctx *ctx, const encrypt_params &P) {
 #ifdef EG_HOSTSIM
     EG_FOR_HOST(P.n, encrypt_body(P, tid, P.table_g, P.table_k))
 #else
-    const size_t smem = 2 * EG_FCHUNK_TABLE_WORDS * 4;
+    const size_t smem = 0;
     if (ctx->encrypt_grid == 0) {
-        CU(cudaFuncSetAttribute(k_encrypt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0, sms = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_encrypt, EG_RING_THREADS, smem));
         CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
@@ -312,9 +307,8 @@ static eg_status launch_sumsq_prove(eg_ctx *ctx, const sumsq_prove_params &P) {
 #ifdef EG_HOSTSIM
     EG_FOR_HOST(P.n, sumsq_prove_body(P, tid, P.table_g, P.table_k))
 #else
-    const size_t smem = 2 * EG_FCHUNK_TABLE_WORDS * 4;
+    const size_t smem = 0;
     if (ctx->sumsq_prove_grid == 0) {
-        CU(cudaFuncSetAttribute(k_sumsq_prove, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0, sms = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sumsq_prove, EG_RING_THREADS, smem));
         CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
@@ -383,13 +377,19 @@ static void launch_verdict(eg_ctx *ctx, const verdict_params &P) {
     ctx->launches++;
 }
 
+// wide fixed-base table of one base (ge.cuh): EG_WIDE_TABLE_WORDS words, followed by EG_WIDE_SCRATCH_WORDS of window bases
+#define EG_TABLE_ALLOC_BYTES ((EG_WIDE_TABLE_WORDS + EG_WIDE_SCRATCH_WORDS) * 4)
 static void launch_build_table(eg_ctx *ctx, const uint32_t *enc_words, int use_generator, uint32_t *table, uint32_t *status) {
+    uint32_t *bases = table + EG_WIDE_TABLE_WORDS;
+    const size_t fill = (size_t)EG_WIDE_WINDOWS * (EG_WIDE_ENTRIES / EG_WIDE_BLOCK);
 #ifdef EG_HOSTSIM
-    EG_FOR_HOST(EG_VCHUNKS * EG_FIXED_TABLE_ENTRIES, build_table_body((int)tid, enc_words, use_generator, table, status))
+    wide_bases_body(enc_words, use_generator, bases, status);
+    EG_FOR_HOST(fill, wide_fill_body(tid, bases, table))
 #else
-    k_build_table<<<EG_VCHUNKS, EG_FIXED_TABLE_ENTRIES, 0, ctx->stream>>>(enc_words, use_generator, table, status);
+    k_wide_bases<<<1, 1, 0, ctx->stream>>>(enc_words, use_generator, bases, status);
+    k_wide_fill<<<grid_for(fill, 64), 64, 0, ctx->stream>>>(bases, table);
 #endif
-    ctx->launches++;
+    ctx->launches += 2;
 }
 
 static void launch_admissible(eg_ctx *ctx, const uint64_t *values, int count, uint32_t *adm) {
@@ -654,8 +654,8 @@ extern "C" eg_status eg_ctx_create(int device_id, eg_ctx **out) {
     for (auto &e : ctx->ev) if (cudaEventCreate(&e) != cudaSuccess) return bail(EG_ERR_CUDA);
     if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(EG_ERR_CUDA);
     for (auto &e : ctx->ev_h2d) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return bail(EG_ERR_CUDA);
-    if (cudaMalloc(&ctx->d_table_g, EG_FCHUNK_TABLE_WORDS * 4) != cudaSuccess) return bail(EG_ERR_OUT_OF_MEMORY);
-    if (cudaMalloc(&ctx->d_table_k, EG_FCHUNK_TABLE_WORDS * 4) != cudaSuccess) return bail(EG_ERR_OUT_OF_MEMORY);
+    if (cudaMalloc(&ctx->d_table_g, EG_TABLE_ALLOC_BYTES) != cudaSuccess) return bail(EG_ERR_OUT_OF_MEMORY);
+    if (cudaMalloc(&ctx->d_table_k, EG_TABLE_ALLOC_BYTES) != cudaSuccess) return bail(EG_ERR_OUT_OF_MEMORY);
     if (cudaMalloc(&ctx->d_status, 1024) != cudaSuccess) return bail(EG_ERR_OUT_OF_MEMORY);
     launch_build_table(ctx, nullptr, 1, ctx->d_table_g, ctx->d_status);
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) return bail(EG_ERR_CUDA);
@@ -706,7 +706,7 @@ extern "C" eg_status eg_ctx_set_blinding_base(eg_ctx *ctx, const uint8_t base[32
     if (!ctx || !base) return EG_ERR_INVALID_ARG;
     CU(cudaSetDevice(ctx->device));
     if (!ctx->d_table_h) {
-        cudaError_t ce = cudaMalloc(&ctx->d_table_h, EG_FCHUNK_TABLE_WORDS * 4);
+        cudaError_t ce = cudaMalloc(&ctx->d_table_h, EG_TABLE_ALLOC_BYTES);
         if (ce != cudaSuccess) { cudaGetLastError(); ctx->d_table_h = nullptr; return fail(ctx, EG_ERR_OUT_OF_MEMORY, "cudaMalloc H table", ce); }
     }
     uint32_t *d_key = ctx->d_status + 16;

@@ -192,9 +192,25 @@ EG_HD void ge_encode(uint32_t w[8], const ge_ext &p) {
 }
 
 // ------------------------------------------------------------------ fixed-base tables
+//
+// [b] F for the batch-constant bases (G, the receiver key K, the Pedersen base H) never doubles: the scalar is cut into
+// EG_WIDE_WINDOWS signed windows of EG_WIDE_BITS bits, b = sum_i d_i 2^(W i) with d_i in [-2^(W-1), 2^(W-1)), and the table
+// holds every |d| 2^(W i) F as an affine Niels point (96 B).  W = 16: 16 windows x 32768 entries = 48 MiB per base; G and
+// K together stay mostly resident in the 126 MB L2 (each lookup is three 32-byte sectors); [b] F costs 16 mixed additions
+// (7 multiplications each).  Measured on B200 (profiles/r1_wide_tables_ab.txt): W = 11 / 13 / 15 / 16 ->
+// 1.860 / 1.895 / 1.922 / 1.934 M ballots/s against 1.865 M with 8-bit windows over 4 chunks staged in shared memory.
 
-#define EG_FIXED_TABLE_ENTRIES 128           // [1..128] F, affine Niels, 96 B each = 12 KB per base
-#define EG_FIXED_TABLE_WORDS (EG_FIXED_TABLE_ENTRIES * 24)
+#ifndef EG_WIDE_BITS
+#define EG_WIDE_BITS 16
+#endif
+#ifndef EG_WIDE_PREFETCH
+#define EG_WIDE_PREFETCH 1
+#endif
+#define EG_WIDE_WINDOWS ((254 + EG_WIDE_BITS - 1) / EG_WIDE_BITS)     // W * windows >= 254: the top digit absorbs the last carry
+#define EG_WIDE_ENTRIES (1 << (EG_WIDE_BITS - 1))                     // |d| = 1 .. 2^(W-1) per window
+#define EG_WIDE_TABLE_WORDS ((size_t)EG_WIDE_WINDOWS * EG_WIDE_ENTRIES * 24)
+#define EG_WIDE_BLOCK 32                                              // entries normalised together by the table builder
+#define EG_WIDE_SCRATCH_WORDS (EG_WIDE_WINDOWS * 32)                  // window bases 2^(W i) F (extended), behind the table
 
 EG_HD void ge_niels_load(ge_niels &n, const uint32_t *tbl, int idx) {
     const uint32_t *e = tbl + idx * 24;
@@ -315,6 +331,30 @@ EG_HD void sc_recode8(uint32_t out[8], const sc &a) {
 EG_HD int sc_digit4(const uint32_t r[8], int i) { return (int)((r[i >> 3] >> ((i & 7) * 4)) & 15u) - 8; }
 EG_HD int sc_digit8(const uint32_t r[8], int i) { return (int)((r[i >> 2] >> ((i & 3) * 8)) & 255u) - 128; }
 
+// EG_WIDE_BITS-bit signed windows, produced low to high with a running carry: digit i of `a` in [-2^(W-1), 2^(W-1)).
+// a < 2^253 and W * EG_WIDE_WINDOWS >= 254, so the top window never carries out.
+EG_HD int sc_wide_digit(const sc &a, int i, uint32_t &carry) {
+    const int o = i * EG_WIDE_BITS, word = o >> 5, sh = o & 31;
+    uint32_t v = word < 8 ? a.v[word] >> sh : 0u;
+    if (sh + EG_WIDE_BITS > 32 && word + 1 < 8) v |= a.v[word + 1] << (32 - sh);
+    v = (v & ((1u << EG_WIDE_BITS) - 1u)) + carry;
+    carry = (v >> (EG_WIDE_BITS - 1)) != 0u;         // v >= 2^(W-1) (v <= 2^W): borrow 2^W from the next window
+    return (int)v - (int)(carry << EG_WIDE_BITS);
+}
+
+// the (at most two) 128-byte lines of a 96-byte table entry, requested ahead of its use
+EG_HD void ge_wide_prefetch(const uint32_t *entry) {
+#if defined(__CUDA_ARCH__) && EG_WIDE_PREFETCH == 2
+    asm volatile("prefetch.global.L1 [%0];" :: "l"(entry));
+    asm volatile("prefetch.global.L1 [%0];" :: "l"(entry + 23));
+#elif defined(__CUDA_ARCH__) && EG_WIDE_PREFETCH == 1
+    asm volatile("prefetch.global.L2 [%0];" :: "l"(entry));
+    asm volatile("prefetch.global.L2 [%0];" :: "l"(entry + 23));
+#else
+    (void)entry;
+#endif
+}
+
 // ------------------------------------------------------------------ the multi-scalar chain
 
 // acc = sum_{v<NV} a_v P_v + sum_{f<NF} b_f F_f
@@ -338,35 +378,39 @@ EG_HD void ge_window_table(ge_cached tbl[8], const ge_ext &P) {
     }
 }
 
+// acc += [b] F from the wide table of F (EG_WIDE_WINDOWS mixed additions, no doublings)
+static EG_HD_NOINLINE void ge_fixed_accumulate(ge_ext &acc, const uint32_t *wide, const sc &b) {
+    uint32_t carry = 0;
+#pragma unroll 1
+    for (int i = 0; i < EG_WIDE_WINDOWS; i++) {
+        const int d = sc_wide_digit(b, i, carry);
+        if (d != 0) ge_hot_add_niels(acc, wide + (size_t)i * (EG_WIDE_ENTRIES * 24), (d < 0 ? -d : d) - 1, d < 0);
+    }
+}
+
 template <int NV, int NF>
 EG_HD void ge_msm_chain(ge_ext &out, const ge_ext *P, const sc *a, const uint32_t *const *ftab, const sc *b) {
     EG_ALIGN16 ge_cached tbl[NV > 0 ? NV : 1][8];
     uint32_t ra[NV > 0 ? NV : 1][8];
-    uint32_t rb[NF > 0 ? NF : 1][8];
 #pragma unroll 1
     for (int v = 0; v < NV; v++) {
         ge_window_table(tbl[v], P[v]);
         sc_recode4(ra[v], a[v]);
     }
-    for (int f = 0; f < NF; f++) sc_recode8(rb[f], b[f]);
-
     ge_ext acc = ge_identity();
+    if (NV > 0) {
 #pragma unroll 1
-    for (int i = 63; i >= 0; i--) {
-        if (i != 63) ge_hot_dbl(acc, 4);
+        for (int i = 63; i >= 0; i--) {
+            if (i != 63) ge_hot_dbl(acc, 4);
 #pragma unroll 1
-        for (int v = 0; v < NV; v++) {
-            int d = sc_digit4(ra[v], i);
-            if (d != 0) ge_hot_add_cached(acc, (const uint32_t *)&tbl[v][(d < 0 ? -d : d) - 1], d < 0);
-        }
-        if ((i & 1) == 0) {
-#pragma unroll 1
-            for (int f = 0; f < NF; f++) {
-                int d = sc_digit8(rb[f], i >> 1);
-                if (d != 0) ge_hot_add_niels(acc, ftab[f], (d < 0 ? -d : d) - 1, d < 0);
+            for (int v = 0; v < NV; v++) {
+                int d = sc_digit4(ra[v], i);
+                if (d != 0) ge_hot_add_cached(acc, (const uint32_t *)&tbl[v][(d < 0 ? -d : d) - 1], d < 0);
             }
         }
     }
+#pragma unroll 1
+    for (int f = 0; f < NF; f++) ge_fixed_accumulate(acc, ftab[f], b[f]);
     out = acc;
 }
 
@@ -378,31 +422,25 @@ template <int MAXV>
 EG_HD void ge_msm_chain_rt(ge_ext &out, int nv, const ge_ext *P, const sc *a, int nf, const uint32_t *const *ftab, const sc *b) {
     EG_ALIGN16 ge_cached tbl[MAXV][8];
     uint32_t ra[MAXV][8];
-    uint32_t rb[2][8];
 #pragma unroll 1
     for (int v = 0; v < nv; v++) {
         ge_window_table(tbl[v], P[v]);
         sc_recode4(ra[v], a[v]);
     }
-#pragma unroll 1
-    for (int f = 0; f < nf; f++) sc_recode8(rb[f], b[f]);
     ge_ext acc = ge_identity();
+    if (nv > 0) {
 #pragma unroll 1
-    for (int i = 63; i >= 0; i--) {
-        if (i != 63) ge_hot_dbl(acc, 4);
+        for (int i = 63; i >= 0; i--) {
+            if (i != 63) ge_hot_dbl(acc, 4);
 #pragma unroll 1
-        for (int v = 0; v < nv; v++) {
-            int d = sc_digit4(ra[v], i);
-            if (d != 0) ge_hot_add_cached(acc, (const uint32_t *)&tbl[v][(d < 0 ? -d : d) - 1], d < 0);
-        }
-        if ((i & 1) == 0) {
-#pragma unroll 1
-            for (int f = 0; f < nf; f++) {
-                int d = sc_digit8(rb[f], i >> 1);
-                if (d != 0) ge_hot_add_niels(acc, ftab[f], (d < 0 ? -d : d) - 1, d < 0);
+            for (int v = 0; v < nv; v++) {
+                int d = sc_digit4(ra[v], i);
+                if (d != 0) ge_hot_add_cached(acc, (const uint32_t *)&tbl[v][(d < 0 ? -d : d) - 1], d < 0);
             }
         }
     }
+#pragma unroll 1
+    for (int f = 0; f < nf; f++) ge_fixed_accumulate(acc, ftab[f], b[f]);
     out = acc;
 }
 
@@ -411,13 +449,12 @@ EG_HD void ge_msm_chain_rt(ge_ext &out, int nv, const ge_ext *P, const sc *a, in
 // A ring proof evaluates several equations on the SAME ciphertext points (one per admissible value, ring.rs:333-361)
 // with different challenges.  Splitting a 253-bit scalar into four 64-bit chunks, a = sum_c 2^(64c) a_c, turns
 // [a]P into sum_c [a_c] P_c with P_c = [2^(64c)] P: the 192 doublings that produce P_1..P_3 (and the four window
-// tables [1..8] P_c) are paid once per point, every equation then needs only 64 shared doublings.  The fixed bases
-// G and K get the same treatment once per context (4 x 128 affine entries each).
+// tables [1..8] P_c) are paid once per point, every equation then needs only 64 shared doublings.  The fixed-base
+// terms are added afterwards from the wide tables.
 
 #define EG_VCHUNKS 4
 #define EG_VTAB_ENTRY_WORDS 32                                  // one cached point
 #define EG_VTAB_WORDS (EG_VCHUNKS * 8 * EG_VTAB_ENTRY_WORDS)    // 4 KB per point
-#define EG_FCHUNK_TABLE_WORDS (EG_VCHUNKS * EG_FIXED_TABLE_WORDS)   // 48 KB per fixed base
 
 // tab[(c * 8 + k) * 32 ..] = cached((k + 1) * 2^(64 c) * P), c < 4, k < 8.  `tab` is 16-byte aligned scratch.
 static EG_HD_NOINLINE void ge_vtab_build(uint32_t *tab, const ge_ext &P) {
@@ -439,29 +476,27 @@ static EG_HD_NOINLINE void ge_vtab_build(uint32_t *tab, const ge_ext &P) {
     }
 }
 
-// out = [a] P + [b0] F0 (+ [b1] F1 when nf == 2): vtab from ge_vtab_build(P) (or null with a ignored), ftab* = 4-chunk
-// fixed tables.  64 doublings, <= 64 + 32 nf additions.
+// out = [a] P + [b0] F0 (+ [b1] F1 when nf == 2): vtab from ge_vtab_build(P) (or null with a ignored), ftab* = wide
+// fixed-base tables.  60 doublings and 64 additions for the per-item point, EG_WIDE_WINDOWS mixed additions per fixed base.
 static EG_HD_NOINLINE void ge_eval64(ge_ext &out, const uint32_t *vtab, const sc &a, int nf, const uint32_t *ftab0, const sc &b0,
                      const uint32_t *ftab1, const sc &b1) {
-    uint32_t ra[8], rb0[8], rb1[8];
-    sc_recode4(ra, a);
-    sc_recode8(rb0, b0);
-    sc_recode8(rb1, b1);
-    // the accumulator stays in registers for the whole loop: the point formulas are expanded here once each (rolled
+    // the accumulator stays in registers for the whole function: the point formulas are expanded here once each (rolled
     // loops), with the field operations as calls (see EG_HOT_OPS above for why they are not expanded)
     ge_ext acc = ge_identity();
     ge_p1p1 t;
+    if (vtab) {
+        uint32_t ra[8];
+        sc_recode4(ra, a);
 #pragma unroll 1
-    for (int i = 15; i >= 0; i--) {
-        if (i != 15) {
+        for (int i = 15; i >= 0; i--) {
+            if (i != 15) {
 #pragma unroll 1
-            for (int k = 0; k < 4; k++) {
-                ge_dbl_p1p1(t, acc);
-                ge_p1p1_to_proj(acc, t);
-                if (k == 3) fe_mul(acc.T, t.E, t.H);
+                for (int k = 0; k < 4; k++) {
+                    ge_dbl_p1p1(t, acc);
+                    ge_p1p1_to_proj(acc, t);
+                    if (k == 3) fe_mul(acc.T, t.E, t.H);
+                }
             }
-        }
-        if (vtab) {
 #pragma unroll 1
             for (int c = 0; c < EG_VCHUNKS; c++) {
                 int d = sc_digit4(ra, 16 * c + i);
@@ -469,25 +504,33 @@ static EG_HD_NOINLINE void ge_eval64(ge_ext &out, const uint32_t *vtab, const sc
                     ge_cached q;
                     ge_cached_load(q, vtab + (c * 8 + (d < 0 ? -d : d) - 1) * EG_VTAB_ENTRY_WORDS);
                     ge_add_cached_p1p1(t, acc, q, d < 0);
-                    ge_p1p1_to_ext(acc, t);
+                    ge_p1p1_to_proj(acc, t);
+                    if (c != EG_VCHUNKS - 1 || i == 0) fe_mul(acc.T, t.E, t.H);     // T is dead when doublings follow
                 }
             }
         }
-        if ((i & 1) == 0) {
+    }
 #pragma unroll 1
-            for (int f = 0; f < nf; f++) {
-                const uint32_t *ft = f ? ftab1 : ftab0;
-                const uint32_t *rb = f ? rb1 : rb0;
+    for (int f = 0; f < nf; f++) {
+        const uint32_t *ft = f ? ftab1 : ftab0;
+        const sc &b = f ? b1 : b0;
+        uint32_t carry = 0;
+        int d = sc_wide_digit(b, 0, carry);
+        const uint32_t *entry = ft + (size_t)((d < 0 ? -d : d) - (d != 0)) * 24;
 #pragma unroll 1
-                for (int c = 0; c < EG_VCHUNKS; c++) {
-                    int d = sc_digit8(rb, 8 * c + (i >> 1));
-                    if (d != 0) {
-                        ge_niels n;
-                        ge_niels_load4(n, ft + c * EG_FIXED_TABLE_WORDS, (d < 0 ? -d : d) - 1);
-                        ge_add_niels_p1p1(t, acc, n, d < 0);
-                        ge_p1p1_to_ext(acc, t);
-                    }
-                }
+        for (int i = 0; i < EG_WIDE_WINDOWS; i++) {
+            const int dc = d;
+            const uint32_t *ec = entry;
+            if (i + 1 < EG_WIDE_WINDOWS) {          // digit and address of the next window; its lines are requested now
+                d = sc_wide_digit(b, i + 1, carry);
+                entry = ft + ((size_t)(i + 1) * EG_WIDE_ENTRIES + (size_t)((d < 0 ? -d : d) - (d != 0))) * 24;
+                ge_wide_prefetch(entry);
+            }
+            if (dc != 0) {
+                ge_niels n;
+                ge_niels_load4(n, ec, 0);
+                ge_add_niels_p1p1(t, acc, n, dc < 0);
+                ge_p1p1_to_ext(acc, t);
             }
         }
     }

@@ -1169,30 +1169,61 @@ EG_HD void verdict_body(const verdict_params &P, size_t item) {
 
 namespace eg {
 
-// table[c * 128 + k] = (k+1) 2^(64c) F in affine Niels form (c < 4), F given as an encoding; status: 0 ok, 1 undecodable, 2 identity
-EG_HD void build_table_body(int tidx, const uint32_t *enc_words, int use_generator, uint32_t *table, uint32_t *status) {
+// Wide fixed-base table of F (ge.cuh "fixed-base tables"), F given as an encoding; two stages.
+// Stage 1 (one thread): status = 0 ok / 1 undecodable / 2 identity; bases[i] = 2^(W i) F, extended, 32 words each.
+EG_HD void wide_bases_body(const uint32_t *enc_words, int use_generator, uint32_t *bases, uint32_t *status) {
     ge_ext F;
     bool ok = true;
     if (use_generator) F = ge_generator();
     else {
         uint32_t w[8];
         for (int k = 0; k < 8; k++) w[k] = enc_words[k];
-        ok = ge_decode(F, w);
+        ok = ge_decode(F, w);                                  // the identity when rejected: the table stays well defined
     }
-    if (tidx == 0) *status = !ok ? 1u : (ge_is_identity(F) ? 2u : 0u);
-    if (!ok) return;
-    // entry tidx = (chunk c, multiple m): m * 2^(64 c) * F; the first 128 entries are the plain [1..128] F table
-    const int chunk = tidx / EG_FIXED_TABLE_ENTRIES;
-    int m = tidx % EG_FIXED_TABLE_ENTRIES + 1;               // 1..128
+    *status = !ok ? 1u : (ge_is_identity(F) ? 2u : 0u);
 #pragma unroll 1
-    for (int k = 0; k < 64 * chunk; k++) ge_dbl(F, F);
-    ge_ext acc = ge_identity();
+    for (int i = 0; i < EG_WIDE_WINDOWS; i++) {
+        point_to_words32(bases + i * 32, F);
+        if (i + 1 < EG_WIDE_WINDOWS) ge_hot_dbl(F, EG_WIDE_BITS);
+    }
+}
+
+// Stage 2: thread tidx = (window i, block jb) writes entries m = jb * EG_WIDE_BLOCK + 1 .. + EG_WIDE_BLOCK of window i:
+// table[(i * EG_WIDE_ENTRIES + m - 1) * 24 ..] = affine Niels form of m 2^(W i) F; one inversion per block.
+EG_HD void wide_fill_body(size_t tidx, const uint32_t *bases, uint32_t *table) {
+    const int blocks = EG_WIDE_ENTRIES / EG_WIDE_BLOCK;
+    const int i = (int)(tidx / blocks), jb = (int)(tidx % blocks);
+    ge_ext B, acc = ge_identity();
+    point_from_words32(B, bases + i * 32);
+    ge_cached cb;
+    ge_to_cached(cb, B);
+    const uint32_t first = (uint32_t)jb * EG_WIDE_BLOCK + 1;
+    ge_p1p1 t;
 #pragma unroll 1
-    for (int bit = 7; bit >= 0; bit--) {
+    for (int bit = EG_WIDE_BITS - 1; bit >= 0; bit--) {
         ge_dbl(acc, acc);
-        if ((m >> bit) & 1) ge_add(acc, acc, F);
+        if ((first >> bit) & 1u) { ge_add_cached_p1p1(t, acc, cb, false); ge_p1p1_to_ext(acc, t); }
     }
-    ge_niels_from_ext(table + tidx * 24, acc);
+    ge_ext pts[EG_WIDE_BLOCK];
+    fe prod[EG_WIDE_BLOCK];
+#pragma unroll 1
+    for (int k = 0; k < EG_WIDE_BLOCK; k++) {
+        if (k) { ge_add_cached_p1p1(t, acc, cb, false); ge_p1p1_to_ext(acc, t); }
+        pts[k] = acc;
+        if (k) fe_mul(prod[k], prod[k - 1], acc.Z); else prod[0] = acc.Z;
+    }
+    fe inv;
+    fe_invert(inv, prod[EG_WIDE_BLOCK - 1]);
+    uint32_t *out = table + ((size_t)i * EG_WIDE_ENTRIES + first - 1) * 24;
+#pragma unroll 1
+    for (int k = EG_WIDE_BLOCK - 1; k >= 0; k--) {
+        fe zi, x, y, u;
+        if (k) { fe_mul(zi, inv, prod[k - 1]); fe_mul(inv, inv, pts[k].Z); } else zi = inv;
+        fe_mul(x, pts[k].X, zi); fe_mul(y, pts[k].Y, zi);
+        fe_add(u, y, x); fe_towords(out + k * 24, u);
+        fe_sub(u, y, x); fe_towords(out + k * 24 + 8, u);
+        fe_mul(u, x, y); fe_mul(u, u, fe_const_2d()); fe_towords(out + k * 24 + 16, u);
+    }
 }
 
 // adm[tid] = cached form of [values[tid]] G   (PreparedRange::new range.rs:341-355)
