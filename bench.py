@@ -39,9 +39,10 @@ BALLOT_BYTES = OPTIONS * 64 + (1 + 2 * OPTIONS) * 32 + 64        # 736, SURVEY.m
 # instructions per field operation.
 FIELD_OPS_PER_COMMIT = 4956 / 2 + 280
 FIELD_OPS_PER_BALLOT = 4956 * 11 + 280 * (34 + 10)               # 66 836
-# What k_ring actually executes per equation side of a two-equation ring: (2 x 1603 table build +
-# 4 x 1139 evaluation + 224 for the [e a]G term + 2 x 304 encoding) / 4 sides, counted from the formulas in ge.cuh.
-EXECUTED_FIELD_OPS_PER_RING_SIDE = (2 * 1603 + 4 * 1139 + 224 + 2 * 304) / 4      # 2148.5
+# What k_ring actually executes per equation side of a two-equation ring, counted from the formulas in
+# ge.cuh: 2 x 1603 table build (192 doublings + 28 additions per point) + 4 sides x (435 for 60 doublings + 497 for 64
+# per-item additions + 112 for 16 fixed-base additions from the wide table) + 112 for the [e a]G term + 2 x 304 encoding.
+EXECUTED_FIELD_OPS_PER_RING_SIDE = (2 * 1603 + 4 * (435 + 497 + 112) + 112 + 2 * 304) / 4      # 2025.5
 IMAD_PER_FIELD_OP = 144
 METRIC = "verified ballots/sec (5-option choice)"
 

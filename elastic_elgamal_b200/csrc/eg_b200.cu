@@ -173,23 +173,24 @@ static eg_status launch_ring(eg_ctx *ctx, ring_params &P) {
     ctx->kind_tasks[1] += sides; ctx->kind_launches[1]++;
     ctx->commit_ev_used += 2;
     const size_t total = P.n * (size_t)P.n_rings;
+    bool short_rings = true;                // rings of <= 2 equations: 4-chunk tables, one CTA of 512 threads per SM
+    for (uint32_t r = 0; r < P.n_rings; r++) short_rings = short_rings && P.sizes[r] <= 2;
 #ifdef EG_HOSTSIM
     TRY(ensure(ctx, ctx->ring_scratch, 2 * EG_VTAB_WORDS * 4));
     P.scratch = (uint32_t *)ctx->ring_scratch.p;
     cudaEventRecord(e_start, ctx->stream);
-    EG_FOR_HOST(total, ring_body(P, tid % P.n, (uint32_t)(tid / P.n), P.scratch, P.table_g, P.table_k))
+    if (short_rings) { EG_FOR_HOST(total, ring_body<EG_VCHUNKS_SHORT>(P, tid % P.n, (uint32_t)(tid / P.n), P.scratch, P.table_g, P.table_k)) }
+    else { EG_FOR_HOST(total, ring_body<EG_VCHUNKS_LONG>(P, tid % P.n, (uint32_t)(tid / P.n), P.scratch, P.table_g, P.table_k)) }
 #else
     const size_t smem = 0;
-    bool short_rings = true;
-    for (uint32_t r = 0; r < P.n_rings; r++) short_rings = short_rings && P.sizes[r] <= 2;
     const int shape = short_rings ? 1 : 0;
     const int threads = shape ? EG_RING2_THREADS : EG_RING_THREADS;
     if (ctx->ring_grid[shape] == 0) {
         int per_sm = 0, sms = 0;
         if (shape) {
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ring<EG_RING2_THREADS, EG_RING2_MINBLOCKS>, threads, smem));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ring<EG_RING2_THREADS, EG_RING2_MINBLOCKS, EG_VCHUNKS_SHORT>, threads, smem));
         } else {
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ring<EG_RING_THREADS, EG_RING_MINBLOCKS>, threads, smem));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ring<EG_RING_THREADS, EG_RING_MINBLOCKS, EG_VCHUNKS_LONG>, threads, smem));
         }
         CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
         if (per_sm < 1) return fail(ctx, EG_ERR_CUDA, "k_ring does not fit on an SM");
@@ -200,8 +201,8 @@ static eg_status launch_ring(eg_ctx *ctx, ring_params &P) {
     TRY(ensure(ctx, ctx->ring_scratch, resident * threads * 2 * EG_VTAB_WORDS * 4));
     P.scratch = (uint32_t *)ctx->ring_scratch.p;
     cudaEventRecord(e_start, ctx->stream);
-    if (shape) k_ring<EG_RING2_THREADS, EG_RING2_MINBLOCKS><<<grid, threads, smem, ctx->stream>>>(P);
-    else k_ring<EG_RING_THREADS, EG_RING_MINBLOCKS><<<grid, threads, smem, ctx->stream>>>(P);
+    if (shape) k_ring<EG_RING2_THREADS, EG_RING2_MINBLOCKS, EG_VCHUNKS_SHORT><<<grid, threads, smem, ctx->stream>>>(P);
+    else k_ring<EG_RING_THREADS, EG_RING_MINBLOCKS, EG_VCHUNKS_LONG><<<grid, threads, smem, ctx->stream>>>(P);
 #endif
     cudaEventRecord(e_stop, ctx->stream);
     ctx->launches++;

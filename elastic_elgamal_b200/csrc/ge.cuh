@@ -452,15 +452,21 @@ EG_HD void ge_msm_chain_rt(ge_ext &out, int nv, const ge_ext *P, const sc *a, in
 // tables [1..8] P_c) are paid once per point, every equation then needs only 64 shared doublings.  The fixed-base
 // terms are added afterwards from the wide tables.
 
-#define EG_VCHUNKS 4
+// The chunk count is a compile-time parameter of the table builder and the evaluator: 4 chunks for rings of two
+// equations (ballot choices), 8 chunks (32 doublings per equation, 224 for the tables) for the longer rings of range
+// proofs -- measured on B200 (profiles/r1_wide_tables_ab.txt): 8 chunks -1.8 % on 5-option ballots, +3.7 % on
+// RangeProof [0, 2^16).
+#define EG_VCHUNKS_SHORT 4
+#define EG_VCHUNKS_LONG 8
 #define EG_VTAB_ENTRY_WORDS 32                                  // one cached point
-#define EG_VTAB_WORDS (EG_VCHUNKS * 8 * EG_VTAB_ENTRY_WORDS)    // 4 KB per point
+#define EG_VTAB_WORDS (EG_VCHUNKS_LONG * 8 * EG_VTAB_ENTRY_WORDS)   // scratch reserved per point: 8 KB
 
-// tab[(c * 8 + k) * 32 ..] = cached((k + 1) * 2^(64 c) * P), c < 4, k < 8.  `tab` is 16-byte aligned scratch.
+// tab[(c * 8 + k) * 32 ..] = cached((k + 1) * 2^(256 c / C) * P), c < C, k < 8.  `tab` is 16-byte aligned scratch.
+template <int C>
 static EG_HD_NOINLINE void ge_vtab_build(uint32_t *tab, const ge_ext &P) {
     ge_ext base = P;
 #pragma unroll 1
-    for (int c = 0; c < EG_VCHUNKS; c++) {
+    for (int c = 0; c < C; c++) {
         uint32_t *t0 = tab + (c * 8) * EG_VTAB_ENTRY_WORDS;
         ge_cached ck;
         ge_to_cached(ck, base);
@@ -472,44 +478,13 @@ static EG_HD_NOINLINE void ge_vtab_build(uint32_t *tab, const ge_ext &P) {
             ge_to_cached(ck, cur);
             ge_cached_store(t0 + k * EG_VTAB_ENTRY_WORDS, ck);
         }
-        if (c + 1 < EG_VCHUNKS) ge_hot_dbl(base, 64);
+        if (c + 1 < C) ge_hot_dbl(base, 256 / C);
     }
 }
 
-// out = [a] P + [b0] F0 (+ [b1] F1 when nf == 2): vtab from ge_vtab_build(P) (or null with a ignored), ftab* = wide
-// fixed-base tables.  60 doublings and 64 additions for the per-item point, EG_WIDE_WINDOWS mixed additions per fixed base.
-static EG_HD_NOINLINE void ge_eval64(ge_ext &out, const uint32_t *vtab, const sc &a, int nf, const uint32_t *ftab0, const sc &b0,
-                     const uint32_t *ftab1, const sc &b1) {
-    // the accumulator stays in registers for the whole function: the point formulas are expanded here once each (rolled
-    // loops), with the field operations as calls (see EG_HOT_OPS above for why they are not expanded)
-    ge_ext acc = ge_identity();
-    ge_p1p1 t;
-    if (vtab) {
-        uint32_t ra[8];
-        sc_recode4(ra, a);
-#pragma unroll 1
-        for (int i = 15; i >= 0; i--) {
-            if (i != 15) {
-#pragma unroll 1
-                for (int k = 0; k < 4; k++) {
-                    ge_dbl_p1p1(t, acc);
-                    ge_p1p1_to_proj(acc, t);
-                    if (k == 3) fe_mul(acc.T, t.E, t.H);
-                }
-            }
-#pragma unroll 1
-            for (int c = 0; c < EG_VCHUNKS; c++) {
-                int d = sc_digit4(ra, 16 * c + i);
-                if (d != 0) {
-                    ge_cached q;
-                    ge_cached_load(q, vtab + (c * 8 + (d < 0 ? -d : d) - 1) * EG_VTAB_ENTRY_WORDS);
-                    ge_add_cached_p1p1(t, acc, q, d < 0);
-                    ge_p1p1_to_proj(acc, t);
-                    if (c != EG_VCHUNKS - 1 || i == 0) fe_mul(acc.T, t.E, t.H);     // T is dead when doublings follow
-                }
-            }
-        }
-    }
+// acc += [b0] F0 (+ [b1] F1 when nf == 2) from the wide tables; `t` is the caller's scratch.  Inlined into its callers so
+// that the accumulator stays in registers.
+EG_HD void ge_fixed_adds(ge_ext &acc, ge_p1p1 &t, int nf, const uint32_t *ftab0, const sc &b0, const uint32_t *ftab1, const sc &b1) {
 #pragma unroll 1
     for (int f = 0; f < nf; f++) {
         const uint32_t *ft = f ? ftab1 : ftab0;
@@ -534,6 +509,54 @@ static EG_HD_NOINLINE void ge_eval64(ge_ext &out, const uint32_t *vtab, const sc
             }
         }
     }
+}
+
+// out = [a] P + [b0] F0 (+ [b1] F1 when nf == 2): vtab from ge_vtab_build<C>(P) (or null: fixed-base terms only), ftab* = wide
+// fixed-base tables.  256 / C - 4 doublings and 64 additions for the per-item point, EG_WIDE_WINDOWS mixed additions per
+// fixed base.
+template <int C>
+static EG_HD_NOINLINE void ge_eval64(ge_ext &out, const uint32_t *vtab, const sc &a, int nf, const uint32_t *ftab0, const sc &b0,
+                     const uint32_t *ftab1, const sc &b1) {
+    constexpr int W = 64 / C;                  // 4-bit windows per chunk
+    // the accumulator stays in registers for the whole function: the point formulas are expanded here once each (rolled
+    // loops), with the field operations as calls (see EG_HOT_OPS above for why they are not expanded)
+    ge_ext acc = ge_identity();
+    ge_p1p1 t;
+    if (vtab) {
+        uint32_t ra[8];
+        sc_recode4(ra, a);
+#pragma unroll 1
+        for (int i = W - 1; i >= 0; i--) {
+            if (i != W - 1) {
+#pragma unroll 1
+                for (int k = 0; k < 4; k++) {
+                    ge_dbl_p1p1(t, acc);
+                    ge_p1p1_to_proj(acc, t);
+                    if (k == 3) fe_mul(acc.T, t.E, t.H);
+                }
+            }
+#pragma unroll 1
+            for (int c = 0; c < C; c++) {
+                int d = sc_digit4(ra, W * c + i);
+                if (d != 0) {
+                    ge_cached q;
+                    ge_cached_load(q, vtab + (c * 8 + (d < 0 ? -d : d) - 1) * EG_VTAB_ENTRY_WORDS);
+                    ge_add_cached_p1p1(t, acc, q, d < 0);
+                    ge_p1p1_to_proj(acc, t);
+                    if (c != C - 1 || i == 0) fe_mul(acc.T, t.E, t.H);     // T is dead when doublings follow
+                }
+            }
+        }
+    }
+    ge_fixed_adds(acc, t, nf, ftab0, b0, ftab1, b1);
+    out = acc;
+}
+
+// fixed-base-only form (the provers' [x] G, [x] K + [y] G)
+static EG_HD_NOINLINE void ge_eval_fixed(ge_ext &out, int nf, const uint32_t *ftab0, const sc &b0, const uint32_t *ftab1, const sc &b1) {
+    ge_ext acc = ge_identity();
+    ge_p1p1 t;
+    ge_fixed_adds(acc, t, nf, ftab0, b0, ftab1, b1);
     out = acc;
 }
 

@@ -371,14 +371,15 @@ static EG_HD_NOINLINE void ring_next_challenge(sc &e, const transcript &rt, uint
     merlin_challenge_scalar(t, EG_LBL("c"), e);
 }
 
+template <int C>
 EG_HD void ring_body(const ring_params &P, size_t item, uint32_t r, uint32_t *scratch, const uint32_t *tab_g, const uint32_t *tab_k) {
     uint32_t *tab_r = scratch, *tab_b = scratch + EG_VTAB_WORDS;
     {
         ge_ext pt;
         planar_load_point(pt, P.pts, P.n, P.ct_p_index[r], item);
-        ge_vtab_build(tab_r, pt);
+        ge_vtab_build<C>(tab_r, pt);
         planar_load_point(pt, P.pts, P.n, P.ct_p_index[r] + 1, item);
-        ge_vtab_build(tab_b, pt);
+        ge_vtab_build<C>(tab_b, pt);
     }
     const uint8_t *proof = in_ptr(P.in, P.proof_buf, item) + P.proof_offset;
     uint32_t w[16];
@@ -402,15 +403,15 @@ EG_HD void ring_body(const ring_params &P, size_t item, uint32_t r, uint32_t *sc
         sc_half(hs, s);
         sc_half(hne, ne);
         ge_ext qg, qk;
-        ge_eval64(qg, tab_r, hne, 1, tab_g, hs, tab_g, hs);
+        ge_eval64<C>(qg, tab_r, hne, 1, tab_g, hs, tab_g, hs);
         const uint64_t a = P.adm_step[r] * (uint64_t)j;
         if (a != 0) {
             sc ea;
             sc_mul(ea, e, sc_from_u64(a));
             sc_half(hea, ea);
-            ge_eval64(qk, tab_b, hne, 2, tab_k, hs, tab_g, hea);
+            ge_eval64<C>(qk, tab_b, hne, 2, tab_k, hs, tab_g, hea);
         } else {
-            ge_eval64(qk, tab_b, hne, 1, tab_k, hs, tab_k, hs);
+            ge_eval64<C>(qk, tab_b, hne, 1, tab_k, hs, tab_k, hs);
         }
         ge_double_compress2(cg, ck, qg, qk);
         if (j + 1 < size) ring_next_challenge(e, rt, j, cg, ck);
@@ -461,8 +462,8 @@ EG_HD void prove_commit_pair(uint32_t out0[8], uint32_t out1[8], const sc &k, co
     sc h;
     sc_half(h, k);
     ge_ext q0, q1;
-    ge_eval64(q0, nullptr, h, 1, tab_g, h, tab_g, h);
-    ge_eval64(q1, nullptr, h, 1, tab_k, h, tab_k, h);
+    ge_eval_fixed(q0, 1, tab_g, h, tab_g, h);
+    ge_eval_fixed(q1, 1, tab_k, h, tab_k, h);
     ge_double_compress2(out0, out1, q0, q1);
 }
 
@@ -471,21 +472,21 @@ EG_HD void prove_commit_pair(uint32_t out0[8], uint32_t out1[8], const sc &k, co
 EG_HD void prove_forge_pair(uint32_t cg[8], uint32_t ck[8], const ge_ext &R, const ge_ext &B, const sc &e, const sc &s, uint32_t a,
                             uint32_t *scratch, const uint32_t *tab_g, const uint32_t *tab_k) {
     uint32_t *tab_r = scratch, *tab_b = scratch + EG_VTAB_WORDS;
-    ge_vtab_build(tab_r, R);
-    ge_vtab_build(tab_b, B);
+    ge_vtab_build<EG_VCHUNKS_SHORT>(tab_r, R);
+    ge_vtab_build<EG_VCHUNKS_SHORT>(tab_b, B);
     sc ne, hne, hs, hea;
     sc_neg(ne, e);
     sc_half(hne, ne);
     sc_half(hs, s);
     ge_ext qg, qk;
-    ge_eval64(qg, tab_r, hne, 1, tab_g, hs, tab_g, hs);
+    ge_eval64<EG_VCHUNKS_SHORT>(qg, tab_r, hne, 1, tab_g, hs, tab_g, hs);
     if (a) {
         sc ea;
         sc_mul(ea, e, sc_from_u64(a));
         sc_half(hea, ea);
-        ge_eval64(qk, tab_b, hne, 2, tab_k, hs, tab_g, hea);
+        ge_eval64<EG_VCHUNKS_SHORT>(qk, tab_b, hne, 2, tab_k, hs, tab_g, hea);
     } else {
-        ge_eval64(qk, tab_b, hne, 1, tab_k, hs, tab_k, hs);
+        ge_eval64<EG_VCHUNKS_SHORT>(qk, tab_b, hne, 1, tab_k, hs, tab_k, hs);
     }
     ge_double_compress2(cg, ck, qg, qk);
 }
@@ -504,8 +505,8 @@ EG_HD void prove_ring1_body(const prove_params &P, size_t item, uint32_t k, uint
     ge_ext qr, qb, R, B;
     sc hone;
     sc_half(hone, sc_from_u64(1));
-    ge_eval64(qr, nullptr, hr, 1, tab_g, hr, tab_g, hr);
-    ge_eval64(qb, nullptr, hr, v ? 2 : 1, tab_k, hr, tab_g, hone);
+    ge_eval_fixed(qr, 1, tab_g, hr, tab_g, hr);
+    ge_eval_fixed(qb, v ? 2 : 1, tab_k, hr, tab_g, hone);
     uint32_t enc_ct[16];
     ge_double_compress2(enc_ct, enc_ct + 8, qr, qb);
     ge_dbl(R, qr);
@@ -566,8 +567,8 @@ EG_HD void prove_common_body(const prove_params &P, size_t item, const uint32_t 
     sc_half(hr, sum_r);
     sc_half(hv, vm1);
     ge_ext q0, q1;
-    ge_eval64(q0, nullptr, hr, 1, tab_g, hr, tab_g, hr);
-    ge_eval64(q1, nullptr, hr, 2, tab_k, hr, tab_g, hv);
+    ge_eval_fixed(q0, 1, tab_g, hr, tab_g, hr);
+    ge_eval_fixed(q1, 2, tab_k, hr, tab_g, hv);
     ge_double_compress2(w, w2, q0, q1);
     transcript st = P.sum_prefix;
     merlin_append_words(st, EG_LBL("[r]G"), w, 8);
@@ -685,8 +686,8 @@ EG_HD void rprove_encrypt(ge_ext &R, ge_ext &B, uint32_t enc_ct[16], const sc &r
     sc_half(hr, r);
     sc_half(hv, sc_from_u64(v));
     ge_ext qr, qb;
-    ge_eval64(qr, nullptr, hr, 1, tab_g, hr, tab_g, hr);
-    ge_eval64(qb, nullptr, hr, v ? 2 : 1, tab_k, hr, tab_g, hv);
+    ge_eval_fixed(qr, 1, tab_g, hr, tab_g, hr);
+    ge_eval_fixed(qb, v ? 2 : 1, tab_k, hr, tab_g, hv);
     ge_double_compress2(enc_ct, enc_ct + 8, qr, qb);
     ge_dbl(R, qr);
     ge_dbl(B, qb);
@@ -700,14 +701,14 @@ EG_HD void rprove_forge(uint32_t cg[8], uint32_t ck[8], const uint32_t *tab_r, c
     sc_half(hne, ne);
     sc_half(hs, s);
     ge_ext qg, qk;
-    ge_eval64(qg, tab_r, hne, 1, tab_g, hs, tab_g, hs);
+    ge_eval64<EG_VCHUNKS_LONG>(qg, tab_r, hne, 1, tab_g, hs, tab_g, hs);
     if (a) {
         sc ea;
         sc_mul(ea, e, sc_from_u64(a));
         sc_half(hea, ea);
-        ge_eval64(qk, tab_b, hne, 2, tab_k, hs, tab_g, hea);
+        ge_eval64<EG_VCHUNKS_LONG>(qk, tab_b, hne, 2, tab_k, hs, tab_g, hea);
     } else {
-        ge_eval64(qk, tab_b, hne, 1, tab_k, hs, tab_k, hs);
+        ge_eval64<EG_VCHUNKS_LONG>(qk, tab_b, hne, 1, tab_k, hs, tab_k, hs);
     }
     ge_double_compress2(cg, ck, qg, qk);
 }
@@ -763,8 +764,8 @@ EG_HD void rprove_ring1_body(const rprove_params &P, size_t item, uint32_t slot,
     prove_commit_pair(cg, ck, x, tab_g, tab_k);
     if (L.vi + 1 < m) {
         uint32_t *tab_r = scratch, *tab_b = scratch + EG_VTAB_WORDS;
-        ge_vtab_build(tab_r, R);
-        ge_vtab_build(tab_b, B);
+        ge_vtab_build<EG_VCHUNKS_LONG>(tab_r, R);
+        ge_vtab_build<EG_VCHUNKS_LONG>(tab_b, B);
         transcript rt;
         ring_transcript_start(rt, P.prefix, enc_ct, k);
         uint8_t *resp = P.ring_out + rprove_off(P, item, P.ring_stride, P.out_inner) + 32 * (1 + (size_t)P.starts[k]);
@@ -812,8 +813,8 @@ EG_HD void rprove_ring2_body(const rprove_params &P, size_t item, uint32_t k, ui
         planar_load_point(R, P.pts, P.n, 2 * k, item);
         planar_load_point(B, P.pts, P.n, 2 * k + 1, item);
         uint32_t *tab_r = scratch, *tab_b = scratch + EG_VTAB_WORDS;
-        ge_vtab_build(tab_r, R);
-        ge_vtab_build(tab_b, B);
+        ge_vtab_build<EG_VCHUNKS_LONG>(tab_r, R);
+        ge_vtab_build<EG_VCHUNKS_LONG>(tab_b, B);
         uint32_t enc_ct[16], cg[8], ck[8];
         planar_load_words(enc_ct, P.enc, P.n, 2 * k, 8, item);
         planar_load_words(enc_ct + 8, P.enc, P.n, 2 * k + 1, 8, item);
@@ -923,8 +924,8 @@ EG_HD void sumsq_prove_body(const sumsq_prove_params &P, size_t item, const uint
         sc_half(her, e_r[i]);
         sc_half(hex_, e_x[i]);
         ge_ext q0, q1;
-        ge_eval64(q0, nullptr, her, 1, tab_g, her, tab_g, her);
-        ge_eval64(q1, nullptr, her, 2, tab_k, her, tab_g, hex_);
+        ge_eval_fixed(q0, 1, tab_g, her, tab_g, her);
+        ge_eval_fixed(q1, 2, tab_k, her, tab_g, hex_);
         ge_double_compress2(c0, c1, q0, q1);
         merlin_append_words(t, EG_LBL("[e_r]G"), c0, 8);
         merlin_append_words(t, EG_LBL("[e_x]G + [e_r]K"), c1, 8);
@@ -940,8 +941,8 @@ EG_HD void sumsq_prove_body(const sumsq_prove_params &P, size_t item, const uint
         sc_half(ha, acc_r);
         sc_half(hx, acc_x);
         ge_ext q0, q1;
-        ge_eval64(q0, nullptr, ha, 1, tab_g, ha, tab_g, ha);
-        ge_eval64(q1, nullptr, ha, 2, tab_k, ha, tab_g, hx);
+        ge_eval_fixed(q0, 1, tab_g, ha, tab_g, ha);
+        ge_eval_fixed(q1, 2, tab_k, ha, tab_g, hx);
         ge_double_compress2(c0, c1, q0, q1);
     }
     const uint8_t *zct = P.sum_ct + item * P.ct_stride;

@@ -47,7 +47,10 @@ __global__ void __launch_bounds__(256) k_pipe(int iters, uint32_t a, uint32_t b,
                 if (KIND == 4) { x[i] = x[i] * a + b; w[i] += x[(i + 1) % U] ^ w[i]; }          // IMAD + ALU
                 if (KIND == 5) d[i] = fma(d[i], da, db);                              // DFMA
                 if (KIND == 6) { w[i] = (uint64_t)(uint32_t)w[i] * a + w[i]; d[i] = fma(d[i], da, db); }  // IMAD.WIDE + DFMA
-                if (KIND == 7) {                                                       // carry-chained wide mads (as in fe_mul)
+                if (KIND == 8 || KIND == 10) x[i] = x[i] * a + b;                      // + 1 IMAD per 2 wide mads
+                if (KIND == 9 || KIND == 10) x[i] = (x[i] ^ a) + (x[i] >> 5);          // + 3 ALU ops (LOP3, SHF, IADD3) per 2 wide mads
+                if (KIND == 11) { x[i] = (x[i] ^ a) + (x[i] >> 5); x[i] = (x[i] ^ b) + (x[i] >> 7); }   // + 6 ALU ops
+                if (KIND >= 7) {                                                       // carry-chained wide mads (as in fe_mul)
                     uint32_t lo = (uint32_t)w[i], hi = (uint32_t)(w[i] >> 32);
                     asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.cc.u32 %1, %2, %3, %1;\n\t"
                                  "madc.lo.cc.u32 %0, %2, %4, %0;\n\tmadc.hi.u32 %1, %2, %4, %1;"
@@ -68,6 +71,15 @@ static __device__ __noinline__ eg::fe fe_mul_sf_call(const eg::fe a, const eg::f
     eg::fe r;
 #if defined(__CUDA_ARCH__)
     eg::fe_mul_ptx_sf(r, a, b);
+#else
+    eg::fe_mul_portable(r, a, b);
+#endif
+    return r;
+}
+static __device__ __noinline__ eg::fe fe_mul_k_call(const eg::fe a, const eg::fe b) {
+    eg::fe r;
+#if defined(__CUDA_ARCH__)
+    eg::fe_mul_ptx_k(r, a, b);
 #else
     eg::fe_mul_portable(r, a, b);
 #endif
@@ -99,6 +111,7 @@ __global__ void __launch_bounds__(128) k_field(int iters, const uint32_t *seed, 
         if (KIND == 4) { eg::fe_add(x, x, y); eg::fe_sub(y, y, x); }
         if (KIND == 5) { x = fe_mul_sf_call(x, y); y = fe_mul_sf_call(y, x); }
         if (KIND == 6) { x = fe_sq_sf_call(x); y = fe_sq_sf_call(y); }
+        if (KIND == 7) { x = fe_mul_k_call(x, y); y = fe_mul_k_call(y, x); }
     }
     long long t1 = clock64();
     uint32_t acc = 0;
@@ -159,6 +172,10 @@ int main(int argc, char **argv) {
     PIPE(5, "dfma", 1);
     PIPE(6, "imad_wide_plus_dfma(pairs)", 1);
     PIPE(7, "mad_wide_carry_chain(wide mads)", 2);
+    PIPE(8, "wide_chain_plus_imad_2to1(wide mads)", 2);
+    PIPE(9, "wide_chain_plus_3alu_per_2(wide mads)", 2);
+    PIPE(10, "wide_chain_plus_imad_plus_3alu(wide mads)", 2);
+    PIPE(11, "wide_chain_plus_6alu_per_2(wide mads)", 2);
     const int fiters = iters / 4;
 #define FIELD(kind, nm, cps_) run(nm, [&](int bl, int th) { k_field<kind><<<bl, th>>>(fiters, seed, sink, cycles); }, sms * cps_, 128, (double)fiters * 2)
     FIELD(0, "fe_mul_ptx_w16", 4);
@@ -168,6 +185,9 @@ int main(int argc, char **argv) {
     FIELD(4, "fe_addsub_w16", 4);
     FIELD(5, "fe_mul_shiftfold_w16", 4);
     FIELD(6, "fe_sq_shiftfold_w16", 4);
+    FIELD(7, "fe_mul_karatsuba_w16", 4);
+    FIELD(7, "fe_mul_karatsuba_w20", 5);
+    FIELD(7, "fe_mul_karatsuba_w32", 8);
     FIELD(5, "fe_mul_shiftfold_w20", 5);
     FIELD(6, "fe_sq_shiftfold_w20", 5);
     FIELD(0, "fe_mul_ptx_w20", 5);
