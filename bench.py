@@ -410,7 +410,7 @@ def main():
         "traffic": traffic,
         "launches": commit_launches, "avg_launch_ms": commit_ms / max(1, commit_launches),
         "share_of_step": commit_ms / dev_ms if dev_ms else None,
-        "ncu": "profiles/r1_k_ring_full_s5.txt: fmaheavy pipe 88.0 % busy, issue slots 45.9 %, 19.7 warps/SM, top stall math_pipe_throttle (ncu --set full, same command)",
+        "ncu": "profiles/r1_k_ring_full_s6.txt: fmaheavy pipe 85.2 % busy, issue slots 45.9 %, 15.8 warps/SM, top stalls wait / math_pipe_throttle (ncu --set full, same command)",
         "second_kernel": {"kernel": "k_commit (sum proof)", "launches": other_launches, "equation_sides": other_tasks,
                           "ms": other_ms, "share_of_step": other_ms / dev_ms if dev_ms else None} if dom_kind == 1 else None,
         "algorithmic": {"field_ops_per_equation_side": FIELD_OPS_PER_COMMIT, "imad_per_field_op": IMAD_PER_FIELD_OP,

@@ -284,6 +284,15 @@ EG_HD void ge_cached_load(ge_cached &c, const uint32_t *e) {
 #ifndef EG_HOT_DBL_OPS
 #define EG_HOT_DBL_OPS EG_HOT_OPS
 #endif
+#ifndef EG_HOT_DBL_PROJ_OPS
+#define EG_HOT_DBL_PROJ_OPS EG_HOT_DBL_OPS
+#endif
+#ifndef EG_EVAL_DBL_OPS
+#define EG_EVAL_DBL_OPS fe_ops_call
+#endif
+#ifndef EG_EVAL_PROJ_OPS
+#define EG_EVAL_PROJ_OPS fe_ops_call
+#endif
 
 // acc = 2^n acc (n >= 1); intermediate doublings stay projective, T is produced by the last one
 static EG_HD_NOINLINE void ge_hot_dbl(ge_ext &acc, int n) {
@@ -292,8 +301,8 @@ static EG_HD_NOINLINE void ge_hot_dbl(ge_ext &acc, int n) {
 #pragma unroll 1
     for (int k = 0; k < n; k++) {
         ge_dbl_p1p1<EG_HOT_DBL_OPS>(t, a);
-        ge_p1p1_to_proj<EG_HOT_DBL_OPS>(a, t);
-        if (k == n - 1) EG_HOT_DBL_OPS::mul(a.T, t.E, t.H);
+        ge_p1p1_to_proj<EG_HOT_DBL_PROJ_OPS>(a, t);
+        if (k == n - 1) EG_HOT_DBL_PROJ_OPS::mul(a.T, t.E, t.H);
     }
     acc = a;
 }
@@ -530,8 +539,8 @@ static EG_HD_NOINLINE void ge_eval64(ge_ext &out, const uint32_t *vtab, const sc
             if (i != W - 1) {
 #pragma unroll 1
                 for (int k = 0; k < 4; k++) {
-                    ge_dbl_p1p1(t, acc);
-                    ge_p1p1_to_proj(acc, t);
+                    ge_dbl_p1p1<EG_EVAL_DBL_OPS>(t, acc);
+                    ge_p1p1_to_proj<EG_EVAL_PROJ_OPS>(acc, t);
                     if (k == 3) fe_mul(acc.T, t.E, t.H);
                 }
             }

@@ -15,6 +15,19 @@ def sc(x):
     return (x % L).to_bytes(32, "little")
 
 
+def wide_window_edge_scalars():
+    """Scalars that sit on the digit boundaries of the signed fixed-base windows (ge.cuh sc_wide_digit: 16-bit windows,
+    digits in [-2^15, 2^15), carries rippling through runs of 0xffff / 0x7fff / 0x8000 chunks), all canonical (< l)."""
+    out = []
+    for chunk in (0x8000, 0x7fff, 0xffff, 0x8001, 0x0001, 0xfffe):
+        x = sum(chunk << (16 * i) for i in range(16)) % L
+        out += [sc(x), sc(L - x)]
+    for k in (15, 16, 17, 31, 32, 47, 48, 63, 64, 127, 128, 239, 240, 247, 251, 252):
+        out += [sc(2**k), sc(2**k - 1), sc(L - 2**k), sc((2**k) + 0x8000), sc((0x7fff8000ffff0000 << k) % L)]
+    out += [sc(L - 2), sc((L - 1) // 2), sc((L + 1) // 2), sc(2**252 + 2**15), sc(2**252 - 2**15)]
+    return out
+
+
 def check_group_helpers(e, n=24):
     rnd = random.Random(11)
     # elements: valid multiples, the RFC 9496 invalid vectors, identity
@@ -38,14 +51,15 @@ def check_group_helpers(e, n=24):
     for i, w in enumerate(wide):
         assert bytes(out[i]) == O.scalar_reduce_wide(w)
     # [k]G and [a]A + [b]G
-    ks = [sc(rnd.randrange(L)) for _ in range(n)] + [sc(0), sc(1), sc(L - 1), sc(8), sc(2**252)]
+    ks = [sc(rnd.randrange(L)) for _ in range(n)] + [sc(0), sc(1), sc(L - 1), sc(8), sc(2**252)] + wide_window_edge_scalars()
     out, ok = e.mul_generator(np.frombuffer(b"".join(ks), np.uint8))
     assert ok.all()
     for i, k in enumerate(ks):
         assert bytes(out[i]) == O.point_mul_generator(k), i
-    a = [sc(rnd.randrange(L)) for _ in range(n)] + [sc(0), sc(L - 1), sc(1)]
-    b = [sc(rnd.randrange(L)) for _ in range(n)] + [sc(5), sc(0), sc(L - 1)]
-    A = [O.point_mul_generator(sc(rnd.randrange(L))) for _ in range(n)] + [bytes(32), W.G_ENC, W.G_ENC]
+    edge = wide_window_edge_scalars()[::5]
+    a = [sc(rnd.randrange(L)) for _ in range(n)] + [sc(0), sc(L - 1), sc(1)] + edge[::-1]
+    b = [sc(rnd.randrange(L)) for _ in range(n)] + [sc(5), sc(0), sc(L - 1)] + edge
+    A = [O.point_mul_generator(sc(rnd.randrange(L))) for _ in range(n)] + [bytes(32), W.G_ENC, W.G_ENC] + [W.G_ENC] * len(edge)
     out, ok = e.double_mul_generator(np.frombuffer(b"".join(a), np.uint8), np.frombuffer(b"".join(A), np.uint8),
                                      np.frombuffer(b"".join(b), np.uint8))
     assert ok.all()
