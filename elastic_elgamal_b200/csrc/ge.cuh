@@ -308,12 +308,14 @@ static EG_HD_NOINLINE void ge_hot_dbl(ge_ext &acc, int n) {
 }
 
 // acc += (neg ? -Q : Q), Q a cached point at `entry` (32 words, 16-byte aligned)
-static EG_HD_NOINLINE void ge_hot_add_cached(ge_ext &acc, const uint32_t *entry, bool neg) {
+// need_t = false leaves T stale: enough when a doubling follows
+static EG_HD_NOINLINE void ge_hot_add_cached(ge_ext &acc, const uint32_t *entry, bool neg, bool need_t = true) {
     ge_cached q;
     ge_cached_load(q, entry);
     ge_p1p1 t;
     ge_add_cached_p1p1<EG_HOT_OPS>(t, acc, q, neg);
-    ge_p1p1_to_ext<EG_HOT_OPS>(acc, t);
+    ge_p1p1_to_proj<EG_HOT_OPS>(acc, t);
+    if (need_t) EG_HOT_OPS::mul(acc.T, t.E, t.H);
 }
 
 // acc += (neg ? -Q : Q), Q = entry `idx` of an affine Niels table (24 words per entry, 16-byte aligned)
@@ -414,7 +416,7 @@ EG_HD void ge_msm_chain(ge_ext &out, const ge_ext *P, const sc *a, const uint32_
 #pragma unroll 1
             for (int v = 0; v < NV; v++) {
                 int d = sc_digit4(ra[v], i);
-                if (d != 0) ge_hot_add_cached(acc, (const uint32_t *)&tbl[v][(d < 0 ? -d : d) - 1], d < 0);
+                if (d != 0) ge_hot_add_cached(acc, (const uint32_t *)&tbl[v][(d < 0 ? -d : d) - 1], d < 0, v != NV - 1 || i == 0);
             }
         }
     }
@@ -444,7 +446,7 @@ EG_HD void ge_msm_chain_rt(ge_ext &out, int nv, const ge_ext *P, const sc *a, in
 #pragma unroll 1
             for (int v = 0; v < nv; v++) {
                 int d = sc_digit4(ra[v], i);
-                if (d != 0) ge_hot_add_cached(acc, (const uint32_t *)&tbl[v][(d < 0 ? -d : d) - 1], d < 0);
+                if (d != 0) ge_hot_add_cached(acc, (const uint32_t *)&tbl[v][(d < 0 ? -d : d) - 1], d < 0, v != nv - 1 || i == 0);
             }
         }
     }
