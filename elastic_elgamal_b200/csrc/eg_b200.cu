@@ -54,7 +54,7 @@ struct eg_ctx {
     cudaStream_t copy_stream = nullptr;     // host -> device prefetch of the next chunk
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr};
     dev_buf in2[3];
-    dev_buf pts, enc, commit, chal, flags, res[3], in[4], verdicts, partial, running, adm, misc, slots, consts, res_big;
+    dev_buf pts, enc, commit, chal, flags, res[3], in[4], verdicts, partial, running, adm, misc, slots, consts, res_big, term;
     size_t adm_used = 0;      // cached points in `adm` (32 words each); entries 0,1 = the [O, G] pair
     std::map<std::string, std::vector<uint64_t>> adm_cache_key;
     size_t chunk_items = 0;   // 0 = default
@@ -155,6 +155,15 @@ static void launch_commit(eg_ctx *ctx, const commit_params &P) {
     ctx->commit_tasks += total;
     ctx->call_commit_tasks += total;
     ctx->call_commit_launches++;
+}
+
+static void launch_terminal(eg_ctx *ctx, const terminal_params &P) {
+#ifdef EG_HOSTSIM
+    EG_FOR_HOST(P.n, terminal_body(P, tid))
+#else
+    k_terminal<<<grid_for(P.n, 128), 128, 0, ctx->stream>>>(P);
+#endif
+    ctx->launches++;
 }
 
 // One launch evaluates every equation of every ring of the chunk.  Accounted like k_commit: tasks = equation sides.
@@ -692,7 +701,7 @@ extern "C" void eg_ctx_destroy(eg_ctx *ctx) {
     dev_buf *bufs[] = {&ctx->pts, &ctx->enc, &ctx->commit, &ctx->chal, &ctx->flags, &ctx->res[0], &ctx->res[1], &ctx->res[2],
                        &ctx->in[0], &ctx->in[1], &ctx->in[2], &ctx->in[3], &ctx->verdicts, &ctx->partial, &ctx->running,
                        &ctx->adm, &ctx->misc, &ctx->slots, &ctx->consts, &ctx->res_big, &ctx->ring_scratch,
-                       &ctx->in2[0], &ctx->in2[1], &ctx->in2[2]};
+                       &ctx->in2[0], &ctx->in2[1], &ctx->in2[2], &ctx->term};
     for (dev_buf *b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->d_table_g) cudaFree(ctx->d_table_g);
     if (ctx->d_table_k) cudaFree(ctx->d_table_k);

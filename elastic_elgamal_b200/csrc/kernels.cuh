@@ -171,8 +171,10 @@ struct commit_params {
     const uint32_t *chal;       // planar scalars (8 words)
     uint32_t *commit;           // planar encodings (8 words)
     const uint32_t *adm;        // admissible values: cached points, 32 words each (YpX, YmX, Z, T2d)
-    const uint32_t *table_g;    // 128-entry affine tables (24 words per entry)
+    const uint32_t *table_g;    // wide fixed-base tables (ge.cuh)
     const uint32_t *table_k;
+    uint32_t *term_pts;         // when set: slot k stores the half-scalar point Q (2Q = C) at planar index term_base + k
+    uint32_t term_base;         //   of this buffer instead of encoding C; k_terminal encodes all of an item's points at once
 };
 
 EG_HD void commit_body(const commit_params &P, size_t item, int slot, const uint32_t *tab_g, const uint32_t *tab_k) {
@@ -198,6 +200,14 @@ EG_HD void commit_body(const commit_params &P, size_t item, int slot, const uint
     sc_neg(ne, e);
     ge_ext acc;
     const uint32_t *ft[1] = {s.base ? tab_k : tab_g};
+    if (P.term_pts) {
+        sc hne, hr;
+        sc_half(hne, ne);
+        sc_half(hr, r);
+        ge_msm_chain<1, 1>(acc, &pt, &hne, ft, &hr);
+        planar_store_point(P.term_pts, P.n, P.term_base + slot, item, acc);
+        return;
+    }
     ge_msm_chain<1, 1>(acc, &pt, &ne, ft, &r);
     ge_encode(w, acc);
     planar_store_words(P.commit, P.n, s.out_index, 8, item, w);
@@ -351,7 +361,9 @@ struct ring_params {
     const uint32_t *enc;
     uint32_t *commit;
     uint32_t *scratch;                      // 2 * EG_VTAB_WORDS words per resident thread
-    const uint32_t *table_g, *table_k;      // 4-chunk fixed tables
+    const uint32_t *table_g, *table_k;      // wide fixed-base tables
+    uint32_t *term_pts;                     // when set: the half-scalar points of ring r's LAST equation go to planar
+                                            // indexes 2r, 2r + 1 of this buffer and are encoded by k_terminal
 };
 
 // the ring's own transcript: prefix + start_proof("ring_enc") + "enc" + "i"   (ring.rs:325-331)
@@ -413,11 +425,65 @@ EG_HD void ring_body(const ring_params &P, size_t item, uint32_t r, uint32_t *sc
         } else {
             ge_eval64<C>(qk, tab_b, hne, 1, tab_k, hs, tab_k, hs);
         }
+        if (j + 1 == size && P.term_pts) {
+            planar_store_point(P.term_pts, P.n, 2 * r, item, qg);
+            planar_store_point(P.term_pts, P.n, 2 * r + 1, item, qk);
+            return;
+        }
         ge_double_compress2(cg, ck, qg, qk);
         if (j + 1 < size) ring_next_challenge(e, rt, j, cg, ck);
     }
     planar_store_words(P.commit, P.n, P.commit_index0 + 2 * r, 8, item, cg);
     planar_store_words(P.commit, P.n, P.commit_index0 + 2 * r + 1, 8, item, ck);
+}
+
+// ---- terminal commitments: encode(2 Q_k) for all deferred points of an item with ONE field inversion ---------------
+//
+// The commitments of a ring's last equation (and of an EncryptedChoice's sum proof) are only read by the outer
+// transcripts, so their encodings are not needed inside the sequential chains: k_ring / k_commit store the half-scalar
+// points and one thread per item encodes all of them here (Montgomery's trick over ge_dc_prepare's products): a 5-option
+// ballot pays 12 x ~30 + 265 field operations instead of 5 x 304 + 2 x 280.
+#define EG_TERM_MAX (2 * EG_MAX_RINGS + 2)
+
+struct terminal_params {
+    size_t n;
+    uint32_t n_pts;
+    uint16_t out_index[EG_TERM_MAX];        // planar index in `commit` of the encoding of point k
+    const uint32_t *term_pts;
+    uint32_t *commit;
+};
+
+EG_HD void terminal_body(const terminal_params &P, size_t item) {
+    fe prefix[EG_TERM_MAX];
+    fe run = fe_one();
+#pragma unroll 1
+    for (uint32_t k = 0; k < P.n_pts; k++) {
+        ge_ext q;
+        ge_dc_state st;
+        fe t, u;
+        planar_load_point(q, P.term_pts, P.n, k, item);
+        ge_dc_prepare(st, t, q);
+        fe_select(u, t, fe_one(), fe_iszero(t));
+        if (k) fe_mul(run, run, u); else run = u;
+        prefix[k] = run;
+    }
+    fe inv;
+    fe_invert(inv, run);
+#pragma unroll 1
+    for (int k = (int)P.n_pts - 1; k >= 0; k--) {
+        ge_ext q;
+        ge_dc_state st;
+        fe t, u, ik;
+        planar_load_point(q, P.term_pts, P.n, (uint32_t)k, item);
+        ge_dc_prepare(st, t, q);
+        const bool z = fe_iszero(t);
+        fe_select(u, t, fe_one(), z);
+        if (k) { fe_mul(ik, inv, prefix[k - 1]); fe_mul(inv, inv, u); } else ik = inv;
+        fe_select(ik, ik, fe_zero(), z);
+        uint32_t w[8];
+        ge_dc_finish(w, st, ik);
+        planar_store_words(P.commit, P.n, P.out_index[k], 8, item, w);
+    }
 }
 
 // ------------------------------------------------------------------ proving side: encrypt_bool / EncryptedChoice::new
