@@ -55,6 +55,7 @@ struct eg_ctx {
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr};
     dev_buf in2[3];
     dev_buf pts, enc, commit, chal, flags, res[3], in[4], verdicts, partial, running, adm, misc, slots, consts, res_big, term;
+    terminal_params term_plan;   // deferred encodings of the slot table uploaded last (upload_slots); n_pts == 0: none
     size_t adm_used = 0;      // cached points in `adm` (32 words each); entries 0,1 = the [O, G] pair
     std::map<std::string, std::vector<uint64_t>> adm_cache_key;
     size_t chunk_items = 0;   // 0 = default
@@ -543,7 +544,15 @@ static void launch_ciphertexts_sum(eg_ctx *ctx, const uint8_t *parts, size_t n_p
     ctx->launches++;
 }
 
-static void launch_msm(eg_ctx *ctx, const msm_params &P) {
+// k_msm over the slot table uploaded last; slots whose encoding was deferred by upload_slots are encoded together by
+// k_terminal (one inversion per item) right after.
+static eg_status launch_msm(eg_ctx *ctx, const msm_params &P0) {
+    msm_params P = P0;
+    const uint32_t n_term = ctx->term_plan.n_pts;
+    if (n_term) {
+        TRY(ensure(ctx, ctx->term, P.n * (size_t)n_term * 128));
+        P.term_pts = (uint32_t *)ctx->term.p;
+    }
     size_t total = P.n * (size_t)P.n_slots;
 #ifdef EG_HOSTSIM
     EG_FOR_HOST(total, msm_body(P, tid % P.n, (int)(tid / P.n), P.table_g, P.table_k, P.table_h))
@@ -551,6 +560,12 @@ static void launch_msm(eg_ctx *ctx, const msm_params &P) {
     k_msm<<<grid_for(total, 128), 128, 0, ctx->stream>>>(P);
 #endif
     ctx->launches++;
+    if (n_term) {
+        terminal_params tp = ctx->term_plan;
+        tp.n = P.n; tp.term_pts = P.term_pts; tp.commit = P.commit;
+        launch_terminal(ctx, tp);
+    }
+    return EG_SUCCESS;
 }
 
 static void launch_sigma_final(eg_ctx *ctx, const sigma_final_params &P) {

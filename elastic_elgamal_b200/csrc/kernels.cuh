@@ -236,13 +236,14 @@ struct scalar_src {
 
 struct msm_slot {
     uint8_t nv, nf;             // per-item / constant bases ; fixed bases (G / K tables)
-    uint8_t out_enc;            // store the 8-word encoding at commit[out_index]
+    uint8_t out_enc;            // 1: store the 8-word encoding at commit[out_index]; 2: deferred to k_terminal (see `term`)
     uint8_t out_point;          // store the extended point at pts[out_index]
     uint32_t out_index;
     uint32_t p_index[EG_MSM_MAXV];   // planar point index, or index into const_pts when bit 31 is set
     scalar_src vs[EG_MSM_MAXV];
     uint8_t fbase[2];           // 0: G, 1: K, 2: H (Pedersen blinding base, eg_ctx_set_blinding_base)
-    uint8_t pad2[2];
+    uint8_t term;               // out_enc == 2: index of the half-scalar point in msm_params::term_pts (encoded by k_terminal)
+    uint8_t pad2;
     scalar_src fs[2];
 };
 
@@ -259,6 +260,7 @@ struct msm_params {
     uint32_t *pts_out;          // planar points out
     const uint32_t *table_g, *table_k;
     const uint32_t *table_h;    // may be null when no slot uses base 2
+    uint32_t *term_pts;         // planar points of the deferred encodings (slots with out_enc == 2)
 };
 
 EG_HD bool load_scalar(sc &out, const msm_params &P, const scalar_src &src, size_t item) {
@@ -289,6 +291,13 @@ EG_HD void msm_body(const msm_params &P, size_t item, int slot, const uint32_t *
         load_scalar(b[f], P, s.fs[f], item);
     }
     ge_ext acc;
+    if (s.out_enc == 2) {       // all scalars halved: acc = Q with 2 Q = the commitment, encoded later with its siblings
+        for (int v = 0; v < s.nv; v++) { sc h; sc_half(h, a[v]); a[v] = h; }
+        for (int f = 0; f < s.nf; f++) { sc h; sc_half(h, b[f]); b[f] = h; }
+        ge_msm_chain_rt<EG_MSM_MAXV>(acc, s.nv, pts, a, s.nf, ft, b);
+        planar_store_point(P.term_pts, P.n, s.term, item, acc);
+        return;
+    }
     ge_msm_chain_rt<EG_MSM_MAXV>(acc, s.nv, pts, a, s.nf, ft, b);
     if (s.out_point) planar_store_point(P.pts_out, P.n, s.out_index, item, acc);
     if (s.out_enc) {
