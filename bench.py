@@ -41,8 +41,9 @@ FIELD_OPS_PER_COMMIT = 4956 / 2 + 280
 FIELD_OPS_PER_BALLOT = 4956 * 11 + 280 * (34 + 10)               # 66 836
 # What k_ring actually executes per equation side of a two-equation ring, counted from the formulas in
 # ge.cuh: 2 x 1603 table build (192 doublings + 28 additions per point) + 4 sides x (435 for 60 doublings + 497 for 64
-# per-item additions + 112 for 16 fixed-base additions from the wide table) + 112 for the [e a]G term + 2 x 304 encoding.
-EXECUTED_FIELD_OPS_PER_RING_SIDE = (2 * 1603 + 4 * (435 + 497 + 112) + 112 + 2 * 304) / 4      # 2025.5
+# per-item additions + 112 for 16 fixed-base additions from the wide table) + 112 for the [e a]G term + 304 for encoding
+# the first equation's pair (the last equation's points are encoded by k_terminal, outside this kernel).
+EXECUTED_FIELD_OPS_PER_RING_SIDE = (2 * 1603 + 4 * (435 + 497 + 112) + 112 + 304) / 4      # 1949.5
 IMAD_PER_FIELD_OP = 144
 METRIC = "verified ballots/sec (5-option choice)"
 
@@ -410,7 +411,7 @@ def main():
         "traffic": traffic,
         "launches": commit_launches, "avg_launch_ms": commit_ms / max(1, commit_launches),
         "share_of_step": commit_ms / dev_ms if dev_ms else None,
-        "ncu": "profiles/r1_k_ring_full_s6.txt: fmaheavy pipe 85.2 % busy, issue slots 45.9 %, 15.8 warps/SM, top stalls wait / math_pipe_throttle (ncu --set full, same command)",
+        "ncu": "profiles/r1_k_ring_full_s7.txt: fmaheavy pipe 88.4 % busy, issue slots 45.6 %, 15.8 warps/SM, top stalls wait / math_pipe_throttle (ncu --set full, same command)",
         "second_kernel": {"kernel": "k_commit (sum proof)", "launches": other_launches, "equation_sides": other_tasks,
                           "ms": other_ms, "share_of_step": other_ms / dev_ms if dev_ms else None} if dom_kind == 1 else None,
         "algorithmic": {"field_ops_per_equation_side": FIELD_OPS_PER_COMMIT, "imad_per_field_op": IMAD_PER_FIELD_OP,
