@@ -345,6 +345,38 @@ def check_encrypt_choice(e, pk, options=5, n=12, seed=W.SEED_CHOICE):
     assert (v == 0).all()
 
 
+def check_identity_commitments(e, pk, options=5, n=20):
+    """Valid proofs whose commitments are the identity element (all-zero encodings): the prover's nonces are caller
+    supplied, so all-zero 64-byte blocks give x = 0, i.e. [x]G = [x]K = O, in the real equation of a ring (first
+    equation for value 0: encoded inside k_ring; last equation for value 1: deferred to k_terminal) and in the sum
+    proof (k_commit -> k_terminal).  The oracle must accept what the engine produced, and the engine its own output."""
+    draws = 3 * options + 1
+    rnd = random.Random(5)
+    wide = np.frombuffer(rnd.randbytes(n * draws * 64), np.uint8).reshape(n, draws, 64).copy()
+    values = np.zeros((n, options), np.uint8)
+    for i in range(n):
+        c = i % options
+        values[i, c] = 1
+        pos = 0
+        for k in range(options):                     # ring k draws r_k, x_k and, for value 0, the forged response
+            if (i // options + k) % 2 == 0:
+                wide[i, pos + 1] = 0                 # x_k = 0
+            pos += 2 + (0 if k == c else 1)
+        if i % 3 != 1:
+            wide[i, draws - 1] = 0                   # nonce of the sum proof
+    cts, rings, sums = e.encrypt_choice(options, values, wide, single=True)
+    expected, exp_tally = O.verify_choice_batch(pk, options, True, cts, rings, sums)
+    assert (expected == 0).all()
+    got, tally = e.verify_choice(options, cts, rings, sums, single=True, tally=True)
+    assert (got == 0).all() and (tally == exp_tally).all()
+    # and a flipped response still fails the same way on both sides
+    rings = rings.copy()
+    rings[0, 1, 0] ^= 1
+    expected, _ = O.verify_choice_batch(pk, options, True, cts, rings, sums)
+    got, _ = e.verify_choice(options, cts, rings, sums, single=True, tally=False)
+    assert got.tolist() == expected.tolist() and got[0] != 0
+
+
 def check_encrypt_multi_choice(e, pk, options=4, n=10, seed=b"\x09" * 32):
     """EncryptedChoice::new with MultiChoice (choice.rs:313-349): any 0/1 pattern, no sum proof."""
     rnd = random.Random(17)

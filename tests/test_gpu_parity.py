@@ -164,6 +164,11 @@ def test_encrypt_choice(env):
     PC.check_encrypt_multi_choice(env[0], env[2], options=6, n=100)
 
 
+def test_identity_commitments(env):
+    PC.check_identity_commitments(env[0], env[2], options=5, n=200)
+    PC.check_identity_commitments(env[0], env[2], options=1, n=20)
+
+
 def test_encrypt_reference_snapshots(env):
     PC.check_encrypt_against_reference_snapshots(env[0])
 
