@@ -85,6 +85,24 @@ static __device__ __noinline__ eg::fe fe_mul_k_call(const eg::fe a, const eg::fe
 #endif
     return r;
 }
+struct fe_pair { eg::fe x, y; };
+// two independent multiplications / squarings in one call: does the extra instruction-level parallelism pay?
+static __device__ __noinline__ fe_pair fe_mul2_call(const eg::fe a0, const eg::fe b0, const eg::fe a1, const eg::fe b1) {
+    fe_pair r;
+#if defined(__CUDA_ARCH__)
+    eg::fe_mul_ptx(r.x, a0, b0);
+    eg::fe_mul_ptx(r.y, a1, b1);
+#endif
+    return r;
+}
+static __device__ __noinline__ fe_pair fe_sq2_call(const eg::fe a0, const eg::fe a1) {
+    fe_pair r;
+#if defined(__CUDA_ARCH__)
+    eg::fe_sq_ptx(r.x, a0);
+    eg::fe_sq_ptx(r.y, a1);
+#endif
+    return r;
+}
 static __device__ __noinline__ eg::fe fe_sq_sf_call(const eg::fe a) {
     eg::fe r;
 #if defined(__CUDA_ARCH__)
@@ -112,6 +130,8 @@ __global__ void __launch_bounds__(128) k_field(int iters, const uint32_t *seed, 
         if (KIND == 5) { x = fe_mul_sf_call(x, y); y = fe_mul_sf_call(y, x); }
         if (KIND == 6) { x = fe_sq_sf_call(x); y = fe_sq_sf_call(y); }
         if (KIND == 7) { x = fe_mul_k_call(x, y); y = fe_mul_k_call(y, x); }
+        if (KIND == 8) { fe_pair q = fe_mul2_call(x, y, y, x); x = q.x; y = q.y; }
+        if (KIND == 9) { fe_pair q = fe_sq2_call(x, y); x = q.x; y = q.y; }
     }
     long long t1 = clock64();
     uint32_t acc = 0;
@@ -185,6 +205,12 @@ int main(int argc, char **argv) {
     FIELD(4, "fe_addsub_w16", 4);
     FIELD(5, "fe_mul_shiftfold_w16", 4);
     FIELD(6, "fe_sq_shiftfold_w16", 4);
+    FIELD(8, "fe_mul2_pair_w8", 2);
+    FIELD(8, "fe_mul2_pair_w12", 3);
+    FIELD(8, "fe_mul2_pair_w16", 4);
+    FIELD(9, "fe_sq2_pair_w8", 2);
+    FIELD(9, "fe_sq2_pair_w12", 3);
+    FIELD(9, "fe_sq2_pair_w16", 4);
     FIELD(7, "fe_mul_karatsuba_w16", 4);
     FIELD(7, "fe_mul_karatsuba_w20", 5);
     FIELD(7, "fe_mul_karatsuba_w32", 8);
