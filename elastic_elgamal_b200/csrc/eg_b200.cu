@@ -748,7 +748,7 @@ extern "C" eg_status eg_ctx_set_receiver(eg_ctx *ctx, const uint8_t key[32]) {
 }
 
 // Pedersen blinding base H of CommitmentEquivalenceProof (commitment.rs:140-145: `commitment_blinding_base`), e.g. the
-// Bulletproofs base of tests/snapshots.rs:253-257.  Gets the same chunked fixed-base table as G and K.
+// Bulletproofs base of tests/snapshots.rs:253-257.  Gets the same wide fixed-base table as G and K.
 extern "C" eg_status eg_ctx_set_blinding_base(eg_ctx *ctx, const uint8_t base[32]) {
     if (!ctx || !base) return EG_ERR_INVALID_ARG;
     CU(cudaSetDevice(ctx->device));

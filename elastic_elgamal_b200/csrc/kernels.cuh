@@ -502,7 +502,7 @@ EG_HD void terminal_body(const terminal_params &P, size_t item) {
 // draw order, each reduced as in Ristretto::generate_scalar (ristretto.rs:28-32).  Ring k draws r_k, x_k
 // and -- when its value is 0 -- the forged response s_1 while the rings are added (ring.rs:97-116); after the common
 // challenge, rings whose value is 1 draw the forged s_0 in ring order (ring.rs:170-175); the sum proof nonce comes last.
-// All fixed-base work goes through the 4-chunk tables; every encoding is produced by double-and-compress on the
+// All fixed-base work goes through the wide tables (ge_eval_fixed); every encoding is produced by double-and-compress on the
 // half-scalar point.
 struct prove_params {
     size_t n;
