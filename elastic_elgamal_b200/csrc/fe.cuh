@@ -243,52 +243,6 @@ EG_HD void fe_sq(fe &r, const fe &a) {
 }
 
 // n >= 1 squarings; kept as a rolled loop so the exponentiation chains stay small in the I-cache
-// A/B hook (-DEG_PAIR_OPS=1): two independent multiplications / squarings in ONE call, so that the callee's carry-chain
-// streams interleave and the call overhead is paid once.  The microbenchmark likes it (16 warps per SM: 0.36 vs 0.33
-// multiplications, 0.50 vs 0.45 squarings per clock per SM), the kernels do not: 1.998 vs 2.040 M ballots/s, the paired
-// callee's register footprint adds spills around every call (profiles/r1_field_layer_negative_results.txt).  Off.
-#ifndef EG_PAIR_OPS
-#define EG_PAIR_OPS 0
-#endif
-#if defined(__CUDA_ARCH__) && !defined(EG_INLINE_FE) && !defined(EG_PORTABLE_FE) && EG_PAIR_OPS
-struct fe_pair { fe x, y; };
-static __device__ __noinline__ fe_pair fe_mul2_call(const fe a0, const fe b0, const fe a1, const fe b1) {
-    fe_pair r;
-    EG_FE_MUL_PTX(r.x, a0, b0);
-    EG_FE_MUL_PTX(r.y, a1, b1);
-    return r;
-}
-static __device__ __noinline__ fe_pair fe_sq2_call(const fe a0, const fe a1) {
-    fe_pair r;
-    EG_FE_SQ_PTX(r.x, a0);
-    EG_FE_SQ_PTX(r.y, a1);
-    return r;
-}
-#define EG_HAVE_PAIR_CALLS 1
-#endif
-
-// r0 = a0 b0, r1 = a1 b1 (outputs may alias inputs)
-EG_HD void fe_mul2(fe &r0, fe &r1, const fe &a0, const fe &b0, const fe &a1, const fe &b1) {
-#if defined(EG_HAVE_PAIR_CALLS)
-    const fe_pair q = fe_mul2_call(a0, b0, a1, b1);
-    r0 = q.x; r1 = q.y;
-#else
-    fe t;
-    fe_mul(t, a0, b0); fe_mul(r1, a1, b1); r0 = t;
-#endif
-}
-
-// r0 = a0^2, r1 = a1^2
-EG_HD void fe_sq2(fe &r0, fe &r1, const fe &a0, const fe &a1) {
-#if defined(EG_HAVE_PAIR_CALLS)
-    const fe_pair q = fe_sq2_call(a0, a1);
-    r0 = q.x; r1 = q.y;
-#else
-    fe t;
-    fe_sq(t, a0); fe_sq(r1, a1); r0 = t;
-#endif
-}
-
 EG_HD void fe_sqn(fe &r, const fe &a, int n) {
     fe t = a;
 #pragma unroll 1

@@ -38,8 +38,6 @@ EG_HD ge_ext ge_generator() {
 struct fe_ops_call {
     static EG_HD void mul(fe &r, const fe &a, const fe &b) { fe_mul(r, a, b); }
     static EG_HD void sq(fe &r, const fe &a) { fe_sq(r, a); }
-    static EG_HD void mul2(fe &r0, fe &r1, const fe &a0, const fe &b0, const fe &a1, const fe &b1) { fe_mul2(r0, r1, a0, b0, a1, b1); }
-    static EG_HD void sq2(fe &r0, fe &r1, const fe &a0, const fe &a1) { fe_sq2(r0, r1, a0, a1); }
 };
 struct fe_ops_inline {
     static EG_HD void mul(fe &r, const fe &a, const fe &b) {
@@ -56,28 +54,26 @@ struct fe_ops_inline {
         fe_sq_portable(r, a);
 #endif
     }
-    static EG_HD void mul2(fe &r0, fe &r1, const fe &a0, const fe &b0, const fe &a1, const fe &b1) { fe t; mul(t, a0, b0); mul(r1, a1, b1); r0 = t; }
-    static EG_HD void sq2(fe &r0, fe &r1, const fe &a0, const fe &a1) { fe t; sq(t, a0); sq(r1, a1); r0 = t; }
 };
 
 template <class O = fe_ops_call>
 EG_HD void ge_p1p1_to_ext(ge_ext &r, const ge_p1p1 &p) {
-    O::mul2(r.X, r.Y, p.E, p.F, p.G, p.H); O::mul2(r.Z, r.T, p.F, p.G, p.E, p.H);
+    O::mul(r.X, p.E, p.F); O::mul(r.Y, p.G, p.H); O::mul(r.Z, p.F, p.G); O::mul(r.T, p.E, p.H);
 }
 
 // projective only (T left stale): enough when a doubling follows
 template <class O = fe_ops_call>
 EG_HD void ge_p1p1_to_proj(ge_ext &r, const ge_p1p1 &p) {
-    O::mul2(r.X, r.Y, p.E, p.F, p.G, p.H); O::mul(r.Z, p.F, p.G);
+    O::mul(r.X, p.E, p.F); O::mul(r.Y, p.G, p.H); O::mul(r.Z, p.F, p.G);
 }
 
 // dbl-2008-hwcd; reads X, Y, Z only
 template <class O = fe_ops_call>
 EG_HD void ge_dbl_p1p1(ge_p1p1 &r, const ge_ext &p) {
     fe a, b, c, t;
-    O::sq2(a, b, p.X, p.Y);
-    fe_add(t, p.X, p.Y);
-    O::sq2(c, t, p.Z, t); fe_add(c, c, c);
+    O::sq(a, p.X); O::sq(b, p.Y);
+    O::sq(c, p.Z); fe_add(c, c, c);
+    fe_add(t, p.X, p.Y); O::sq(t, t);
     fe_add(r.H, a, b);              // A + B
     fe_sub(r.E, t, r.H);            // E = (X+Y)^2 - A - B
     fe_sub(r.G, b, a);              // G = B - A
@@ -95,8 +91,9 @@ EG_HD void ge_add_cached_p1p1(ge_p1p1 &r, const ge_ext &p, const ge_cached &q, b
     fe a, b, c, d, pm, pp;
     fe_sub(a, p.Y, p.X); fe_add(b, p.Y, p.X);
     fe_select(pm, q.YmX, q.YpX, neg); fe_select(pp, q.YpX, q.YmX, neg);
-    O::mul2(a, b, a, pm, b, pp);
-    O::mul2(c, d, p.T, q.T2d, p.Z, q.Z); fe_add(d, d, d);
+    O::mul(a, a, pm); O::mul(b, b, pp);
+    O::mul(c, p.T, q.T2d);
+    O::mul(d, p.Z, q.Z); fe_add(d, d, d);
     fe_sub(r.E, b, a); fe_add(r.H, b, a);
     fe nf, ng;
     fe_sub(nf, d, c); fe_add(ng, d, c);
@@ -109,7 +106,7 @@ EG_HD void ge_add_niels_p1p1(ge_p1p1 &r, const ge_ext &p, const ge_niels &q, boo
     fe a, b, c, d, pm, pp;
     fe_sub(a, p.Y, p.X); fe_add(b, p.Y, p.X);
     fe_select(pm, q.ymx, q.ypx, neg); fe_select(pp, q.ypx, q.ymx, neg);
-    O::mul2(a, b, a, pm, b, pp);
+    O::mul(a, a, pm); O::mul(b, b, pp);
     O::mul(c, p.T, q.xy2d);
     fe_add(d, p.Z, p.Z);
     fe_sub(r.E, b, a); fe_add(r.H, b, a);
@@ -304,8 +301,8 @@ static EG_HD_NOINLINE void ge_hot_dbl(ge_ext &acc, int n) {
 #pragma unroll 1
     for (int k = 0; k < n; k++) {
         ge_dbl_p1p1<EG_HOT_DBL_OPS>(t, a);
-        if (k == n - 1) ge_p1p1_to_ext<EG_HOT_DBL_PROJ_OPS>(a, t);
-        else ge_p1p1_to_proj<EG_HOT_DBL_PROJ_OPS>(a, t);
+        ge_p1p1_to_proj<EG_HOT_DBL_PROJ_OPS>(a, t);
+        if (k == n - 1) EG_HOT_DBL_PROJ_OPS::mul(a.T, t.E, t.H);
     }
     acc = a;
 }
@@ -317,8 +314,8 @@ static EG_HD_NOINLINE void ge_hot_add_cached(ge_ext &acc, const uint32_t *entry,
     ge_cached_load(q, entry);
     ge_p1p1 t;
     ge_add_cached_p1p1<EG_HOT_OPS>(t, acc, q, neg);
-    if (need_t) ge_p1p1_to_ext<EG_HOT_OPS>(acc, t);
-    else ge_p1p1_to_proj<EG_HOT_OPS>(acc, t);
+    ge_p1p1_to_proj<EG_HOT_OPS>(acc, t);
+    if (need_t) EG_HOT_OPS::mul(acc.T, t.E, t.H);
 }
 
 // acc += (neg ? -Q : Q), Q = entry `idx` of an affine Niels table (24 words per entry, 16-byte aligned)
@@ -545,8 +542,8 @@ static EG_HD_NOINLINE void ge_eval64(ge_ext &out, const uint32_t *vtab, const sc
 #pragma unroll 1
                 for (int k = 0; k < 4; k++) {
                     ge_dbl_p1p1<EG_EVAL_DBL_OPS>(t, acc);
-                    if (k == 3) ge_p1p1_to_ext<EG_EVAL_PROJ_OPS>(acc, t);
-                    else ge_p1p1_to_proj<EG_EVAL_PROJ_OPS>(acc, t);
+                    ge_p1p1_to_proj<EG_EVAL_PROJ_OPS>(acc, t);
+                    if (k == 3) fe_mul(acc.T, t.E, t.H);
                 }
             }
 #pragma unroll 1
@@ -556,8 +553,8 @@ static EG_HD_NOINLINE void ge_eval64(ge_ext &out, const uint32_t *vtab, const sc
                     ge_cached q;
                     ge_cached_load(q, vtab + (c * 8 + (d < 0 ? -d : d) - 1) * EG_VTAB_ENTRY_WORDS);
                     ge_add_cached_p1p1(t, acc, q, d < 0);
-                    if (c != C - 1 || i == 0) ge_p1p1_to_ext(acc, t);
-                    else ge_p1p1_to_proj(acc, t);                           // T is dead when doublings follow
+                    ge_p1p1_to_proj(acc, t);
+                    if (c != C - 1 || i == 0) fe_mul(acc.T, t.E, t.H);     // T is dead when doublings follow
                 }
             }
         }

@@ -88,7 +88,7 @@ static __device__ __noinline__ eg::fe fe_mul_k_call(const eg::fe a, const eg::fe
 struct fe_pair { eg::fe x, y; };
 // two independent multiplications / squarings in one call: does the extra instruction-level parallelism pay?
 static __device__ __noinline__ fe_pair fe_mul2_call(const eg::fe a0, const eg::fe b0, const eg::fe a1, const eg::fe b1) {
-    fe_pair r;
+    fe_pair r = {};
 #if defined(__CUDA_ARCH__)
     eg::fe_mul_ptx(r.x, a0, b0);
     eg::fe_mul_ptx(r.y, a1, b1);
@@ -96,7 +96,7 @@ static __device__ __noinline__ fe_pair fe_mul2_call(const eg::fe a0, const eg::f
     return r;
 }
 static __device__ __noinline__ fe_pair fe_sq2_call(const eg::fe a0, const eg::fe a1) {
-    fe_pair r;
+    fe_pair r = {};
 #if defined(__CUDA_ARCH__)
     eg::fe_sq_ptx(r.x, a0);
     eg::fe_sq_ptx(r.y, a1);
