@@ -542,27 +542,23 @@ EG_HD void prove_commit_pair(uint32_t out0[8], uint32_t out1[8], const sc &k, co
     ge_double_compress2(out0, out1, q0, q1);
 }
 
-// forged equation j (value a_j in {0, 1}) of a ring with challenge e and response s:
-// ([s]G - [e]R, [s]K - [e](B - [a]G)), encoded
-EG_HD void prove_forge_pair(uint32_t cg[8], uint32_t ck[8], const ge_ext &R, const ge_ext &B, const sc &e, const sc &s, uint32_t a,
-                            uint32_t *scratch, const uint32_t *tab_g, const uint32_t *tab_k) {
-    uint32_t *tab_r = scratch, *tab_b = scratch + EG_VTAB_WORDS;
-    ge_vtab_build<EG_VCHUNKS_SHORT>(tab_r, R);
-    ge_vtab_build<EG_VCHUNKS_SHORT>(tab_b, B);
-    sc ne, hne, hs, hea;
-    sc_neg(ne, e);
-    sc_half(hne, ne);
-    sc_half(hs, s);
+// Forged equation with admissible value [a]G of a ring over the ciphertext (R, B) = ([r]G, [v]G + [r]K), challenge e and
+// response s (ring.rs:104-116, 176-186): ([s]G - [e]R, [s]K - [e](B - [a]G)).  The prover knows r and v, so both
+// commitments are fixed-base: [s - e r]G and [s - e r]K + [e (a - v)]G -- the same group elements, hence the same
+// encodings, as the reference's vartime_double_mul_generator / vartime_multi_mul on R and B.
+EG_HD void prove_forge_fixed(uint32_t cg[8], uint32_t ck[8], const sc &r, uint64_t v, const sc &e, const sc &s, uint64_t a,
+                             const uint32_t *tab_g, const uint32_t *tab_k) {
+    sc er, t, d, u, ht, hu;
+    sc_mul(er, e, r);
+    sc_sub(t, s, er);
+    if (a >= v) d = sc_from_u64(a - v);
+    else { sc m = sc_from_u64(v - a); sc_neg(d, m); }
+    sc_mul(u, e, d);
+    sc_half(ht, t);
+    sc_half(hu, u);
     ge_ext qg, qk;
-    ge_eval64<EG_VCHUNKS_SHORT>(qg, tab_r, hne, 1, tab_g, hs, tab_g, hs);
-    if (a) {
-        sc ea;
-        sc_mul(ea, e, sc_from_u64(a));
-        sc_half(hea, ea);
-        ge_eval64<EG_VCHUNKS_SHORT>(qk, tab_b, hne, 2, tab_k, hs, tab_g, hea);
-    } else {
-        ge_eval64<EG_VCHUNKS_SHORT>(qk, tab_b, hne, 1, tab_k, hs, tab_k, hs);
-    }
+    ge_eval_fixed(qg, 1, tab_g, ht, tab_g, ht);
+    ge_eval_fixed(qk, 2, tab_k, ht, tab_g, hu);
     ge_double_compress2(cg, ck, qg, qk);
 }
 
@@ -577,22 +573,18 @@ EG_HD void prove_ring1_body(const prove_params &P, size_t item, uint32_t k, uint
     prove_draw(x, P, item, pos + 1);
     sc_half(hr, r);
     // ExtendedCiphertext::new (encryption.rs:310-327): R = [r]G, B = [v]G + [r]K
-    ge_ext qr, qb, R, B;
+    ge_ext qr, qb;
     sc hone;
     sc_half(hone, sc_from_u64(1));
     ge_eval_fixed(qr, 1, tab_g, hr, tab_g, hr);
     ge_eval_fixed(qb, v ? 2 : 1, tab_k, hr, tab_g, hone);
     uint32_t enc_ct[16];
     ge_double_compress2(enc_ct, enc_ct + 8, qr, qb);
-    ge_dbl(R, qr);
-    ge_dbl(B, qb);
     uint8_t *ct_out = P.cts + (item * P.options + k) * 64;
     store32_bytes(ct_out, enc_ct);
     store32_bytes(ct_out + 32, enc_ct + 8);
     planar_store_words(P.enc, P.n, 2 * k, 8, item, enc_ct);
     planar_store_words(P.enc, P.n, 2 * k + 1, 8, item, enc_ct + 8);
-    planar_store_point(P.pts, P.n, 2 * k, item, R);
-    planar_store_point(P.pts, P.n, 2 * k + 1, item, B);
     planar_store_words(P.sec, P.n, 2 * k, 8, item, r.v);
     planar_store_words(P.sec, P.n, 2 * k + 1, 8, item, x.v);
     // Ring::new (ring.rs:54-131): commitments of the real equation, then the forged ones above it
@@ -605,7 +597,7 @@ EG_HD void prove_ring1_body(const prove_params &P, size_t item, uint32_t k, uint
         ring_next_challenge(e1, rt, 0, cg, ck);
         prove_draw(s1, P, item, pos + 2);
         store32_bytes(P.ring + (item * (1 + 2 * (size_t)P.options) + 1 + 2 * k + 1) * 32, s1.v);
-        prove_forge_pair(cg, ck, R, B, e1, s1, 1, scratch, tab_g, tab_k);
+        prove_forge_fixed(cg, ck, r, 0, e1, s1, 1, tab_g, tab_k);
     }
     planar_store_words(P.commit, P.n, 2 * k, 8, item, cg);
     planar_store_words(P.commit, P.n, 2 * k + 1, 8, item, ck);
@@ -678,11 +670,8 @@ EG_HD void prove_ring2_body(const prove_params &P, size_t item, uint32_t k, uint
     sc s0, e1;
     prove_draw(s0, P, item, pos + before);
     store32_bytes(resp, s0.v);
-    ge_ext R, B;
-    planar_load_point(R, P.pts, P.n, 2 * k, item);
-    planar_load_point(B, P.pts, P.n, 2 * k + 1, item);
     uint32_t cg[8], ck[8], enc_ct[16];
-    prove_forge_pair(cg, ck, R, B, e0, s0, 0, scratch, tab_g, tab_k);
+    prove_forge_fixed(cg, ck, r, 1, e0, s0, 0, tab_g, tab_k);
     planar_load_words(enc_ct, P.enc, P.n, 2 * k, 8, item);
     planar_load_words(enc_ct + 8, P.enc, P.n, 2 * k + 1, 8, item);
     transcript rt;
@@ -755,8 +744,8 @@ EG_HD rprove_pos rprove_layout(const rprove_params &P, uint64_t value, uint32_t 
     return out;
 }
 
-// out = ([r]G, [v]G + [r]K) as points and encodings
-EG_HD void rprove_encrypt(ge_ext &R, ge_ext &B, uint32_t enc_ct[16], const sc &r, uint64_t v, const uint32_t *tab_g, const uint32_t *tab_k) {
+// enc_ct = encodings of ([r]G, [v]G + [r]K)
+EG_HD void rprove_encrypt(uint32_t enc_ct[16], const sc &r, uint64_t v, const uint32_t *tab_g, const uint32_t *tab_k) {
     sc hr, hv;
     sc_half(hr, r);
     sc_half(hv, sc_from_u64(v));
@@ -764,28 +753,6 @@ EG_HD void rprove_encrypt(ge_ext &R, ge_ext &B, uint32_t enc_ct[16], const sc &r
     ge_eval_fixed(qr, 1, tab_g, hr, tab_g, hr);
     ge_eval_fixed(qb, v ? 2 : 1, tab_k, hr, tab_g, hv);
     ge_double_compress2(enc_ct, enc_ct + 8, qr, qb);
-    ge_dbl(R, qr);
-    ge_dbl(B, qb);
-}
-
-// forged equation with admissible value [a]G: (cg, ck) = ([s]G - [e]R, [s]K - [e](B - [a]G)), window tables prebuilt
-EG_HD void rprove_forge(uint32_t cg[8], uint32_t ck[8], const uint32_t *tab_r, const uint32_t *tab_b, const sc &e, const sc &s, uint64_t a,
-                        const uint32_t *tab_g, const uint32_t *tab_k) {
-    sc ne, hne, hs, hea;
-    sc_neg(ne, e);
-    sc_half(hne, ne);
-    sc_half(hs, s);
-    ge_ext qg, qk;
-    ge_eval64<EG_VCHUNKS_LONG>(qg, tab_r, hne, 1, tab_g, hs, tab_g, hs);
-    if (a) {
-        sc ea;
-        sc_mul(ea, e, sc_from_u64(a));
-        sc_half(hea, ea);
-        ge_eval64<EG_VCHUNKS_LONG>(qk, tab_b, hne, 2, tab_k, hs, tab_g, hea);
-    } else {
-        ge_eval64<EG_VCHUNKS_LONG>(qk, tab_b, hne, 1, tab_k, hs, tab_k, hs);
-    }
-    ge_double_compress2(cg, ck, qg, qk);
 }
 
 // phase 0, one thread per (item, slot): slot < n_rings = ring `slot` (ciphertext + Ring::new); slot == n_rings = main ciphertext
@@ -793,11 +760,10 @@ EG_HD void rprove_ring1_body(const rprove_params &P, size_t item, uint32_t slot,
     const uint64_t value = P.values[item * P.value_stride];
     const uint32_t Rn = P.n_rings;
     uint32_t enc_ct[16];
-    ge_ext R, B;
     if (slot == Rn) {
         sc r;
         rprove_draw(r, P, item, 0);
-        rprove_encrypt(R, B, enc_ct, r, value, tab_g, tab_k);
+        rprove_encrypt(enc_ct, r, value, tab_g, tab_k);
         uint8_t *o = P.ct_out + rprove_off(P, item, P.ct_stride, P.out_inner);
         store32_bytes(o, enc_ct);
         store32_bytes(o + 32, enc_ct + 8);
@@ -820,7 +786,7 @@ EG_HD void rprove_ring1_body(const rprove_params &P, size_t item, uint32_t slot,
             sc_sub(r, r, ri);
         }
     }
-    rprove_encrypt(R, B, enc_ct, r, (uint64_t)L.vi * P.steps[k], tab_g, tab_k);
+    rprove_encrypt(enc_ct, r, (uint64_t)L.vi * P.steps[k], tab_g, tab_k);
     if (!last) {
         uint8_t *o = P.partial_out + rprove_off(P, item, P.partial_stride, P.out_inner) + 64 * (size_t)k;
         store32_bytes(o, enc_ct);
@@ -830,17 +796,12 @@ EG_HD void rprove_ring1_body(const rprove_params &P, size_t item, uint32_t slot,
     rprove_draw(x, P, item, xpos);
     planar_store_words(P.enc, P.n, 2 * k, 8, item, enc_ct);
     planar_store_words(P.enc, P.n, 2 * k + 1, 8, item, enc_ct + 8);
-    planar_store_point(P.pts, P.n, 2 * k, item, R);
-    planar_store_point(P.pts, P.n, 2 * k + 1, item, B);
     planar_store_words(P.sec, P.n, 2 * k, 8, item, r.v);
     planar_store_words(P.sec, P.n, 2 * k + 1, 8, item, x.v);
     // Ring::new (ring.rs:97-131): commitments of the real equation, then the forged equations above it
     uint32_t cg[8], ck[8];
     prove_commit_pair(cg, ck, x, tab_g, tab_k);
     if (L.vi + 1 < m) {
-        uint32_t *tab_r = scratch, *tab_b = scratch + EG_VTAB_WORDS;
-        ge_vtab_build<EG_VCHUNKS_LONG>(tab_r, R);
-        ge_vtab_build<EG_VCHUNKS_LONG>(tab_b, B);
         transcript rt;
         ring_transcript_start(rt, P.prefix, enc_ct, k);
         uint8_t *resp = P.ring_out + rprove_off(P, item, P.ring_stride, P.out_inner) + 32 * (1 + (size_t)P.starts[k]);
@@ -850,7 +811,7 @@ EG_HD void rprove_ring1_body(const rprove_params &P, size_t item, uint32_t slot,
             ring_next_challenge(e, rt, eq - 1, cg, ck);
             rprove_draw(s_, P, item, xpos + (eq - L.vi));
             store32_bytes(resp + 32 * (size_t)eq, s_.v);
-            rprove_forge(cg, ck, tab_r, tab_b, e, s_, (uint64_t)eq * P.steps[k], tab_g, tab_k);
+            prove_forge_fixed(cg, ck, r, (uint64_t)L.vi * P.steps[k], e, s_, (uint64_t)eq * P.steps[k], tab_g, tab_k);
         }
     }
     planar_store_words(P.commit, P.n, 2 * k, 8, item, cg);
@@ -884,12 +845,6 @@ EG_HD void rprove_ring2_body(const rprove_params &P, size_t item, uint32_t k, ui
     planar_load_words(x.v, P.sec, P.n, 2 * k + 1, 8, item);
     uint8_t *resp = P.ring_out + rprove_off(P, item, P.ring_stride, P.out_inner) + 32 * (1 + (size_t)P.starts[k]);
     if (L.vi > 0) {
-        ge_ext R, B;
-        planar_load_point(R, P.pts, P.n, 2 * k, item);
-        planar_load_point(B, P.pts, P.n, 2 * k + 1, item);
-        uint32_t *tab_r = scratch, *tab_b = scratch + EG_VTAB_WORDS;
-        ge_vtab_build<EG_VCHUNKS_LONG>(tab_r, R);
-        ge_vtab_build<EG_VCHUNKS_LONG>(tab_b, B);
         uint32_t enc_ct[16], cg[8], ck[8];
         planar_load_words(enc_ct, P.enc, P.n, 2 * k, 8, item);
         planar_load_words(enc_ct + 8, P.enc, P.n, 2 * k + 1, 8, item);
@@ -900,7 +855,7 @@ EG_HD void rprove_ring2_body(const rprove_params &P, size_t item, uint32_t k, ui
             sc s_;
             rprove_draw(s_, P, item, L.pos2 + eq);
             store32_bytes(resp + 32 * (size_t)eq, s_.v);
-            rprove_forge(cg, ck, tab_r, tab_b, e, s_, (uint64_t)eq * P.steps[k], tab_g, tab_k);
+            prove_forge_fixed(cg, ck, r, (uint64_t)L.vi * P.steps[k], e, s_, (uint64_t)eq * P.steps[k], tab_g, tab_k);
             ring_next_challenge(e, rt, eq, cg, ck);
         }
     }
@@ -930,8 +885,7 @@ EG_HD void encrypt_body(const encrypt_params &P, size_t item, const uint32_t *ta
     sc r;
     load32_bytes(w, b); load32_bytes(w + 8, b + 32);
     sc_from_wide_words(r, w);
-    ge_ext R, B;
-    rprove_encrypt(R, B, enc_ct, r, P.with_zero_proof ? 0 : P.values[item], tab_g, tab_k);
+    rprove_encrypt(enc_ct, r, P.with_zero_proof ? 0 : P.values[item], tab_g, tab_k);
     store32_bytes(P.cts + item * 64, enc_ct);
     store32_bytes(P.cts + item * 64 + 32, enc_ct + 8);
     if (!P.with_zero_proof) return;
