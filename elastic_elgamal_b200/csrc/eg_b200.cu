@@ -59,7 +59,8 @@ struct eg_ctx {
     size_t adm_used = 0;      // cached points in `adm` (32 words each); entries 0,1 = the [O, G] pair
     std::map<std::string, std::vector<uint64_t>> adm_cache_key;
     size_t chunk_items = 0;   // 0 = default
-    int ring_mode = 2;        // 2: k_ring (one thread per ring, chunked tables); 1: k_commit / k_ring_hash launches per equation
+    int ring_mode = 0;        // 2: k_ring (one thread per ring, chunked tables); 1: k_commit / k_ring_hash launches per equation;
+                              // 0: chosen per chunk (1 when the chunk cannot fill the persistent k_ring grid, run_ring_job)
     int ring_grid[2] = {0, 0};   // resident CTAs of the two k_ring shapes (queried once)
     int prove_grid[3] = {0, 0, 0};
     int rprove_grid[3] = {0, 0, 0};
@@ -679,7 +680,7 @@ extern "C" eg_status eg_ctx_set_chunk_items(eg_ctx *ctx, size_t items) {
 }
 
 extern "C" eg_status eg_ctx_set_ring_mode(eg_ctx *ctx, int mode) {
-    if (!ctx || (mode != 1 && mode != 2)) return EG_ERR_INVALID_ARG;
+    if (!ctx || mode < 0 || mode > 2) return EG_ERR_INVALID_ARG;
     ctx->ring_mode = mode;
     return EG_SUCCESS;
 }

@@ -303,9 +303,11 @@ eg_status eg_last_kernel_stats(const eg_ctx *ctx, int kind, uint64_t *launches, 
 eg_status eg_selftest_field(eg_ctx *ctx, size_t n, uint64_t seed, uint64_t *mismatches);
 /* Tuning knob: items processed per internal chunk (0 = default 262144).  Results do not depend on it. */
 eg_status eg_ctx_set_chunk_items(eg_ctx *ctx, size_t items);
-/* Tuning / A-B knob for RingProof verification: 2 (default) = one thread per ring with per-point chunked window tables
- * (k_ring, 64 doublings per equation); 1 = one launch per equation index (k_commit + k_ring_hash, 252 doublings).
- * Results do not depend on it. */
+/* Tuning / A-B knob for RingProof verification: 2 = one thread per ring with per-point chunked window tables (k_ring,
+ * 64 doublings per equation; the engine for large batches); 1 = one launch per equation index with one thread per
+ * equation side (k_commit + k_ring_hash, 252 doublings; lower latency for small batches); 0 (default) = chosen per
+ * chunk: 1 when the chunk has too few ring threads to fill the persistent k_ring grid (measured crossovers).  Results do not depend
+ * on it. */
 eg_status eg_ctx_set_ring_mode(eg_ctx *ctx, int mode);
 /* Raw CUDA stream handle (cudaStream_t) so callers can order their own work / time with events on it. */
 void     *eg_ctx_stream(const eg_ctx *ctx);

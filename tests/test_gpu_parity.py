@@ -19,7 +19,8 @@ def env():
     e = Engine(device=0)           # fails loudly without a GPU / without the built extension
     sk, pk = W.receiver()
     e.set_receiver(pk)
-    yield e, sk, pk
+    e.set_ring_mode(2)             # the batches below are small: pin the large-batch engine (k_ring), which the library's
+    yield e, sk, pk                # automatic choice would reserve for chunks of >= 2 waves (test_ring_mode_auto)
     e.close()
 
 
@@ -150,6 +151,35 @@ def test_ring_mode_1_still_matches(env):
         PC.check_verify_bool(e, pk, n=200, seed=5)
         PC.check_verify_choice(e, pk, options=5, n=200, single=True, frac=0.2)
         PC.check_verify_range(e, pk, 100, n=60, frac=0.2)
+    finally:
+        e.set_ring_mode(2)
+
+
+def test_ring_mode_auto(env):
+    """Default engine choice: small chunks go through the per-equation pipeline, large ones through k_ring; a batch
+    that mixes both (a full 257 638-ballot chunk + a 42 362-ballot remainder) must still give tiled verdicts and the
+    tally of the accepted ballots."""
+    e, sk, pk = env
+    e.set_ring_mode(0)
+    try:
+        PC.check_verify_bool(e, pk, n=300, seed=6)
+        PC.check_verify_choice(e, pk, options=5, n=256, single=True, frac=0.1)
+        PC.check_verify_range(e, pk, 1000, n=50, frac=0.2)
+        PC.check_verify_qv(e, pk, sk, n=12)
+        base, total = 1024, 300000
+        cts, rings, sums = O.gen_choice_batch(pk, 5, W.SEED_CHOICE, base)
+        cts, rings, sums = cts.copy(), rings.copy(), sums.copy()
+        W.tamper_choice(cts, rings, sums, random.Random(10), frac=0.02)
+        ov, _ = O.verify_choice_batch(pk, 5, True, cts, rings, sums)
+        reps = (total + base - 1) // base
+        big = [np.ascontiguousarray(np.tile(x, (reps,) + (1,) * (x.ndim - 1))[:total]) for x in (cts, rings, sums)]
+        v, t = e.verify_choice(5, *big)
+        exp = np.tile(ov, reps)[:total]
+        assert (v == exp).all()
+        table = O.DlogTable(0, total + 1)
+        choice = np.arange(total) % base % 5            # gen_choice_batch: item i votes for option i mod 5
+        for k in range(5):
+            assert table.get(O.decrypt_to_element(sk, bytes(t[k]))) == int(np.count_nonzero((exp == 0) & (choice == k)))
     finally:
         e.set_ring_mode(2)
 
