@@ -43,6 +43,18 @@ def test_verify_choice_multi(env):
     PC.check_verify_choice(env[0], env[2], options=3, n=8, single=False, frac=0.5)
 
 
+def test_per_equation_pipeline(env):
+    """Ring mode 1 (what the library picks for small chunks on the GPU) on the CPU-compiled bodies."""
+    e = env[0]
+    e.set_ring_mode(1)
+    try:
+        PC.check_verify_bool(e, env[2], n=10, seed=3)
+        PC.check_verify_choice(e, env[2], options=3, n=8, single=True, frac=0.5)
+        PC.check_verify_range(e, env[2], 21, n=6, frac=0.3)
+    finally:
+        e.set_ring_mode(0)
+
+
 def test_choice_tally_round_trip(env):
     PC.check_choice_tally_decrypts(env[0], env[2], env[1], options=3, n=7)
 
