@@ -48,7 +48,7 @@ def test_per_equation_pipeline(env):
     e = env[0]
     e.set_ring_mode(1)
     try:
-        PC.check_verify_bool(e, env[2], n=10, seed=3)
+        PC.check_verify_bool(e, env[2], n=24)
         PC.check_verify_choice(e, env[2], options=3, n=8, single=True, frac=0.5)
         PC.check_verify_range(e, env[2], 21, n=6, frac=0.3)
     finally:
