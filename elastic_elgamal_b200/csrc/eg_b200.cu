@@ -53,6 +53,8 @@ struct eg_ctx {
     // grow-only scratch
     cudaStream_t copy_stream = nullptr;     // host -> device prefetch of the next chunk
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr};
+    cudaEvent_t ev_pipe[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // pipeline_chunks: in / done / out per buffer set
+    dev_buf pp[2][5];                       // double-buffered inputs / outputs of the pipelined provers
     dev_buf in2[3];
     dev_buf pts, enc, commit, chal, flags, res[3], in[4], verdicts, partial, running, adm, misc, slots, consts, res_big, term;
     terminal_params term_plan;   // deferred encodings of the slot table uploaded last (upload_slots); n_pts == 0: none
@@ -199,6 +201,44 @@ static size_t wave_chunk(eg_ctx *ctx, size_t chunk, size_t rings_per_item, bool 
     (void)ctx; (void)rings_per_item; (void)short_rings;
 #endif
     return chunk;
+}
+
+// Double-buffered chunk pipeline for entry points whose host traffic is comparable to their kernel time (the provers:
+// 64 B of randomness in per draw, whole proofs out).  stage_in(c, b) enqueues the host -> device copies of chunk c into
+// buffer set b on `cs`; compute(c, b) enqueues its kernels on ctx->stream; stage_out(c, b) enqueues the device -> host
+// copies of its results on `cs`.  While the host is blocked in the (pageable) copies of chunks c + 1 and c - 1, the GPU
+// runs chunk c.  Hazards: set b's inputs are rewritten only after chunk c - 2's kernels (ev done), its outputs only after
+// they were copied out (ev out).
+template <class In, class Run, class Out>
+static eg_status pipeline_chunks(eg_ctx *ctx, size_t n_chunks, In stage_in, Run compute, Out stage_out) {
+    cudaStream_t cs = ctx->copy_stream;
+    cudaEvent_t *ev_in = ctx->ev_pipe, *ev_done = ctx->ev_pipe + 2, *ev_out = ctx->ev_pipe + 4;
+    if (n_chunks == 0) return EG_SUCCESS;
+    TRY(stage_in(0, 0, cs));
+    CU(cudaEventRecord(ev_in[0], cs));
+    for (size_t c = 0; c < n_chunks; c++) {
+        const int b = (int)(c & 1);
+        CU(cudaStreamWaitEvent(ctx->stream, ev_in[b], 0));
+        if (c >= 2) CU(cudaStreamWaitEvent(ctx->stream, ev_out[b], 0));
+        TRY(compute(c, b));
+        CU(cudaEventRecord(ev_done[b], ctx->stream));
+        if (c + 1 < n_chunks) {
+            if (c >= 1) CU(cudaStreamWaitEvent(cs, ev_done[b ^ 1], 0));
+            TRY(stage_in(c + 1, b ^ 1, cs));
+            CU(cudaEventRecord(ev_in[b ^ 1], cs));
+        }
+        if (c >= 1) {
+            CU(cudaStreamWaitEvent(cs, ev_done[b ^ 1], 0));
+            TRY(stage_out(c - 1, b ^ 1, cs));
+            CU(cudaEventRecord(ev_out[b ^ 1], cs));
+        }
+    }
+    const int lb = (int)((n_chunks - 1) & 1);
+    CU(cudaStreamWaitEvent(cs, ev_done[lb], 0));
+    TRY(stage_out(n_chunks - 1, lb, cs));
+    CU(cudaStreamSynchronize(cs));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return EG_SUCCESS;
 }
 
 static eg_status launch_ring(eg_ctx *ctx, ring_params &P) {
@@ -702,6 +742,7 @@ extern "C" eg_status eg_ctx_create(int device_id, eg_ctx **out) {
     for (auto &e : ctx->ev) if (cudaEventCreate(&e) != cudaSuccess) return bail(EG_ERR_CUDA);
     if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(EG_ERR_CUDA);
     for (auto &e : ctx->ev_h2d) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return bail(EG_ERR_CUDA);
+    for (auto &e : ctx->ev_pipe) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return bail(EG_ERR_CUDA);
     if (cudaMalloc(&ctx->d_table_g, EG_TABLE_ALLOC_BYTES) != cudaSuccess) return bail(EG_ERR_OUT_OF_MEMORY);
     if (cudaMalloc(&ctx->d_table_k, EG_TABLE_ALLOC_BYTES) != cudaSuccess) return bail(EG_ERR_OUT_OF_MEMORY);
     if (cudaMalloc(&ctx->d_status, 1024) != cudaSuccess) return bail(EG_ERR_OUT_OF_MEMORY);
@@ -726,6 +767,8 @@ extern "C" void eg_ctx_destroy(eg_ctx *ctx) {
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
     for (auto &e : ctx->commit_ev) if (e) cudaEventDestroy(e);
     for (auto &e : ctx->ev_h2d) if (e) cudaEventDestroy(e);
+    for (auto &e : ctx->ev_pipe) if (e) cudaEventDestroy(e);
+    for (auto &set : ctx->pp) for (dev_buf &b : set) if (b.p) cudaFree(b.p);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

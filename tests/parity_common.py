@@ -377,6 +377,20 @@ def check_identity_commitments(e, pk, options=5, n=20):
     assert got.tolist() == expected.tolist() and got[0] != 0
 
 
+def check_provers_chunked(e, pk, chunk=3, n=11):
+    """The provers run a double-buffered chunk pipeline (copies of chunks c + 1 / c - 1 overlap the kernels of chunk c):
+    with a chunk size that splits the batch into several full chunks and a remainder, every output byte must still equal
+    the oracle's."""
+    e.set_chunk_items(chunk)
+    try:
+        check_encrypt_bool(e, pk, n=n)
+        check_encrypt_choice(e, pk, options=3, n=n)
+        check_encrypt_range(e, pk, 21, n=n)
+        check_encrypt_qv(e, pk, n=max(4, n // 2))
+    finally:
+        e.set_chunk_items(0)
+
+
 def check_encrypt_multi_choice(e, pk, options=4, n=10, seed=b"\x09" * 32):
     """EncryptedChoice::new with MultiChoice (choice.rs:313-349): any 0/1 pattern, no sum proof."""
     rnd = random.Random(17)

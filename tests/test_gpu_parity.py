@@ -194,6 +194,10 @@ def test_encrypt_choice(env):
     PC.check_encrypt_multi_choice(env[0], env[2], options=6, n=100)
 
 
+def test_provers_chunk_pipeline(env):
+    PC.check_provers_chunked(env[0], env[2], chunk=37, n=300)
+
+
 def test_identity_commitments(env):
     PC.check_identity_commitments(env[0], env[2], options=5, n=200)
     PC.check_identity_commitments(env[0], env[2], options=1, n=20)

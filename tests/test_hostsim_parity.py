@@ -111,6 +111,10 @@ def test_encrypt_choice(env):
     PC.check_encrypt_multi_choice(env[0], env[2], options=3, n=4)
 
 
+def test_provers_chunk_pipeline(env):
+    PC.check_provers_chunked(env[0], env[2], chunk=3, n=8)
+
+
 def test_identity_commitments(env):
     PC.check_identity_commitments(env[0], env[2], options=3, n=12)
     PC.check_identity_commitments(env[0], env[2], options=1, n=4)
