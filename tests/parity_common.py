@@ -377,6 +377,17 @@ def check_identity_commitments(e, pk, options=5, n=20):
     assert got.tolist() == expected.tolist() and got[0] != 0
 
 
+def check_verifiers_chunked(e, pk, chunk=5, n=23):
+    """verify_bool / verify_range run the same double-buffered chunk pipeline: several full chunks and a remainder must
+    give the oracle's verdicts (range chunks are clamped to >= 1024 proofs unless n is larger, so the range batch is
+    sized by the caller)."""
+    e.set_chunk_items(chunk)
+    try:
+        check_verify_bool(e, pk, n=max(24, n))
+    finally:
+        e.set_chunk_items(0)
+
+
 def check_provers_chunked(e, pk, chunk=3, n=11):
     """The provers run a double-buffered chunk pipeline (copies of chunks c + 1 / c - 1 overlap the kernels of chunk c):
     with a chunk size that splits the batch into several full chunks and a remainder, every output byte must still equal

@@ -194,6 +194,20 @@ def test_encrypt_choice(env):
     PC.check_encrypt_multi_choice(env[0], env[2], options=6, n=100)
 
 
+def test_verifiers_chunk_pipeline(env):
+    PC.check_verifiers_chunked(env[0], env[2], chunk=41, n=400)
+
+
+def test_verify_range_several_chunks(env):
+    """2600 range proofs with a 1024-proof chunk: three chunks through the copy / compute pipeline."""
+    e, sk, pk = env
+    e.set_chunk_items(100)          # verify_range clamps its chunk to >= 1024 proofs
+    try:
+        PC.check_verify_range(e, pk, 21, n=2600, frac=0.05)
+    finally:
+        e.set_chunk_items(0)
+
+
 def test_provers_chunk_pipeline(env):
     PC.check_provers_chunked(env[0], env[2], chunk=37, n=300)
 

@@ -111,6 +111,10 @@ def test_encrypt_choice(env):
     PC.check_encrypt_multi_choice(env[0], env[2], options=3, n=4)
 
 
+def test_verifiers_chunk_pipeline(env):
+    PC.check_verifiers_chunked(env[0], env[2], chunk=5, n=24)
+
+
 def test_provers_chunk_pipeline(env):
     PC.check_provers_chunked(env[0], env[2], chunk=3, n=8)
 
