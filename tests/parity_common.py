@@ -384,6 +384,7 @@ def check_verifiers_chunked(e, pk, chunk=5, n=23):
     e.set_chunk_items(chunk)
     try:
         check_verify_bool(e, pk, n=max(24, n))
+        check_shares_and_decrypt(e, n=max(10, n // 2))
     finally:
         e.set_chunk_items(0)
 

@@ -204,6 +204,7 @@ def test_verify_range_several_chunks(env):
     e.set_chunk_items(100)          # verify_range clamps its chunk to >= 1024 proofs
     try:
         PC.check_verify_range(e, pk, 21, n=2600, frac=0.05)
+        PC.check_verify_qv(e, pk, sk, n=2300)          # verify_qv clamps to >= 1024 ballots per chunk as well
     finally:
         e.set_chunk_items(0)
 
