@@ -7,9 +7,10 @@ PKG = pathlib.Path(__file__).resolve().parent
 DEFAULT_LIB = PKG / "libeg_b200.so"
 
 SUCCESS, ERR_INVALID_ARG, ERR_INVALID_ELEMENT, ERR_IDENTITY_KEY, ERR_NO_RECEIVER, ERR_NO_DEVICE, ERR_CUDA, \
-    ERR_OUT_OF_MEMORY, ERR_LEN_MISMATCH = range(9)
+    ERR_OUT_OF_MEMORY, ERR_LEN_MISMATCH, ERR_NCCL = range(10)
 STATUS_NAMES = ["SUCCESS", "ERR_INVALID_ARG", "ERR_INVALID_ELEMENT", "ERR_IDENTITY_KEY", "ERR_NO_RECEIVER",
-                "ERR_NO_DEVICE", "ERR_CUDA", "ERR_OUT_OF_MEMORY", "ERR_LEN_MISMATCH"]
+                "ERR_NO_DEVICE", "ERR_CUDA", "ERR_OUT_OF_MEMORY", "ERR_LEN_MISMATCH", "ERR_NCCL"]
+COMM_ID_BYTES = 128
 
 V_OK, V_MALFORMED, V_CHALLENGE_MISMATCH, V_CHOICE_SUM, V_CHOICE_RANGE, V_QV_CREDIT_RANGE, V_QV_CREDIT_EQUIV, \
     V_MALFORMED_PARTICIPANT_KEYS = range(8)
@@ -42,6 +43,10 @@ P8 = C.c_void_p   # byte buffers are passed as raw addresses (host numpy arrays 
 
 PROTOTYPES = {
     "eg_ctx_create": (C.c_int32, [C.c_int, C.POINTER(C.c_void_p)]),
+    "eg_ctx_create_multi": (C.c_int32, [C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]),
+    "eg_comm_unique_id": (C.c_int32, [P8]),
+    "eg_ctx_attach_comm": (C.c_int32, [C.c_void_p, P8, C.c_int, C.c_int]),
+    "eg_ctx_comm_info": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "eg_ctx_destroy": (None, [C.c_void_p]),
     "eg_last_error": (C.c_char_p, [C.c_void_p]),
     "eg_version": (C.c_char_p, []),

@@ -68,6 +68,16 @@ struct eg_ctx {
     int rprove_grid[3] = {0, 0, 0};
     int sumsq_prove_grid = 0, encrypt_grid = 0;
     dev_buf ring_scratch;
+    // multi-GPU (comm.inc): NCCL communicator of a per-rank context (eg_ctx_attach_comm) or of a child of a multi-device
+    // context (eg_ctx_create_multi); `children` is non-empty only for the latter's parent, which owns no device state
+    void *comm = nullptr;
+    int rank = 0, world = 1;
+    dev_buf gather;
+    std::vector<eg_ctx *> children;
+    eg_ctx *parent = nullptr;
+    std::vector<uint8_t> host_tally;        // child of a multi context: its partial tally, host copy
+    uint32_t comm_bad = 0;                  // host copy of the combine kernel's flag (comm_combine / comm_check)
+    bool comm_pending = false;
 };
 
 struct eg_dlog_table {
@@ -76,6 +86,7 @@ struct eg_dlog_table {
     size_t cap;
     uint32_t *d_keys;     // cap * 8 words
     uint64_t *d_vals;     // cap
+    std::vector<eg_dlog_table *> children;   // table of a multi-device context: one replica per device
 };
 
 static eg_status fail(eg_ctx *ctx, eg_status st, const char *what, cudaError_t ce = cudaSuccess) {
@@ -657,6 +668,8 @@ static void launch_dlog_lookup(eg_ctx *ctx, const dlog_lookup_params &P) {
     ctx->launches++;
 }
 
+#include "comm.inc"
+
 #ifdef EG_HOSTSIM
 extern "C" const char *eg_version(void) { return "eg_b200 0.1.0 HOSTSIM test harness (not a product build)"; }
 #else
@@ -665,12 +678,26 @@ extern "C" const char *eg_version(void) { return "eg_b200 0.1.0 sm_100a"; }
 
 extern "C" const char *eg_last_error(const eg_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
-extern "C" uint64_t eg_kernel_launch_count(const eg_ctx *ctx) { return ctx ? ctx->launches : 0; }
+// on a multi-device context: the sum over its devices
+extern "C" uint64_t eg_kernel_launch_count(const eg_ctx *ctx) {
+    if (!ctx) return 0;
+    uint64_t total = ctx->launches;
+    for (const eg_ctx *c : ctx->children) total += c->launches;
+    return total;
+}
 
-extern "C" void *eg_ctx_stream(const eg_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+extern "C" void *eg_ctx_stream(const eg_ctx *ctx) { return ctx ? (void *)ctx_first(const_cast<eg_ctx *>(ctx))->stream : nullptr; }
 
 extern "C" eg_status eg_last_commit_stats(const eg_ctx *ctx, uint64_t *launches, uint64_t *tasks, float *ms) {
     if (!ctx) return EG_ERR_INVALID_ARG;
+    if (ctx_is_multi(ctx)) {            // launches / tasks summed over the devices, time = the slowest device
+        uint64_t l = 0, t = 0; float m = 0;
+        for (const eg_ctx *c : ctx->children) { l += c->call_commit_launches; t += c->call_commit_tasks; m = std::max(m, c->timings[2]); }
+        if (launches) *launches = l;
+        if (tasks) *tasks = t;
+        if (ms) *ms = m;
+        return EG_SUCCESS;
+    }
     if (launches) *launches = ctx->call_commit_launches;
     if (tasks) *tasks = ctx->call_commit_tasks;
     if (ms) *ms = ctx->timings[2];
@@ -680,6 +707,14 @@ extern "C" eg_status eg_last_commit_stats(const eg_ctx *ctx, uint64_t *launches,
 // kind 0: k_commit launches of the last call, kind 1: k_ring launches (tasks = equation sides)
 extern "C" eg_status eg_last_kernel_stats(const eg_ctx *ctx, int kind, uint64_t *launches, uint64_t *tasks, float *ms) {
     if (!ctx || kind < 0 || kind > 1) return EG_ERR_INVALID_ARG;
+    if (ctx_is_multi(ctx)) {
+        uint64_t l = 0, t = 0; float m = 0;
+        for (const eg_ctx *c : ctx->children) { l += c->kind_launches[kind]; t += c->kind_tasks[kind]; m = std::max(m, c->kind_ms[kind]); }
+        if (launches) *launches = l;
+        if (tasks) *tasks = t;
+        if (ms) *ms = m;
+        return EG_SUCCESS;
+    }
     if (launches) *launches = ctx->kind_launches[kind];
     if (tasks) *tasks = ctx->kind_tasks[kind];
     if (ms) *ms = ctx->kind_ms[kind];
@@ -689,12 +724,24 @@ extern "C" eg_status eg_last_kernel_stats(const eg_ctx *ctx, int kind, uint64_t 
 extern "C" eg_status eg_last_timings(const eg_ctx *ctx, float out_ms[5]) {
     if (!ctx || !out_ms) return EG_ERR_INVALID_ARG;
     for (int i = 0; i < 5; i++) out_ms[i] = ctx->timings[i];
+    for (const eg_ctx *c : ctx->children)
+        for (int i = 0; i < 5; i++) out_ms[i] = std::max(out_ms[i], c->timings[i]);
     return EG_SUCCESS;
 }
 
 
 extern "C" eg_status eg_selftest_field(eg_ctx *ctx, size_t n, uint64_t seed, uint64_t *mismatches) {
     if (!ctx || !mismatches) return EG_ERR_INVALID_ARG;
+    if (ctx_is_multi(ctx)) {
+        *mismatches = 0;
+        for (eg_ctx *c : ctx->children) {
+            uint64_t m = 0;
+            eg_status st = eg_selftest_field(c, n, seed, &m);
+            if (st != EG_SUCCESS) { ctx->err = c->err; return st; }
+            *mismatches += m;
+        }
+        return EG_SUCCESS;
+    }
     CU(cudaSetDevice(ctx->device));
     *mismatches = 0;
 #ifndef EG_HOSTSIM
@@ -716,12 +763,14 @@ extern "C" eg_status eg_selftest_field(eg_ctx *ctx, size_t n, uint64_t seed, uin
 extern "C" eg_status eg_ctx_set_chunk_items(eg_ctx *ctx, size_t items) {
     if (!ctx) return EG_ERR_INVALID_ARG;
     ctx->chunk_items = items;
+    for (eg_ctx *c : ctx->children) c->chunk_items = items;
     return EG_SUCCESS;
 }
 
 extern "C" eg_status eg_ctx_set_ring_mode(eg_ctx *ctx, int mode) {
     if (!ctx || mode < 0 || mode > 2) return EG_ERR_INVALID_ARG;
     ctx->ring_mode = mode;
+    for (eg_ctx *c : ctx->children) c->ring_mode = mode;
     return EG_SUCCESS;
 }
 
@@ -754,11 +803,24 @@ extern "C" eg_status eg_ctx_create(int device_id, eg_ctx **out) {
 
 extern "C" void eg_ctx_destroy(eg_ctx *ctx) {
     if (!ctx) return;
+    if (ctx_is_multi(ctx) || (!ctx->stream && !ctx->d_status)) {       // the parent of a multi-device context owns no device state
+        for (eg_ctx *c : ctx->children) eg_ctx_destroy(c);
+        delete ctx;
+        return;
+    }
     cudaSetDevice(ctx->device);
+#ifndef EG_HOSTSIM
+    if (ctx->comm) {
+        cudaStreamSynchronize(ctx->stream);
+        nccl_api *api = nccl_load();
+        if (api) api->CommDestroy((ncclComm_t)ctx->comm);
+        ctx->comm = nullptr;
+    }
+#endif
     dev_buf *bufs[] = {&ctx->pts, &ctx->enc, &ctx->commit, &ctx->chal, &ctx->flags, &ctx->res[0], &ctx->res[1], &ctx->res[2],
                        &ctx->in[0], &ctx->in[1], &ctx->in[2], &ctx->in[3], &ctx->verdicts, &ctx->partial, &ctx->running,
                        &ctx->adm, &ctx->misc, &ctx->slots, &ctx->consts, &ctx->res_big, &ctx->ring_scratch,
-                       &ctx->in2[0], &ctx->in2[1], &ctx->in2[2], &ctx->term};
+                       &ctx->in2[0], &ctx->in2[1], &ctx->in2[2], &ctx->term, &ctx->gather};
     for (dev_buf *b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->d_table_g) cudaFree(ctx->d_table_g);
     if (ctx->d_table_k) cudaFree(ctx->d_table_k);
@@ -776,6 +838,16 @@ extern "C" void eg_ctx_destroy(eg_ctx *ctx) {
 
 extern "C" eg_status eg_ctx_set_receiver(eg_ctx *ctx, const uint8_t key[32]) {
     if (!ctx || !key) return EG_ERR_INVALID_ARG;
+    if (ctx_is_multi(ctx)) {
+        ctx->has_receiver = false;
+        for (eg_ctx *c : ctx->children) {
+            eg_status st = eg_ctx_set_receiver(c, key);
+            if (st != EG_SUCCESS) { ctx->err = c->err; return st; }
+        }
+        memcpy(ctx->key, key, 32);
+        ctx->has_receiver = true;
+        return EG_SUCCESS;
+    }
     CU(cudaSetDevice(ctx->device));
     uint32_t *d_key = ctx->d_status + 8;
     CU(cudaMemcpyAsync(d_key, key, 32, cudaMemcpyHostToDevice, ctx->stream));
@@ -795,6 +867,16 @@ extern "C" eg_status eg_ctx_set_receiver(eg_ctx *ctx, const uint8_t key[32]) {
 // Bulletproofs base of tests/snapshots.rs:253-257.  Gets the same wide fixed-base table as G and K.
 extern "C" eg_status eg_ctx_set_blinding_base(eg_ctx *ctx, const uint8_t base[32]) {
     if (!ctx || !base) return EG_ERR_INVALID_ARG;
+    if (ctx_is_multi(ctx)) {
+        ctx->has_blinding_base = false;
+        for (eg_ctx *c : ctx->children) {
+            eg_status st = eg_ctx_set_blinding_base(c, base);
+            if (st != EG_SUCCESS) { ctx->err = c->err; return st; }
+        }
+        memcpy(ctx->blinding_base, base, 32);
+        ctx->has_blinding_base = true;
+        return EG_SUCCESS;
+    }
     CU(cudaSetDevice(ctx->device));
     if (!ctx->d_table_h) {
         cudaError_t ce = cudaMalloc(&ctx->d_table_h, EG_TABLE_ALLOC_BYTES);
@@ -830,3 +912,5 @@ extern "C" eg_status eg_ctx_set_blinding_base(eg_ctx *ctx, const uint8_t base[32
 #include "api_sigma.inc"
 
 #include "api_decrypt.inc"
+
+#include "api_multi.inc"

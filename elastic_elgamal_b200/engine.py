@@ -24,16 +24,41 @@ def _addr(a):
 
 
 class Engine:
-    """Owns an eg_ctx on `device`.  `lib_path` exists for the test harness; the default is the in-tree CUDA library."""
+    """Owns an eg_ctx on `device`, or -- with `devices=[...]` -- a multi-device context (eg_ctx_create_multi) whose batch
+    calls shard across those GPUs inside the library.  `lib_path` exists for the test harness; the default is the in-tree
+    CUDA library."""
 
-    def __init__(self, device=0, lib_path=None):
+    def __init__(self, device=0, lib_path=None, devices=None):
         self.lib = _ffi.load(lib_path)
         h = C.c_void_p()
-        st = self.lib.eg_ctx_create(device, C.byref(h))
+        if devices is not None:
+            ids = (C.c_int * len(devices))(*devices)
+            st = self.lib.eg_ctx_create_multi(ids, len(devices), C.byref(h))
+            device = devices[0] if devices else 0
+        else:
+            st = self.lib.eg_ctx_create(device, C.byref(h))
         if st != _ffi.SUCCESS:
-            raise EngineError(st, "eg_ctx_create failed (no CUDA device? the engine has no CPU fallback)")
+            raise EngineError(st, "eg_ctx_create failed (no CUDA device / NCCL? the engine has no CPU fallback)")
         self.h = h
         self.device = device
+
+    # ---- multi-GPU: one process per GPU (torchrun style); the library owns the NCCL communicator
+    def comm_unique_id(self):
+        """128-byte NCCL unique id (rank 0 calls this; the host distributes it to the other ranks)."""
+        buf = np.zeros(_ffi.COMM_ID_BYTES, np.uint8)
+        st = self.lib.eg_comm_unique_id(_addr(buf))
+        if st != _ffi.SUCCESS:
+            raise EngineError(st, "eg_comm_unique_id failed (libnccl.so.2 not loadable?)")
+        return buf
+
+    def attach_comm(self, unique_id, rank, world):
+        unique_id = _u8(unique_id, (_ffi.COMM_ID_BYTES,))
+        self._check(self.lib.eg_ctx_attach_comm(self.h, _addr(unique_id), rank, world))
+
+    def comm_info(self):
+        r, w, d = C.c_int(0), C.c_int(0), C.c_int(0)
+        self._check(self.lib.eg_ctx_comm_info(self.h, C.byref(r), C.byref(w), C.byref(d)))
+        return {"rank": r.value, "world": w.value, "devices": d.value}
 
     def close(self):
         if getattr(self, "h", None):

@@ -44,8 +44,9 @@ enum {
     EG_ERR_NO_DEVICE = 5,         /* no usable CUDA device (there is no CPU fallback) */
     EG_ERR_CUDA = 6,              /* CUDA runtime failure; see eg_last_error */
     EG_ERR_OUT_OF_MEMORY = 7,
-    EG_ERR_LEN_MISMATCH = 8       /* VerificationError::LenMismatch / OptionsLenMismatch (src/proofs/mod.rs:70-78,
+    EG_ERR_LEN_MISMATCH = 8,      /* VerificationError::LenMismatch / OptionsLenMismatch (src/proofs/mod.rs:70-78,
                                      src/app/choice.rs:149-158): in a fixed-stride batch this is an API-level error */
+    EG_ERR_NCCL = 9               /* NCCL could not be loaded / a collective failed; see eg_last_error */
 };
 
 /* Per-item verdicts (uint8_t).  0 = Ok(..); the rest mirror the reference's error enums. */
@@ -73,6 +74,29 @@ void      eg_ctx_destroy(eg_ctx *ctx);
 const char *eg_last_error(const eg_ctx *ctx);
 /* Library build identification: "eg_b200 <version> sm_100a". */
 const char *eg_version(void);
+
+/* ---- multi-GPU ------------------------------------------------------------------
+ * The loop being replaced (examples/voting.rs:188-204) is a map over independent ballots with a commutative fold, so a
+ * batch shards across the GPUs of one box; the only exchange is the per-GPU partial tally (options x 64 B), which the
+ * library combines itself: ONE ncclAllGather over NVLink followed by a point-addition kernel (NCCL has no
+ * elliptic-curve reduction operator).  NCCL is bound at run time (libnccl.so.2), only when one of these is called.
+ *
+ * (1) One process, several devices.  The context owns one child context per device (own streams, tables, scratch) and a
+ *     communicator from ncclCommInitAll.  Every host-pointer batch entry point then shards the batch contiguously
+ *     across the devices (one host thread each); verdicts come back in input order; `tally` outputs are the totals over
+ *     all devices.  `_dev` entry points need a single-device context (EG_ERR_INVALID_ARG); helper entry points (group
+ *     helpers, wire codec, key-set validation, proofs of possession, commitment equivalence) run on the first device. */
+eg_status eg_ctx_create_multi(const int *device_ids, int n_dev, eg_ctx **out);
+/* (2) One process per GPU (torchrun / MPI style).  Rank 0 obtains a unique id, the host distributes its 128 bytes over
+ *     any channel it already has, every rank attaches it to its single-device context (ncclCommInitRank; collective).
+ *     From then on the `tally` output of eg_verify_choice_batch[_dev] and eg_verify_qv_batch is the total over all ranks
+ *     (identical bytes on every rank) and those calls are collective: every rank calls them, with its own slice of the
+ *     batch (n may differ, 0 included) and the same options / `tally != NULL`.  Verdicts stay local to the rank. */
+#define EG_COMM_ID_BYTES 128
+eg_status eg_comm_unique_id(uint8_t id[EG_COMM_ID_BYTES]);
+eg_status eg_ctx_attach_comm(eg_ctx *ctx, const uint8_t id[EG_COMM_ID_BYTES], int rank, int world);
+/* rank / world of the attached communicator (0 / 1 without one); devices = children of a multi-device context (else 1) */
+eg_status eg_ctx_comm_info(const eg_ctx *ctx, int *rank, int *world, int *devices);
 
 /* PublicKey::<Ristretto>::from_bytes (src/keys/mod.rs:161-176): validates K (decodable, not the identity),
  * keeps its bytes for the transcripts (PublicKey::as_bytes :188-190) and builds K's fixed-base table. */
