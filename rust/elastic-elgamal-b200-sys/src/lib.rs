@@ -25,6 +25,10 @@ pub const EG_ERR_NO_DEVICE: eg_status = 5;
 pub const EG_ERR_CUDA: eg_status = 6;
 pub const EG_ERR_OUT_OF_MEMORY: eg_status = 7;
 pub const EG_ERR_LEN_MISMATCH: eg_status = 8;
+pub const EG_ERR_NCCL: eg_status = 9;
+
+/// Size of the NCCL unique id exchanged by `eg_comm_unique_id` / `eg_ctx_attach_comm`.
+pub const EG_COMM_ID_BYTES: usize = 128;
 
 pub const EG_V_OK: u8 = 0;
 pub const EG_V_MALFORMED: u8 = 1;
@@ -65,6 +69,10 @@ pub struct eg_keyset {
 }
 
 extern "C" {
+    pub fn eg_ctx_create_multi(device_ids: *const c_int, n_dev: c_int, out: *mut *mut eg_ctx) -> eg_status;
+    pub fn eg_comm_unique_id(id: *mut u8) -> eg_status;
+    pub fn eg_ctx_attach_comm(ctx: *mut eg_ctx, id: *const u8, rank: c_int, world: c_int) -> eg_status;
+    pub fn eg_ctx_comm_info(ctx: *const eg_ctx, rank: *mut c_int, world: *mut c_int, devices: *mut c_int) -> eg_status;
     pub fn eg_ctx_create(device_id: c_int, out: *mut *mut eg_ctx) -> eg_status;
     pub fn eg_ctx_destroy(ctx: *mut eg_ctx);
     pub fn eg_last_error(ctx: *const eg_ctx) -> *const c_char;
