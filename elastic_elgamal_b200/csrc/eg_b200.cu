@@ -28,6 +28,8 @@ using namespace eg;
 
 // =================================================================== context
 
+#define EG_STAT_KINDS 3          // timed kernel kinds (eg_last_kernel_stats): 0 = k_commit, 1 = k_ring, 2 = k_msm
+
 struct dev_buf {
     void *p = nullptr;
     size_t cap = 0;
@@ -45,11 +47,11 @@ struct eg_ctx {
     float timings[5] = {0, 0, 0, 0, 0};
     cudaEvent_t ev[8];
     std::vector<cudaEvent_t> commit_ev;     // pairs (start, stop) around every k_commit / k_ring launch of the current call
-    std::vector<uint8_t> commit_ev_kind;    // per pair: 0 = k_commit, 1 = k_ring
+    std::vector<uint8_t> commit_ev_kind;    // per pair: 0 = k_commit, 1 = k_ring, 2 = k_msm
     size_t commit_ev_used = 0;
     uint64_t call_commit_tasks = 0, call_commit_launches = 0;
-    uint64_t kind_tasks[2] = {0, 0}, kind_launches[2] = {0, 0};   // per kind, current call
-    float kind_ms[2] = {0, 0};
+    uint64_t kind_tasks[EG_STAT_KINDS] = {0, 0, 0}, kind_launches[EG_STAT_KINDS] = {0, 0, 0};   // per kind, current call
+    float kind_ms[EG_STAT_KINDS] = {0, 0, 0};
     // grow-only scratch
     cudaStream_t copy_stream = nullptr;     // host -> device prefetch of the next chunk
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr};
@@ -121,6 +123,43 @@ static eg_status ensure(eg_ctx *ctx, dev_buf &b, size_t bytes) {
 
 static inline unsigned grid_for(size_t threads, unsigned block) { return (unsigned)((threads + block - 1) / block); }
 
+// Per-call statistics of the equation-evaluation kernels: one CUDA event pair around every launch of kind `kind`
+// (EG_STAT_KINDS), `tasks` = what the launch evaluates (equation sides for k_commit / k_ring, multi-scalar sums for k_msm).
+static void reset_call_stats(eg_ctx *ctx) {
+    ctx->commit_ev_used = 0;
+    ctx->call_commit_tasks = 0;
+    ctx->call_commit_launches = 0;
+    for (int q = 0; q < EG_STAT_KINDS; q++) { ctx->kind_tasks[q] = 0; ctx->kind_launches[q] = 0; ctx->kind_ms[q] = 0; }
+    for (float &t : ctx->timings) t = 0;
+}
+
+// After a failure inside a chunk loop: copies of earlier chunks may still be in flight to / from the caller's buffers and
+// the context's staging; drain both streams (ignoring their status) so that the caller may free its buffers and the next
+// call on the context starts clean.
+static eg_status drain_on_error(eg_ctx *ctx, eg_status st) {
+    if (st != EG_SUCCESS) {
+        if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+        if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+        cudaGetLastError();
+    }
+    return st;
+}
+
+static cudaEvent_t stat_begin(eg_ctx *ctx, int kind, size_t tasks) {
+    if (ctx->commit_ev_used + 2 > ctx->commit_ev.size()) {
+        cudaEvent_t a = nullptr, b = nullptr;
+        cudaEventCreate(&a); cudaEventCreate(&b);
+        ctx->commit_ev.push_back(a); ctx->commit_ev.push_back(b);
+    }
+    cudaEvent_t e_start = ctx->commit_ev[ctx->commit_ev_used], e_stop = ctx->commit_ev[ctx->commit_ev_used + 1];
+    if (ctx->commit_ev_kind.size() < ctx->commit_ev.size() / 2) ctx->commit_ev_kind.resize(ctx->commit_ev.size() / 2);
+    ctx->commit_ev_kind[ctx->commit_ev_used / 2] = (uint8_t)kind;
+    ctx->kind_tasks[kind] += tasks; ctx->kind_launches[kind]++;
+    ctx->commit_ev_used += 2;
+    cudaEventRecord(e_start, ctx->stream);
+    return e_stop;
+}
+
 // ------------------------------------------------------------------- launchers (the only kernel start sites)
 
 #ifdef EG_HOSTSIM
@@ -148,17 +187,7 @@ static void launch_scalars(eg_ctx *ctx, const scalars_params &P) {
 
 static void launch_commit(eg_ctx *ctx, const commit_params &P) {
     size_t total = P.n * (size_t)P.n_slots;
-    if (ctx->commit_ev_used + 2 > ctx->commit_ev.size()) {
-        cudaEvent_t a = nullptr, b = nullptr;
-        cudaEventCreate(&a); cudaEventCreate(&b);
-        ctx->commit_ev.push_back(a); ctx->commit_ev.push_back(b);
-    }
-    cudaEvent_t e_start = ctx->commit_ev[ctx->commit_ev_used], e_stop = ctx->commit_ev[ctx->commit_ev_used + 1];
-    if (ctx->commit_ev_kind.size() < ctx->commit_ev.size() / 2) ctx->commit_ev_kind.resize(ctx->commit_ev.size() / 2);
-    ctx->commit_ev_kind[ctx->commit_ev_used / 2] = 0;
-    ctx->kind_tasks[0] += total; ctx->kind_launches[0]++;
-    ctx->commit_ev_used += 2;
-    cudaEventRecord(e_start, ctx->stream);
+    cudaEvent_t e_stop = stat_begin(ctx, 0, total);
 #ifdef EG_HOSTSIM
     EG_FOR_HOST(total, commit_body(P, tid % P.n, (int)(tid / P.n), P.table_g, P.table_k))
 #else
@@ -221,7 +250,7 @@ static size_t wave_chunk(eg_ctx *ctx, size_t chunk, size_t rings_per_item, bool 
 // runs chunk c.  Hazards: set b's inputs are rewritten only after chunk c - 2's kernels (ev done), its outputs only after
 // they were copied out (ev out).
 template <class In, class Run, class Out>
-static eg_status pipeline_chunks(eg_ctx *ctx, size_t n_chunks, In stage_in, Run compute, Out stage_out) {
+static eg_status pipeline_chunks_impl(eg_ctx *ctx, size_t n_chunks, In stage_in, Run compute, Out stage_out) {
     cudaStream_t cs = ctx->copy_stream;
     cudaEvent_t *ev_in = ctx->ev_pipe, *ev_done = ctx->ev_pipe + 2, *ev_out = ctx->ev_pipe + 4;
     if (n_chunks == 0) return EG_SUCCESS;
@@ -252,27 +281,22 @@ static eg_status pipeline_chunks(eg_ctx *ctx, size_t n_chunks, In stage_in, Run 
     return EG_SUCCESS;
 }
 
+template <class In, class Run, class Out>
+static eg_status pipeline_chunks(eg_ctx *ctx, size_t n_chunks, In stage_in, Run compute, Out stage_out) {
+    return drain_on_error(ctx, pipeline_chunks_impl(ctx, n_chunks, stage_in, compute, stage_out));
+}
+
 static eg_status launch_ring(eg_ctx *ctx, ring_params &P) {
     size_t sides = 0;
     for (uint32_t r = 0; r < P.n_rings; r++) sides += 2 * (size_t)P.sizes[r];
     sides *= P.n;
-    if (ctx->commit_ev_used + 2 > ctx->commit_ev.size()) {
-        cudaEvent_t a = nullptr, b = nullptr;
-        cudaEventCreate(&a); cudaEventCreate(&b);
-        ctx->commit_ev.push_back(a); ctx->commit_ev.push_back(b);
-    }
-    cudaEvent_t e_start = ctx->commit_ev[ctx->commit_ev_used], e_stop = ctx->commit_ev[ctx->commit_ev_used + 1];
-    if (ctx->commit_ev_kind.size() < ctx->commit_ev.size() / 2) ctx->commit_ev_kind.resize(ctx->commit_ev.size() / 2);
-    ctx->commit_ev_kind[ctx->commit_ev_used / 2] = 1;
-    ctx->kind_tasks[1] += sides; ctx->kind_launches[1]++;
-    ctx->commit_ev_used += 2;
     const size_t total = P.n * (size_t)P.n_rings;
     bool short_rings = true;                // rings of <= 2 equations: 4-chunk tables, one CTA of 512 threads per SM
     for (uint32_t r = 0; r < P.n_rings; r++) short_rings = short_rings && P.sizes[r] <= 2;
 #ifdef EG_HOSTSIM
     TRY(ensure(ctx, ctx->ring_scratch, 2 * EG_VTAB_WORDS * 4));
     P.scratch = (uint32_t *)ctx->ring_scratch.p;
-    cudaEventRecord(e_start, ctx->stream);
+    cudaEvent_t e_stop = stat_begin(ctx, 1, sides);
     if (short_rings) { EG_FOR_HOST(total, ring_body<EG_VCHUNKS_SHORT>(P, tid % P.n, (uint32_t)(tid / P.n), P.scratch, P.table_g, P.table_k)) }
     else { EG_FOR_HOST(total, ring_body<EG_VCHUNKS_LONG>(P, tid % P.n, (uint32_t)(tid / P.n), P.scratch, P.table_g, P.table_k)) }
 #else
@@ -284,7 +308,7 @@ static eg_status launch_ring(eg_ctx *ctx, ring_params &P) {
     const unsigned grid = (unsigned)std::min<size_t>(resident, (total + threads - 1) / threads);
     TRY(ensure(ctx, ctx->ring_scratch, resident * threads * 2 * EG_VTAB_WORDS * 4));
     P.scratch = (uint32_t *)ctx->ring_scratch.p;
-    cudaEventRecord(e_start, ctx->stream);
+    cudaEvent_t e_stop = stat_begin(ctx, 1, sides);
     if (shape) k_ring<EG_RING2_THREADS, EG_RING2_MINBLOCKS, EG_VCHUNKS_SHORT><<<grid, threads, smem, ctx->stream>>>(P);
     else k_ring<EG_RING_THREADS, EG_RING_MINBLOCKS, EG_VCHUNKS_LONG><<<grid, threads, smem, ctx->stream>>>(P);
 #endif
@@ -606,11 +630,13 @@ static eg_status launch_msm(eg_ctx *ctx, const msm_params &P0) {
         P.term_pts = (uint32_t *)ctx->term.p;
     }
     size_t total = P.n * (size_t)P.n_slots;
+    cudaEvent_t e_stop = stat_begin(ctx, 2, total);
 #ifdef EG_HOSTSIM
     EG_FOR_HOST(total, msm_body(P, tid % P.n, (int)(tid / P.n), P.table_g, P.table_k, P.table_h))
 #else
     k_msm<<<grid_for(total, 128), 128, 0, ctx->stream>>>(P);
 #endif
+    cudaEventRecord(e_stop, ctx->stream);
     ctx->launches++;
     if (n_term) {
         terminal_params tp = ctx->term_plan;
@@ -704,9 +730,9 @@ extern "C" eg_status eg_last_commit_stats(const eg_ctx *ctx, uint64_t *launches,
     return EG_SUCCESS;
 }
 
-// kind 0: k_commit launches of the last call, kind 1: k_ring launches (tasks = equation sides)
+// kind 0: k_commit launches of the last call, kind 1: k_ring launches (tasks = equation sides), kind 2: k_msm (tasks = sums)
 extern "C" eg_status eg_last_kernel_stats(const eg_ctx *ctx, int kind, uint64_t *launches, uint64_t *tasks, float *ms) {
-    if (!ctx || kind < 0 || kind > 1) return EG_ERR_INVALID_ARG;
+    if (!ctx || kind < 0 || kind >= EG_STAT_KINDS) return EG_ERR_INVALID_ARG;
     if (ctx_is_multi(ctx)) {
         uint64_t l = 0, t = 0; float m = 0;
         for (const eg_ctx *c : ctx->children) { l += c->kind_launches[kind]; t += c->kind_tasks[kind]; m = std::max(m, c->kind_ms[kind]); }

@@ -206,7 +206,9 @@ typedef struct {
 } eg_keyset;
 
 /* PublicKeySet::verify_share (src/sharing/key_set.rs:209-228) for n_tallies ciphertexts x n_shares candidate shares
- * each; share j of every tally comes from participant `indexes[j]`. */
+ * each; share j of every tally comes from participant `indexes[j]`.  At most 8 shares per call (EG_ERR_INVALID_ARG
+ * beyond; call again with the next group of participants).  Participant keys are validated like PublicKey::from_bytes
+ * (src/keys/mod.rs:161-176): undecodable or identity -> EG_ERR_INVALID_ELEMENT. */
 eg_status eg_verify_shares_batch(eg_ctx *ctx, const eg_keyset *keyset, size_t n_tallies, uint32_t n_shares,
                                  const uint32_t *indexes /* n_shares */, const uint8_t *cts /* n_tallies*64 */,
                                  const uint8_t *shares /* n_tallies*n_shares*32 */,
@@ -305,6 +307,14 @@ eg_status eg_verify_choice_batch_dev(eg_ctx *ctx, size_t n, uint32_t options, in
 eg_status eg_verify_range_batch_dev(eg_ctx *ctx, const eg_range *range, const char *transcript_label, size_t n,
                                     const uint8_t *d_cts, const uint8_t *d_partial_cts, const uint8_t *d_ring_proofs,
                                     uint8_t *d_verdicts);
+/* QuadraticVotingBallot::verify, PublicKeySet::verify_share and combine_shares + decrypt on device buffers */
+eg_status eg_verify_qv_batch_dev(eg_ctx *ctx, const eg_qv_params *params, size_t n, const uint8_t *d_ballots, uint8_t *d_verdicts,
+                                 uint8_t *d_tally);
+eg_status eg_verify_shares_batch_dev(eg_ctx *ctx, const eg_keyset *keyset, size_t n_tallies, uint32_t n_shares, const uint32_t *indexes,
+                                     const uint8_t *d_cts, const uint8_t *d_shares, const uint8_t *d_proofs, uint8_t *d_verdicts);
+eg_status eg_combine_decrypt_batch_dev(eg_ctx *ctx, uint32_t threshold, const uint32_t *indexes, size_t n_tallies, uint32_t share_stride,
+                                       const uint8_t *d_cts, const uint8_t *d_shares, const eg_dlog_table *table, uint64_t *d_values,
+                                       uint8_t *d_found);
 /* eg_ciphertexts_sum on device buffers, asynchronous on the context's stream: the local combine after the all_gather
  * of per-GPU partial tallies.  *d_bad_flag (optional, device) becomes non-zero when a part does not decode. */
 eg_status eg_ciphertexts_sum_dev(eg_ctx *ctx, size_t n_parts, size_t n_cts, const uint8_t *d_parts, uint8_t *d_out,
@@ -320,7 +330,8 @@ eg_status eg_last_timings(const eg_ctx *ctx, float out_ms[5]);
 /* The equation-evaluation kernels (k_ring + k_commit) in the last batch call: number of launches, number of
  * verification-equation sides evaluated, summed device time of those launches (one CUDA event pair per launch). */
 eg_status eg_last_commit_stats(const eg_ctx *ctx, uint64_t *launches, uint64_t *tasks, float *ms);
-/* The same split by kernel: kind 0 = k_commit (single-use equation sides), kind 1 = k_ring (one thread per ring). */
+/* The same split by kernel: kind 0 = k_commit (single-use equation sides), kind 1 = k_ring (one thread per ring),
+ * kind 2 = k_msm (general multi-scalar sums: share proofs, sum-of-squares, Lagrange recombination; tasks = sums). */
 eg_status eg_last_kernel_stats(const eg_ctx *ctx, int kind, uint64_t *launches, uint64_t *tasks, float *ms);
 /* On-device self-test of the tuned GF(2^255-19) multiply / square / add / sub against the portable formulation on
  * n pseudo-random and edge-case operands; *mismatches must come back 0. */
