@@ -302,3 +302,57 @@ def test_fuzz_differential(env, seed):
 @pytest.mark.parametrize("shares,threshold", [(5, 3), (10, 7), (4, 4), (3, 1), (6, 2), (40, 16), (64, 1)])
 def test_keysets_validate(env, shares, threshold):
     PC.check_keysets_validate(env[0], n_sets=40, shares=shares, threshold=threshold)
+
+
+def test_device_pointer_forms_match_host_forms(env):
+    """eg_*_batch_dev (inputs already in HBM) give the same bytes as the host-pointer forms: QV + tally, decryption shares,
+    combine + decrypt (range / bool / choice are exercised by bench.py every round)."""
+    import ctypes as C
+
+    import torch
+    e, sk, pk = env
+    dev = torch.device("cuda", 0)
+
+    def up(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    # QuadraticVotingBallot::verify
+    p, ep = O.qv_params(5, 20), e.qv_params(5, 20)
+    n = 40
+    votes = np.array([PC.QV_VOTES[i % 4] for i in range(n)], np.uint64)
+    ballots = O.gen_qv_batch(pk, p, W.SEED_QV, votes).copy()
+    ballots[3, -1] = 0xff
+    ballots[5, 32:64] = np.frombuffer(O.point_add(bytes(ballots[5, 32:64]), W.G_ENC), np.uint8)
+    hv, ht = e.verify_qv(ep, ballots)
+    d_b, d_v, d_t = up(ballots), torch.empty(n, dtype=torch.uint8, device=dev), torch.empty((5, 64), dtype=torch.uint8, device=dev)
+    e._check(e.lib.eg_verify_qv_batch_dev(e.h, C.byref(ep), n, d_b.data_ptr(), d_v.data_ptr(), d_t.data_ptr()))
+    assert (d_v.cpu().numpy() == hv).all() and (d_t.cpu().numpy() == ht).all()
+    ov, ot = O.verify_qv_batch(pk, p, ballots)
+    assert (hv == ov).all() and (ht == ot).all()
+    # verify_share + combine_shares + decrypt
+    rng = O.rng_from_seed(bytes([9] * 32))
+    ks, secrets = O.dealer_new(5, 3, rng)
+    eks = PC.as_engine_keyset(ks)
+    used, n, hi = (0, 2, 4), 50, 128
+    rnd = random.Random(11)
+    values = [rnd.randrange(hi + 10) for _ in range(n)]
+    cts = [O.encrypt(bytes(ks.shared_key), v, rng) for v in values]
+    rows = [[O.decrypt_share(ks, i, secrets[i], ct, rng) for i in used] for ct in cts]
+    cts_a = np.frombuffer(b"".join(cts), np.uint8).reshape(n, 64).copy()
+    sh_a = np.frombuffer(b"".join(b"".join(r[0] for r in row) for row in rows), np.uint8).reshape(n, 3, 32).copy()
+    pr_a = np.frombuffer(b"".join(b"".join(r[1] for r in row) for row in rows), np.uint8).reshape(n, 3, 64).copy()
+    pr_a[1, 0] = pr_a[2, 0]
+    sh_a[4, 2] = np.frombuffer(W.BAD_POINT, np.uint8)
+    hv = e.verify_shares(eks, list(used), cts_a, sh_a, pr_a)
+    table = e.dlog_table(0, hi)
+    hvals, hfound = e.combine_decrypt(list(used), cts_a, sh_a, table)
+    idx = (C.c_uint32 * 3)(*used)
+    d_c, d_s, d_p = up(cts_a), up(sh_a), up(pr_a)
+    d_v = torch.empty((n, 3), dtype=torch.uint8, device=dev)
+    d_vals, d_found = torch.empty(n, dtype=torch.int64, device=dev), torch.empty(n, dtype=torch.uint8, device=dev)
+    e._check(e.lib.eg_verify_shares_batch_dev(e.h, C.byref(eks), n, 3, idx, d_c.data_ptr(), d_s.data_ptr(), d_p.data_ptr(), d_v.data_ptr()))
+    e._check(e.lib.eg_combine_decrypt_batch_dev(e.h, 3, idx, n, 3, d_c.data_ptr(), d_s.data_ptr(), table.h, d_vals.data_ptr(), d_found.data_ptr()))
+    assert (d_v.cpu().numpy() == hv).all()
+    f = d_found.cpu().numpy()
+    assert (f == hfound).all() and (d_vals.cpu().numpy().view(np.uint64)[f == 1] == hvals[hfound == 1]).all()
+    assert hv[1, 0] == O.CHALLENGE_MISMATCH and hv[4, 2] == O.MALFORMED and hfound[4] == 2
+    table.close()
