@@ -65,6 +65,7 @@ struct eg_ctx {
     size_t chunk_items = 0;   // 0 = default
     int ring_mode = 0;        // 2: k_ring (one thread per ring, chunked tables); 1: k_commit / k_ring_hash launches per equation;
                               // 0: chosen per chunk (1 when the chunk cannot fill the persistent k_ring grid, run_ring_job)
+    int prover_ct = 0;        // eg_ctx_set_prover_mode: constant-time fixed-base arithmetic for the provers' secret scalars
     int ring_grid[2] = {0, 0};   // resident CTAs of the two k_ring shapes (queried once)
     int prove_grid[3] = {0, 0, 0};
     int rprove_grid[3] = {0, 0, 0};
@@ -797,6 +798,13 @@ extern "C" eg_status eg_ctx_set_ring_mode(eg_ctx *ctx, int mode) {
     if (!ctx || mode < 0 || mode > 2) return EG_ERR_INVALID_ARG;
     ctx->ring_mode = mode;
     for (eg_ctx *c : ctx->children) c->ring_mode = mode;
+    return EG_SUCCESS;
+}
+
+extern "C" eg_status eg_ctx_set_prover_mode(eg_ctx *ctx, int constant_time) {
+    if (!ctx || constant_time < 0 || constant_time > 1) return EG_ERR_INVALID_ARG;
+    ctx->prover_ct = constant_time;
+    for (eg_ctx *c : ctx->children) c->prover_ct = constant_time;
     return EG_SUCCESS;
 }
 

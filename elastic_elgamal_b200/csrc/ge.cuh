@@ -563,11 +563,56 @@ static EG_HD_NOINLINE void ge_eval64(ge_ext &out, const uint32_t *vtab, const sc
     out = acc;
 }
 
-// fixed-base-only form (the provers' [x] G, [x] K + [y] G)
-static EG_HD_NOINLINE void ge_eval_fixed(ge_ext &out, int nf, const uint32_t *ftab0, const sc &b0, const uint32_t *ftab1, const sc &b1) {
+// Constant-time form of ge_fixed_adds for SECRET scalars (the provers' randomness r and nonces x; the reference uses the
+// constant-time G::mul_generator / multi_mul there, src/proofs/ring.rs:99,115-116).  The scalar is cut into 64 signed
+// 4-bit windows; window i needs |d| * 16^i F with |d| <= 8, which is entry |d| * 16^(i mod 4) of wide window i / 4, so no
+// second table is needed.  Every window reads all eight candidates and keeps one with masks, conditionally negates with
+// masks and always adds (d = 0 adds the identity in Niels form): no branch and no address depends on the scalar.  64 mixed
+// additions and 512 entry reads per base instead of 16 and 16: about 4 x the fixed-base work (eg_ctx_set_prover_mode).
+EG_HD void ge_fixed_adds_ct(ge_ext &acc, ge_p1p1 &t, int nf, const uint32_t *ftab0, const sc &b0, const uint32_t *ftab1, const sc &b1) {
+#pragma unroll 1
+    for (int f = 0; f < nf; f++) {
+        const uint32_t *ft = f ? ftab1 : ftab0;
+        uint32_t ra[8];
+        sc_recode4(ra, f ? b1 : b0);
+#pragma unroll 1
+        for (int i = 0; i < 64; i++) {
+            const int d = sc_digit4(ra, i);                         // secret, in [-8, 7]
+            const uint32_t sign = (uint32_t)(d >> 31);              // all ones when negative
+            const uint32_t mag = ((uint32_t)d ^ sign) - sign;       // |d|
+            const uint32_t *win = ft + (size_t)(i >> 2) * (EG_WIDE_ENTRIES * 24);
+            const uint32_t stride = 1u << (4 * (i & 3));
+            uint32_t e[24];
+            for (int w = 0; w < 24; w++) e[w] = 0;
+            e[0] = 1; e[8] = 1;                                     // identity: (y + x, y - x, 2dxy) = (1, 1, 0)
+#pragma unroll 1
+            for (uint32_t k = 1; k <= 8; k++) {
+                const uint32_t *q = win + (size_t)(k * stride - 1) * 24;
+                const uint32_t m = (uint32_t)0 - (uint32_t)((((mag ^ k) - 1u) >> 31) & 1u);      // all ones iff mag == k
+                for (int w = 0; w < 24; w++) e[w] = (e[w] & ~m) | (q[w] & m);
+            }
+            ge_niels n;
+            for (int w = 0; w < 8; w++) {
+                n.ypx.v[w] = (e[w] & ~sign) | (e[8 + w] & sign);    // negation swaps y + x and y - x ...
+                n.ymx.v[w] = (e[8 + w] & ~sign) | (e[w] & sign);
+                n.xy2d.v[w] = e[16 + w];
+            }
+            fe nx;
+            fe_neg(nx, n.xy2d);                                     // ... and negates 2dxy
+            for (int w = 0; w < 8; w++) n.xy2d.v[w] = (n.xy2d.v[w] & ~sign) | (nx.v[w] & sign);
+            ge_add_niels_p1p1(t, acc, n, false);
+            ge_p1p1_to_ext(acc, t);
+        }
+    }
+}
+
+// fixed-base-only form (the provers' [x] G, [x] K + [y] G); ct selects the constant-time table walk for secret scalars
+static EG_HD_NOINLINE void ge_eval_fixed(ge_ext &out, int nf, const uint32_t *ftab0, const sc &b0, const uint32_t *ftab1, const sc &b1,
+                                         bool ct = false) {
     ge_ext acc = ge_identity();
     ge_p1p1 t;
-    ge_fixed_adds(acc, t, nf, ftab0, b0, ftab1, b1);
+    if (ct) ge_fixed_adds_ct(acc, t, nf, ftab0, b0, ftab1, b1);
+    else ge_fixed_adds(acc, t, nf, ftab0, b0, ftab1, b1);
     out = acc;
 }
 
@@ -575,8 +620,8 @@ static EG_HD_NOINLINE void ge_eval_fixed(ge_ext &out, int nf, const uint32_t *ft
 EG_HD void sc_half(sc &r, const sc &x) {
     uint32_t t[8];
     uint64_t c = 0;
-    const bool odd = (x.v[0] & 1u) != 0;
-    for (int i = 0; i < 8; i++) { c += (uint64_t)x.v[i] + (odd ? sc_L(i) : 0u); t[i] = (uint32_t)c; c >>= 32; }
+    const uint32_t odd = (uint32_t)0 - (x.v[0] & 1u);       // mask: x may be secret (prover nonces), no branch on it
+    for (int i = 0; i < 8; i++) { c += (uint64_t)x.v[i] + (sc_L(i) & odd); t[i] = (uint32_t)c; c >>= 32; }
     for (int i = 0; i < 7; i++) r.v[i] = (t[i] >> 1) | (t[i + 1] << 31);
     r.v[7] = t[7] >> 1;          // x + l < 2^254: no carry out of limb 7
 }

@@ -7,6 +7,7 @@
 // The kernel bodies are __host__ __device__ functions of (item, slot) so that tests/hostsim can run the very
 // same logic on the CPU (test harness only; the product library launches only the __global__ wrappers).
 #pragma once
+#include "chacha.cuh"
 #include "fe.cuh"
 #include "ge.cuh"
 #include "merlin.cuh"
@@ -522,23 +523,28 @@ struct prove_params {
     uint32_t *commit;            // planar encodings: terminal commitments of ring k at 2k, 2k+1
     uint32_t *chal;              // planar scalars: common challenge at 0
     const uint32_t *table_g, *table_k;
+    rand_src rnd;                // caller-supplied blocks (`wide`) or in-kernel ChaCha20 (chacha.cuh); constant-time flag
 };
 
 EG_HD void prove_draw(sc &out, const prove_params &P, size_t item, uint32_t pos) {
     uint32_t w[16];
-    const uint8_t *b = P.wide + (item * P.draws + pos) * 64;
-    load32_bytes(w, b);
-    load32_bytes(w + 8, b + 32);
+    if (P.rnd.seeded) {
+        chacha20_block(w, P.rnd.key, rand_counter(P.rnd, item, pos));
+    } else {
+        const uint8_t *b = P.wide + (item * P.draws + pos) * 64;
+        load32_bytes(w, b);
+        load32_bytes(w + 8, b + 32);
+    }
     sc_from_wide_words(out, w);
 }
 
 // out0 = encode([k] G), out1 = encode([k] K)
-EG_HD void prove_commit_pair(uint32_t out0[8], uint32_t out1[8], const sc &k, const uint32_t *tab_g, const uint32_t *tab_k) {
+EG_HD void prove_commit_pair(uint32_t out0[8], uint32_t out1[8], const sc &k, const uint32_t *tab_g, const uint32_t *tab_k, bool ct) {
     sc h;
     sc_half(h, k);
     ge_ext q0, q1;
-    ge_eval_fixed(q0, 1, tab_g, h, tab_g, h);
-    ge_eval_fixed(q1, 1, tab_k, h, tab_k, h);
+    ge_eval_fixed(q0, 1, tab_g, h, tab_g, h, ct);
+    ge_eval_fixed(q1, 1, tab_k, h, tab_k, h, ct);
     ge_double_compress2(out0, out1, q0, q1);
 }
 
@@ -547,7 +553,7 @@ EG_HD void prove_commit_pair(uint32_t out0[8], uint32_t out1[8], const sc &k, co
 // commitments are fixed-base: [s - e r]G and [s - e r]K + [e (a - v)]G -- the same group elements, hence the same
 // encodings, as the reference's vartime_double_mul_generator / vartime_multi_mul on R and B.
 EG_HD void prove_forge_fixed(uint32_t cg[8], uint32_t ck[8], const sc &r, uint64_t v, const sc &e, const sc &s, uint64_t a,
-                             const uint32_t *tab_g, const uint32_t *tab_k) {
+                             const uint32_t *tab_g, const uint32_t *tab_k, bool ct) {
     sc er, t, d, u, ht, hu;
     sc_mul(er, e, r);
     sc_sub(t, s, er);
@@ -557,8 +563,8 @@ EG_HD void prove_forge_fixed(uint32_t cg[8], uint32_t ck[8], const sc &r, uint64
     sc_half(ht, t);
     sc_half(hu, u);
     ge_ext qg, qk;
-    ge_eval_fixed(qg, 1, tab_g, ht, tab_g, ht);
-    ge_eval_fixed(qk, 2, tab_k, ht, tab_g, hu);
+    ge_eval_fixed(qg, 1, tab_g, ht, tab_g, ht, ct);
+    ge_eval_fixed(qk, 2, tab_k, ht, tab_g, hu, ct);
     ge_double_compress2(cg, ck, qg, qk);
 }
 
@@ -576,8 +582,10 @@ EG_HD void prove_ring1_body(const prove_params &P, size_t item, uint32_t k, uint
     ge_ext qr, qb;
     sc hone;
     sc_half(hone, sc_from_u64(1));
-    ge_eval_fixed(qr, 1, tab_g, hr, tab_g, hr);
-    ge_eval_fixed(qb, v ? 2 : 1, tab_k, hr, tab_g, hone);
+    const bool ct = P.rnd.ct != 0;
+    if (ct && !v) hone = sc_zero();          // constant-time mode: always two terms, [0]G for a zero vote
+    ge_eval_fixed(qr, 1, tab_g, hr, tab_g, hr, ct);
+    ge_eval_fixed(qb, (v || ct) ? 2 : 1, tab_k, hr, tab_g, hone, ct);
     uint32_t enc_ct[16];
     ge_double_compress2(enc_ct, enc_ct + 8, qr, qb);
     uint8_t *ct_out = P.cts + (item * P.options + k) * 64;
@@ -589,7 +597,7 @@ EG_HD void prove_ring1_body(const prove_params &P, size_t item, uint32_t k, uint
     planar_store_words(P.sec, P.n, 2 * k + 1, 8, item, x.v);
     // Ring::new (ring.rs:54-131): commitments of the real equation, then the forged ones above it
     uint32_t cg[8], ck[8];
-    prove_commit_pair(cg, ck, x, tab_g, tab_k);
+    prove_commit_pair(cg, ck, x, tab_g, tab_k, ct);
     if (!v) {
         transcript rt;
         ring_transcript_start(rt, P.ring_prefix, enc_ct, k);
@@ -597,7 +605,7 @@ EG_HD void prove_ring1_body(const prove_params &P, size_t item, uint32_t k, uint
         ring_next_challenge(e1, rt, 0, cg, ck);
         prove_draw(s1, P, item, pos + 2);
         store32_bytes(P.ring + (item * (1 + 2 * (size_t)P.options) + 1 + 2 * k + 1) * 32, s1.v);
-        prove_forge_fixed(cg, ck, r, 0, e1, s1, 1, tab_g, tab_k);
+        prove_forge_fixed(cg, ck, r, 0, e1, s1, 1, tab_g, tab_k, ct);
     }
     planar_store_words(P.commit, P.n, 2 * k, 8, item, cg);
     planar_store_words(P.commit, P.n, 2 * k + 1, 8, item, ck);
@@ -634,14 +642,15 @@ EG_HD void prove_common_body(const prove_params &P, size_t item, const uint32_t 
     sc_half(hr, sum_r);
     sc_half(hv, vm1);
     ge_ext q0, q1;
-    ge_eval_fixed(q0, 1, tab_g, hr, tab_g, hr);
-    ge_eval_fixed(q1, 2, tab_k, hr, tab_g, hv);
+    const bool ct = P.rnd.ct != 0;
+    ge_eval_fixed(q0, 1, tab_g, hr, tab_g, hr, ct);
+    ge_eval_fixed(q1, 2, tab_k, hr, tab_g, hv, ct);
     ge_double_compress2(w, w2, q0, q1);
     transcript st = P.sum_prefix;
     merlin_append_words(st, EG_LBL("[r]G"), w, 8);
     merlin_append_words(st, EG_LBL("[r]K"), w2, 8);
     prove_draw(x, P, item, 3 * P.options);
-    prove_commit_pair(w, w2, x, tab_g, tab_k);
+    prove_commit_pair(w, w2, x, tab_g, tab_k, ct);
     merlin_append_words(st, EG_LBL("[x]G"), w, 8);
     merlin_append_words(st, EG_LBL("[x]K"), w2, 8);
     sc c, s;
@@ -671,7 +680,7 @@ EG_HD void prove_ring2_body(const prove_params &P, size_t item, uint32_t k, uint
     prove_draw(s0, P, item, pos + before);
     store32_bytes(resp, s0.v);
     uint32_t cg[8], ck[8], enc_ct[16];
-    prove_forge_fixed(cg, ck, r, 1, e0, s0, 0, tab_g, tab_k);
+    prove_forge_fixed(cg, ck, r, 1, e0, s0, 0, tab_g, tab_k, P.rnd.ct != 0);
     planar_load_words(enc_ct, P.enc, P.n, 2 * k, 8, item);
     planar_load_words(enc_ct + 8, P.enc, P.n, 2 * k + 1, 8, item);
     transcript rt;
@@ -712,6 +721,8 @@ struct rprove_params {
     uint32_t *pts, *enc, *sec, *commit, *chal;       // planar scratch; ring k: pts / enc / commit 2k, 2k+1; sec 2k = r_k, 2k+1 = x_k
     uint32_t *ct_sec;                                // optional planar scalar (index 0): r of the main ciphertext
     const uint32_t *table_g, *table_k;
+    rand_src rnd;                                    // seeded: the item's stream is the RECORD's stream (group > 1: item / group),
+                                                     // its blocks start at rnd.block0 + (item % group) * wide_inner / 64
 };
 
 EG_HD size_t rprove_off(const rprove_params &P, size_t item, size_t stride, size_t inner) {
@@ -720,9 +731,15 @@ EG_HD size_t rprove_off(const rprove_params &P, size_t item, size_t stride, size
 
 EG_HD void rprove_draw(sc &out, const rprove_params &P, size_t item, uint32_t pos) {
     uint32_t w[16];
-    const uint8_t *b = P.wide + rprove_off(P, item, P.wide_stride, P.wide_inner) + (size_t)pos * 64;
-    load32_bytes(w, b);
-    load32_bytes(w + 8, b + 32);
+    if (P.rnd.seeded) {
+        const size_t record = P.group > 1 ? item / P.group : item;
+        const uint32_t inner = P.group > 1 ? (uint32_t)((item % P.group) * (P.wide_inner / 64)) : 0u;
+        chacha20_block(w, P.rnd.key, rand_counter(P.rnd, record, inner + pos));
+    } else {
+        const uint8_t *b = P.wide + rprove_off(P, item, P.wide_stride, P.wide_inner) + (size_t)pos * 64;
+        load32_bytes(w, b);
+        load32_bytes(w + 8, b + 32);
+    }
     sc_from_wide_words(out, w);
 }
 
@@ -745,13 +762,13 @@ EG_HD rprove_pos rprove_layout(const rprove_params &P, uint64_t value, uint32_t 
 }
 
 // enc_ct = encodings of ([r]G, [v]G + [r]K)
-EG_HD void rprove_encrypt(uint32_t enc_ct[16], const sc &r, uint64_t v, const uint32_t *tab_g, const uint32_t *tab_k) {
+EG_HD void rprove_encrypt(uint32_t enc_ct[16], const sc &r, uint64_t v, const uint32_t *tab_g, const uint32_t *tab_k, bool ct) {
     sc hr, hv;
     sc_half(hr, r);
     sc_half(hv, sc_from_u64(v));
     ge_ext qr, qb;
-    ge_eval_fixed(qr, 1, tab_g, hr, tab_g, hr);
-    ge_eval_fixed(qb, v ? 2 : 1, tab_k, hr, tab_g, hv);
+    ge_eval_fixed(qr, 1, tab_g, hr, tab_g, hr, ct);
+    ge_eval_fixed(qb, (v || ct) ? 2 : 1, tab_k, hr, tab_g, hv, ct);
     ge_double_compress2(enc_ct, enc_ct + 8, qr, qb);
 }
 
@@ -763,7 +780,7 @@ EG_HD void rprove_ring1_body(const rprove_params &P, size_t item, uint32_t slot,
     if (slot == Rn) {
         sc r;
         rprove_draw(r, P, item, 0);
-        rprove_encrypt(enc_ct, r, value, tab_g, tab_k);
+        rprove_encrypt(enc_ct, r, value, tab_g, tab_k, P.rnd.ct != 0);
         uint8_t *o = P.ct_out + rprove_off(P, item, P.ct_stride, P.out_inner);
         store32_bytes(o, enc_ct);
         store32_bytes(o + 32, enc_ct + 8);
@@ -786,7 +803,8 @@ EG_HD void rprove_ring1_body(const rprove_params &P, size_t item, uint32_t slot,
             sc_sub(r, r, ri);
         }
     }
-    rprove_encrypt(enc_ct, r, (uint64_t)L.vi * P.steps[k], tab_g, tab_k);
+    const bool ct = P.rnd.ct != 0;
+    rprove_encrypt(enc_ct, r, (uint64_t)L.vi * P.steps[k], tab_g, tab_k, ct);
     if (!last) {
         uint8_t *o = P.partial_out + rprove_off(P, item, P.partial_stride, P.out_inner) + 64 * (size_t)k;
         store32_bytes(o, enc_ct);
@@ -800,7 +818,7 @@ EG_HD void rprove_ring1_body(const rprove_params &P, size_t item, uint32_t slot,
     planar_store_words(P.sec, P.n, 2 * k + 1, 8, item, x.v);
     // Ring::new (ring.rs:97-131): commitments of the real equation, then the forged equations above it
     uint32_t cg[8], ck[8];
-    prove_commit_pair(cg, ck, x, tab_g, tab_k);
+    prove_commit_pair(cg, ck, x, tab_g, tab_k, ct);
     if (L.vi + 1 < m) {
         transcript rt;
         ring_transcript_start(rt, P.prefix, enc_ct, k);
@@ -811,7 +829,7 @@ EG_HD void rprove_ring1_body(const rprove_params &P, size_t item, uint32_t slot,
             ring_next_challenge(e, rt, eq - 1, cg, ck);
             rprove_draw(s_, P, item, xpos + (eq - L.vi));
             store32_bytes(resp + 32 * (size_t)eq, s_.v);
-            prove_forge_fixed(cg, ck, r, (uint64_t)L.vi * P.steps[k], e, s_, (uint64_t)eq * P.steps[k], tab_g, tab_k);
+            prove_forge_fixed(cg, ck, r, (uint64_t)L.vi * P.steps[k], e, s_, (uint64_t)eq * P.steps[k], tab_g, tab_k, ct);
         }
     }
     planar_store_words(P.commit, P.n, 2 * k, 8, item, cg);
@@ -855,7 +873,7 @@ EG_HD void rprove_ring2_body(const rprove_params &P, size_t item, uint32_t k, ui
             sc s_;
             rprove_draw(s_, P, item, L.pos2 + eq);
             store32_bytes(resp + 32 * (size_t)eq, s_.v);
-            prove_forge_fixed(cg, ck, r, (uint64_t)L.vi * P.steps[k], e, s_, (uint64_t)eq * P.steps[k], tab_g, tab_k);
+            prove_forge_fixed(cg, ck, r, (uint64_t)L.vi * P.steps[k], e, s_, (uint64_t)eq * P.steps[k], tab_g, tab_k, P.rnd.ct != 0);
             ring_next_challenge(e, rt, eq, cg, ck);
         }
     }
@@ -876,24 +894,33 @@ struct encrypt_params {
     uint8_t *proofs;                     // mode 1: n * 64
     transcript prefix;                   // mode 1: Transcript::new("zero_encryption") + start_proof("log_eq") + "K"
     const uint32_t *table_g, *table_k;
+    rand_src rnd;
 };
+
+// block `k` of item `item`: from the caller's buffer at `b`, or generated
+EG_HD void rand_block(uint32_t w[16], const rand_src &R, size_t item, uint32_t k, const uint8_t *b) {
+    if (R.seeded) { chacha20_block(w, R.key, rand_counter(R, item, k)); return; }
+    load32_bytes(w, b);
+    load32_bytes(w + 8, b + 32);
+}
 
 EG_HD void encrypt_body(const encrypt_params &P, size_t item, const uint32_t *tab_g, const uint32_t *tab_k) {
     const uint32_t draws = 1 + P.with_zero_proof;
     uint32_t w[16], enc_ct[16];
     const uint8_t *b = P.wide + item * draws * 64;
+    const bool ct = P.rnd.ct != 0;
     sc r;
-    load32_bytes(w, b); load32_bytes(w + 8, b + 32);
+    rand_block(w, P.rnd, item, 0, b);
     sc_from_wide_words(r, w);
-    rprove_encrypt(enc_ct, r, P.with_zero_proof ? 0 : P.values[item], tab_g, tab_k);
+    rprove_encrypt(enc_ct, r, P.with_zero_proof ? 0 : P.values[item], tab_g, tab_k, ct);
     store32_bytes(P.cts + item * 64, enc_ct);
     store32_bytes(P.cts + item * 64 + 32, enc_ct + 8);
     if (!P.with_zero_proof) return;
     sc x, c, s_;
-    load32_bytes(w, b + 64); load32_bytes(w + 8, b + 96);
+    rand_block(w, P.rnd, item, 1, b + 64);
     sc_from_wide_words(x, w);
     uint32_t c0[8], c1[8];
-    prove_commit_pair(c0, c1, x, tab_g, tab_k);
+    prove_commit_pair(c0, c1, x, tab_g, tab_k, ct);
     transcript t = P.prefix;
     merlin_append_words(t, EG_LBL("[r]G"), enc_ct, 8);
     merlin_append_words(t, EG_LBL("[r]K"), enc_ct + 8, 8);
@@ -925,14 +952,16 @@ struct sumsq_prove_params {
     const uint32_t *r_sum;               // planar scalars over n items: randomness of the sum ciphertext
     transcript prefix;                   // Transcript::new(label) + start_proof("sum_of_squares") + "K"
     const uint32_t *table_g, *table_k;
+    rand_src rnd;
 };
 
 EG_HD void sumsq_prove_body(const sumsq_prove_params &P, size_t item, const uint32_t *tab_g, const uint32_t *tab_k) {
     transcript t = P.prefix;
     uint32_t w[16], c0[8], c1[8];
     const uint8_t *wide = P.wide + item * P.wide_stride;
+    const bool ct = P.rnd.ct != 0;
     sc e_z, e_r[EG_MSM_MAXV], e_x[EG_MSM_MAXV];
-    load32_bytes(w, wide); load32_bytes(w + 8, wide + 32);
+    rand_block(w, P.rnd, item, 0, wide);
     sc_from_wide_words(e_z, w);
     sc acc_r = e_z, acc_x = sc_zero();       // sum e_x,i r_i + e_z ; sum e_x,i x_i
     sc sum_random;                            // r_z - sum x_i r_i   (mul.rs:117,132-133)
@@ -945,16 +974,16 @@ EG_HD void sumsq_prove_body(const sumsq_prove_params &P, size_t item, const uint
         load32_bytes(w, ct + 32);
         merlin_append_words(t, EG_LBL("X"), w, 8);
         const uint8_t *b = wide + 64 * (size_t)(1 + 2 * i);
-        load32_bytes(w, b); load32_bytes(w + 8, b + 32);
+        rand_block(w, P.rnd, item, 1 + 2 * i, b);
         sc_from_wide_words(e_r[i], w);
-        load32_bytes(w, b + 64); load32_bytes(w + 8, b + 96);
+        rand_block(w, P.rnd, item, 2 + 2 * i, b + 64);
         sc_from_wide_words(e_x[i], w);
         sc her, hex_;
         sc_half(her, e_r[i]);
         sc_half(hex_, e_x[i]);
         ge_ext q0, q1;
-        ge_eval_fixed(q0, 1, tab_g, her, tab_g, her);
-        ge_eval_fixed(q1, 2, tab_k, her, tab_g, hex_);
+        ge_eval_fixed(q0, 1, tab_g, her, tab_g, her, ct);
+        ge_eval_fixed(q1, 2, tab_k, her, tab_g, hex_, ct);
         ge_double_compress2(c0, c1, q0, q1);
         merlin_append_words(t, EG_LBL("[e_r]G"), c0, 8);
         merlin_append_words(t, EG_LBL("[e_x]G + [e_r]K"), c1, 8);
@@ -970,8 +999,8 @@ EG_HD void sumsq_prove_body(const sumsq_prove_params &P, size_t item, const uint
         sc_half(ha, acc_r);
         sc_half(hx, acc_x);
         ge_ext q0, q1;
-        ge_eval_fixed(q0, 1, tab_g, ha, tab_g, ha);
-        ge_eval_fixed(q1, 2, tab_k, ha, tab_g, hx);
+        ge_eval_fixed(q0, 1, tab_g, ha, tab_g, ha, ct);
+        ge_eval_fixed(q1, 2, tab_k, ha, tab_g, hx, ct);
         ge_double_compress2(c0, c1, q0, q1);
     }
     const uint8_t *zct = P.sum_ct + item * P.ct_stride;

@@ -66,18 +66,30 @@ EG_HD void sc_tobytes(uint8_t s[32], const sc &a) {
 EG_HD bool sc_iszero(const sc &a) { uint32_t o = 0; for (int i = 0; i < 8; i++) o |= a.v[i]; return o == 0; }
 EG_HD bool sc_eq(const sc &a, const sc &b) { uint32_t o = 0; for (int i = 0; i < 8; i++) o |= a.v[i] ^ b.v[i]; return o == 0; }
 
+// t (< 2 l) -> t mod l without a data-dependent branch: subtract l, keep the difference unless it borrowed.  The operands
+// of sc_add / sc_neg / sc_sub / sc_mul are secrets on the proving side (randomness, nonces), so these stay branch-free.
+EG_HD void sc_csub_l(uint32_t t[8]) {
+    uint32_t d[8];
+    int64_t c = 0;
+    for (int i = 0; i < 8; i++) { c += (int64_t)t[i] - (int64_t)sc_L(i); d[i] = (uint32_t)c; c >>= 32; }
+    const uint32_t keep = (uint32_t)c;                      // all ones when t < l (the subtraction borrowed)
+    for (int i = 0; i < 8; i++) t[i] = (t[i] & keep) | (d[i] & ~keep);
+}
+
 EG_HD void sc_add(sc &r, const sc &a, const sc &b) {
     uint64_t c = 0;
     uint32_t t[8];
     for (int i = 0; i < 8; i++) { c += (uint64_t)a.v[i] + b.v[i]; t[i] = (uint32_t)c; c >>= 32; }
-    if (sc_geq_l(t)) sc_sub_l(t);       // a, b < l < 2^253: no carry out
+    sc_csub_l(t);                       // a, b < l < 2^253: no carry out
     for (int i = 0; i < 8; i++) r.v[i] = t[i];
 }
 
 EG_HD void sc_neg(sc &r, const sc &a) {
-    if (sc_iszero(a)) { r = sc_zero(); return; }
+    uint32_t nz = 0;
+    for (int i = 0; i < 8; i++) nz |= a.v[i];
+    const uint32_t m = (uint32_t)0 - (uint32_t)((nz | ((uint32_t)0 - nz)) >> 31);     // all ones unless a == 0
     int64_t c = 0;
-    for (int i = 0; i < 8; i++) { c += (int64_t)sc_L(i) - (int64_t)a.v[i]; r.v[i] = (uint32_t)c; c >>= 32; }
+    for (int i = 0; i < 8; i++) { c += (int64_t)sc_L(i) - (int64_t)a.v[i]; r.v[i] = (uint32_t)c & m; c >>= 32; }
 }
 
 EG_HD void sc_sub(sc &r, const sc &a, const sc &b) { sc n; sc_neg(n, b); sc_add(r, a, n); }
@@ -96,8 +108,14 @@ EG_HD void sc_montmul(uint32_t r[8], const uint32_t a[8], const uint32_t b[8]) {
         for (int j = 1; j < 8; j++) { c += (uint64_t)m * sc_L(j) + t[j]; t[j - 1] = (uint32_t)c; c >>= 32; }
         c += t[8]; t[7] = (uint32_t)c; t[8] = t[9] + (uint32_t)(c >> 32); t[9] = 0;
     }
-    if (t[8] || sc_geq_l(t)) sc_sub_l(t);
-    for (int i = 0; i < 8; i++) r[i] = t[i];
+    {   // result < 2 l: one conditional subtraction over 9 limbs, branch-free (keep the difference unless it borrowed)
+        uint32_t d[8];
+        int64_t c = 0;
+        for (int i = 0; i < 8; i++) { c += (int64_t)t[i] - (int64_t)sc_L(i); d[i] = (uint32_t)c; c >>= 32; }
+        c += (int64_t)t[8];
+        const uint32_t keep = (uint32_t)(c >> 32);          // all ones when t < l
+        for (int i = 0; i < 8; i++) r[i] = (t[i] & keep) | (d[i] & ~keep);
+    }
 }
 
 EG_HD void sc_mul(sc &r, const sc &a, const sc &b) {

@@ -106,6 +106,14 @@ class Engine:
     def set_ring_mode(self, mode):
         self._check(self.lib.eg_ctx_set_ring_mode(self.h, mode))
 
+    def set_prover_mode(self, constant_time):
+        """True: constant-time fixed-base arithmetic for the provers' secret scalars (include/eg_b200.h)."""
+        self._check(self.lib.eg_ctx_set_prover_mode(self.h, 1 if constant_time else 0))
+
+    @staticmethod
+    def _seed(seed):
+        return _u8(np.frombuffer(bytes(seed), dtype=np.uint8), (32,))
+
     # ---- PublicKey::from_bytes
     def set_receiver(self, key):
         key = _u8(np.frombuffer(bytes(key), dtype=np.uint8), (32,))
@@ -229,36 +237,53 @@ class Engine:
         return v
 
     # ---- encryption side (randomness supplied by the caller as 64-byte blocks in the reference's draw order)
-    def encrypt(self, values, wide_rand):
+    # Every encrypt_* takes either `wide_rand` (the blocks themselves) or `seed=` (32 bytes) + `counter_base=`: the seeded
+    # form generates the blocks in the kernel (eg_*_batch_seeded).
+    def encrypt(self, values, wide_rand=None, seed=None, counter_base=0):
         values = np.ascontiguousarray(values, dtype=np.uint64).reshape(-1)
         n = values.shape[0]
-        wide_rand = _u8(wide_rand, (n, 64))
         cts = np.empty((n, 64), np.uint8)
+        if seed is not None:
+            self._check(self.lib.eg_encrypt_batch_seeded(self.h, n, _addr(values), _addr(self._seed(seed)), counter_base, _addr(cts)))
+            return cts
+        wide_rand = _u8(wide_rand, (n, 64))
         self._check(self.lib.eg_encrypt_batch(self.h, n, _addr(values), _addr(wide_rand), _addr(cts)))
         return cts
 
-    def encrypt_zero(self, wide_rand):
+    def encrypt_zero(self, wide_rand=None, seed=None, counter_base=0, n=None):
+        if seed is not None:
+            cts, proofs = np.empty((n, 64), np.uint8), np.empty((n, 64), np.uint8)
+            self._check(self.lib.eg_encrypt_zero_batch_seeded(self.h, n, _addr(self._seed(seed)), counter_base, _addr(cts), _addr(proofs)))
+            return cts, proofs
         wide_rand = _u8(wide_rand, (-1, 2, 64))
         n = wide_rand.shape[0]
         cts, proofs = np.empty((n, 64), np.uint8), np.empty((n, 64), np.uint8)
         self._check(self.lib.eg_encrypt_zero_batch(self.h, n, _addr(wide_rand), _addr(cts), _addr(proofs)))
         return cts, proofs
 
-    def encrypt_bool(self, values, wide_rand):
+    def encrypt_bool(self, values, wide_rand=None, seed=None, counter_base=0):
         values = _u8(values, (-1,))
         n = values.shape[0]
-        wide_rand = _u8(wide_rand, (n, 3, 64))
         cts, proofs = np.empty((n, 64), np.uint8), np.empty((n, 96), np.uint8)
+        if seed is not None:
+            self._check(self.lib.eg_encrypt_bool_batch_seeded(self.h, n, _addr(values), _addr(self._seed(seed)), counter_base, _addr(cts),
+                                                              _addr(proofs)))
+            return cts, proofs
+        wide_rand = _u8(wide_rand, (n, 3, 64))
         self._check(self.lib.eg_encrypt_bool_batch(self.h, n, _addr(values), _addr(wide_rand), _addr(cts), _addr(proofs)))
         return cts, proofs
 
-    def encrypt_choice(self, options, values, wide_rand, single=True):
+    def encrypt_choice(self, options, values, wide_rand=None, single=True, seed=None, counter_base=0):
         values = _u8(values, (-1, options))
         n = values.shape[0]
         draws = 3 * options + (1 if single else 0)
-        wide_rand = _u8(wide_rand, (n, draws, 64))
         cts, rings = np.empty((n, options, 64), np.uint8), np.empty((n, 1 + 2 * options, 32), np.uint8)
         sums = np.empty((n, 64), np.uint8) if single else None
+        if seed is not None:
+            self._check(self.lib.eg_encrypt_choice_batch_seeded(self.h, n, options, int(single), _addr(values), _addr(self._seed(seed)),
+                                                                counter_base, _addr(cts), _addr(rings), _addr(sums)))
+            return cts, rings, sums
+        wide_rand = _u8(wide_rand, (n, draws, 64))
         self._check(self.lib.eg_encrypt_choice_batch(self.h, n, options, int(single), _addr(values), _addr(wide_rand), _addr(cts),
                                                      _addr(rings), _addr(sums)))
         return cts, rings, sums
@@ -284,14 +309,19 @@ class Engine:
                                                    _addr(partials) if rng.n_rings > 1 else None, _addr(rings), _addr(v)))
         return v
 
-    def encrypt_range(self, rng, label, values, wide_rand):
+    def encrypt_range(self, rng, label, values, wide_rand=None, seed=None, counter_base=0):
         values = np.ascontiguousarray(values, dtype=np.uint64).reshape(-1)
         n = values.shape[0]
         draws = self.lib.eg_range_prover_draws(C.byref(rng))
-        wide_rand = _u8(wide_rand, (n, draws, 64))
         cts = np.empty((n, 64), np.uint8)
         partials = np.empty((n, max(0, rng.n_rings - 1), 64), np.uint8)
         rings = np.empty((n, 1 + rng.rings_size, 32), np.uint8)
+        if seed is not None:
+            self._check(self.lib.eg_encrypt_range_batch_seeded(self.h, C.byref(rng), label.encode(), n, _addr(values), _addr(self._seed(seed)),
+                                                               counter_base, _addr(cts), _addr(partials) if rng.n_rings > 1 else None,
+                                                               _addr(rings)))
+            return cts, partials, rings
+        wide_rand = _u8(wide_rand, (n, draws, 64))
         self._check(self.lib.eg_encrypt_range_batch(self.h, C.byref(rng), label.encode(), n, _addr(values), _addr(wide_rand),
                                                     _addr(cts), _addr(partials) if rng.n_rings > 1 else None, _addr(rings)))
         return cts, partials, rings
@@ -314,12 +344,16 @@ class Engine:
         self._check(self.lib.eg_verify_qv_batch(self.h, C.byref(p), n, _addr(ballots), _addr(v), _addr(t)))
         return v, t
 
-    def encrypt_qv(self, p, votes, wide_rand):
+    def encrypt_qv(self, p, votes, wide_rand=None, seed=None, counter_base=0):
         votes = np.ascontiguousarray(votes, dtype=np.uint64).reshape(-1, p.options)
         n = votes.shape[0]
         draws = self.lib.eg_qv_prover_draws(C.byref(p))
-        wide_rand = _u8(wide_rand, (n, draws, 64))
         ballots = np.empty((n, self.qv_ballot_size(p)), np.uint8)
+        if seed is not None:
+            self._check(self.lib.eg_encrypt_qv_batch_seeded(self.h, C.byref(p), n, _addr(votes), _addr(self._seed(seed)), counter_base,
+                                                            _addr(ballots)))
+            return ballots
+        wide_rand = _u8(wide_rand, (n, draws, 64))
         self._check(self.lib.eg_encrypt_qv_batch(self.h, C.byref(p), n, _addr(votes), _addr(wide_rand), _addr(ballots)))
         return ballots
 

@@ -272,7 +272,8 @@ eg_status eg_encrypt_bool_batch(eg_ctx *ctx, size_t n, const uint8_t *values /* 
 /* EncryptedChoice::new / ::single (src/app/choice.rs:288-349): values[i*options + k] != 0 marks option k of ballot i
  * (exactly one for `single`); item i consumes 3*options (+1 for the sum proof when `single`) blocks: r, x and -- for a
  * zero option -- the forged response per option in option order, then the forged responses of the chosen options,
- * then the sum-proof nonce.  sum_proofs may be NULL when single == 0. */
+ * then the sum-proof nonce.  sum_proofs may be NULL when single == 0.  With single != 0 a row that does not mark exactly
+ * one option is EG_ERR_INVALID_ARG (EncryptedChoice::single cannot produce such a ballot, src/app/choice.rs:288-306). */
 eg_status eg_encrypt_choice_batch(eg_ctx *ctx, size_t n, uint32_t options, int single, const uint8_t *values /* n*options */,
                                   const uint8_t *wide_rand /* n*(3*options+single)*64 */, uint8_t *choices /* n*options*64 */,
                                   uint8_t *ring_proofs /* n*(1+2*options)*32 */, uint8_t *sum_proofs /* n*64 */);
@@ -298,6 +299,43 @@ eg_status eg_encrypt_range_batch(eg_ctx *ctx, const eg_range *range, const char 
 size_t    eg_qv_prover_draws(const eg_qv_params *params);
 eg_status eg_encrypt_qv_batch(eg_ctx *ctx, const eg_qv_params *params, size_t n, const uint64_t *votes /* n*options */,
                               const uint8_t *wide_rand /* n*draws*64 */, uint8_t *ballots /* n*eg_qv_ballot_size */);
+
+/* ---- encryption side with in-kernel randomness ---------------------------------------------------
+ * The same provers, but every 64-byte block is produced inside the kernel by ChaCha20 (RFC 8439 block function, 64-bit
+ * block counter, stream id 0 -- rand_chacha's ChaCha20Rng, the generator of tests/snapshots.rs:31-34 and
+ * benches/basics.rs:17) instead of crossing PCIe (64 B per draw: 2560 B per range proof, 3392 B per quadratic-voting
+ * ballot).  `seed` is the 32-byte ChaCha20 key; item i of the batch draws from its own stream: draw number k (in the draw
+ * order documented above for the caller-supplied form) is the block with counter  counter_base + (i << 20) + k.  Hence
+ *   - the outputs equal those of the caller-supplied form fed with these blocks, byte for byte;
+ *   - counter_base = 1, n = 1 and the key of `ChaChaRng::seed_from_u64(12345)` reproduces the reference snapshots (block 0
+ *     of that stream is the receiver's secret key, tests/snapshots.rs:32-34);
+ *   - the seed is a SECRET of the same weight as the randomness it replaces: one seed per batch from the host's CSPRNG. */
+eg_status eg_encrypt_batch_seeded(eg_ctx *ctx, size_t n, const uint64_t *values, const uint8_t seed[32], uint64_t counter_base,
+                                  uint8_t *cts);
+eg_status eg_encrypt_zero_batch_seeded(eg_ctx *ctx, size_t n, const uint8_t seed[32], uint64_t counter_base, uint8_t *cts,
+                                       uint8_t *proofs);
+eg_status eg_encrypt_bool_batch_seeded(eg_ctx *ctx, size_t n, const uint8_t *values, const uint8_t seed[32], uint64_t counter_base,
+                                       uint8_t *cts, uint8_t *proofs);
+eg_status eg_encrypt_choice_batch_seeded(eg_ctx *ctx, size_t n, uint32_t options, int single, const uint8_t *values,
+                                         const uint8_t seed[32], uint64_t counter_base, uint8_t *choices, uint8_t *ring_proofs,
+                                         uint8_t *sum_proofs);
+eg_status eg_encrypt_range_batch_seeded(eg_ctx *ctx, const eg_range *range, const char *transcript_label, size_t n,
+                                        const uint64_t *values, const uint8_t seed[32], uint64_t counter_base, uint8_t *cts,
+                                        uint8_t *partials, uint8_t *ring_proofs);
+eg_status eg_encrypt_qv_batch_seeded(eg_ctx *ctx, const eg_qv_params *params, size_t n, const uint64_t *votes, const uint8_t seed[32],
+                                     uint64_t counter_base, uint8_t *ballots);
+
+/* Side-channel posture of the encryption side (the reference: constant-time G::mul_generator / multi_mul and zeroizing
+ * secret wrappers, src/proofs/ring.rs:97-116, src/group/mod.rs:79).
+ *   constant_time = 0 (default): secret scalars (randomness r, nonces x) walk the 16-bit-window fixed-base tables with
+ *     secret-dependent addresses and skip zero digits -- fastest; appropriate when the GPU is not shared with an adversary.
+ *   constant_time = 1: every fixed-base multiplication by a secret scalar uses 64 signed 4-bit windows, reads all eight
+ *     candidate entries of a window and selects with masks, always adds; no branch or address depends on a secret scalar
+ *     (about 4 x the fixed-base work).  Scalar arithmetic mod l is branch-free in both modes.  As in the reference, the
+ *     *shape* of a ring proof's computation (which equation is the real one) follows the encrypted value.
+ * In both modes the device scratch that held randomness, nonces, plaintext values and staged randomness blocks is zeroed
+ * before a prover call returns.  Verification entry points only handle public data and stay variable-time. */
+eg_status eg_ctx_set_prover_mode(eg_ctx *ctx, int constant_time);
 
 /* ---- device-pointer variants (inputs already resident in HBM; same semantics) ------------------- */
 eg_status eg_verify_bool_batch_dev(eg_ctx *ctx, size_t n, const uint8_t *d_cts, const uint8_t *d_proofs, uint8_t *d_verdicts);

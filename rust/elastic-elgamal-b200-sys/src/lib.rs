@@ -150,6 +150,13 @@ extern "C" {
                                  proofs: *mut u8) -> eg_status;
     pub fn eg_encrypt_choice_batch(ctx: *mut eg_ctx, n: usize, options: u32, single: c_int, values: *const u8,
                                    wide_rand: *const u8, choices: *mut u8, ring_proofs: *mut u8, sum_proofs: *mut u8) -> eg_status;
+    pub fn eg_encrypt_batch_seeded(ctx: *mut eg_ctx, n: usize, values: *const u64, seed: *const u8, counter_base: u64, cts: *mut u8) -> eg_status;
+    pub fn eg_encrypt_zero_batch_seeded(ctx: *mut eg_ctx, n: usize, seed: *const u8, counter_base: u64, cts: *mut u8, proofs: *mut u8) -> eg_status;
+    pub fn eg_encrypt_bool_batch_seeded(ctx: *mut eg_ctx, n: usize, values: *const u8, seed: *const u8, counter_base: u64, cts: *mut u8, proofs: *mut u8) -> eg_status;
+    pub fn eg_encrypt_choice_batch_seeded(ctx: *mut eg_ctx, n: usize, options: u32, single: c_int, values: *const u8, seed: *const u8, counter_base: u64, choices: *mut u8, ring_proofs: *mut u8, sum_proofs: *mut u8) -> eg_status;
+    pub fn eg_encrypt_range_batch_seeded(ctx: *mut eg_ctx, range: *const eg_range, transcript_label: *const c_char, n: usize, values: *const u64, seed: *const u8, counter_base: u64, cts: *mut u8, partials: *mut u8, ring_proofs: *mut u8) -> eg_status;
+    pub fn eg_encrypt_qv_batch_seeded(ctx: *mut eg_ctx, params: *const eg_qv_params, n: usize, votes: *const u64, seed: *const u8, counter_base: u64, ballots: *mut u8) -> eg_status;
+    pub fn eg_ctx_set_prover_mode(ctx: *mut eg_ctx, constant_time: c_int) -> eg_status;
     pub fn eg_range_prover_draws(range: *const eg_range) -> usize;
     pub fn eg_encrypt_range_batch(ctx: *mut eg_ctx, range: *const eg_range, transcript_label: *const c_char, n: usize,
                                   values: *const u64, wide_rand: *const u8, cts: *mut u8, partials: *mut u8,

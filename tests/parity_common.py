@@ -871,3 +871,160 @@ def check_keysets_validate(e, n_sets=8, shares=5, threshold=3, seed=13):
     if n_sets >= 6 and shares > threshold and threshold > 1:
         assert [x[0] for x in expected[1:6]] == [O.MALFORMED_PARTICIPANT_KEYS] * 3 + [O.MALFORMED] * 2
     assert e.keysets_validate(shares, threshold, keys[:0])[1].shape == (0,)
+
+
+# ---------------------------------------------------------------- seeded provers (in-kernel ChaCha20) / constant-time mode
+
+def _gold():
+    import json
+    import pathlib
+    return json.loads((pathlib.Path(__file__).parent / "golden" / "ristretto_snapshots.json").read_text())
+
+
+def check_seeded_provers(e, pk, sk, n=9, first=3):
+    """eg_*_batch_seeded generate their randomness in the kernel (ChaCha20, key = seed, block counter = counter_base +
+    (i << 20) + draw): byte-identical to the oracle's provers on the same per-item streams (SURVEY.md 8(d) layout), to the
+    caller-supplied form fed with those blocks, and independent of the chunking."""
+    seed, base = W.SEED_CHOICE, first << 20
+    # encrypt_bool
+    ocs, ops = O.gen_bool_batch(pk, seed, n, first=first)
+    values = np.array([(first + i) & 1 for i in range(n)], np.uint8)
+    cts, proofs = e.encrypt_bool(values, seed=seed, counter_base=base)
+    assert (cts == ocs).all() and (proofs == ops).all()
+    # EncryptedChoice::single, also with tiny chunks (item0 of later chunks)
+    options = 4
+    ocs, ors, oss = O.gen_choice_batch(pk, options, seed, n, first=first)
+    values = np.zeros((n, options), np.uint8)
+    for i in range(n):
+        values[i, (first + i) % options] = 1
+    for chunk in (0, 4):
+        e.set_chunk_items(chunk)
+        try:
+            cts, rings, sums = e.encrypt_choice(options, values, single=True, seed=seed, counter_base=base)
+        finally:
+            e.set_chunk_items(0)
+        assert (cts == ocs).all() and (rings == ors).all() and (sums == oss).all()
+    # RangeProof::new
+    spec = O.range_optimal(100)
+    espec = to_engine_range(e, spec)
+    vals = np.array([(17 * (first + i)) % 100 for i in range(n)], np.uint64)
+    oc, op, orr = O.gen_range_batch(pk, spec, "ciphertext_range", seed, vals, first=first)
+    for chunk in (0, 4):
+        e.set_chunk_items(chunk)
+        try:
+            c, p, r = e.encrypt_range(espec, "ciphertext_range", vals, seed=seed, counter_base=base)
+        finally:
+            e.set_chunk_items(0)
+        assert (c == oc).all() and (p == op).all() and (r == orr).all()
+    # QuadraticVotingBallot::new (records of several proofs: block0 / group addressing)
+    p_, ep = O.qv_params(5, 20), e.qv_params(5, 20)
+    votes = np.array([QV_VOTES[(first + i) % 4] for i in range(n)], np.uint64)
+    ob = O.gen_qv_batch(pk, p_, W.SEED_QV, votes, first=first)
+    for chunk in (0, 4):
+        e.set_chunk_items(chunk)
+        try:
+            b = e.encrypt_qv(ep, votes, seed=W.SEED_QV, counter_base=base)
+        finally:
+            e.set_chunk_items(0)
+        assert (b == ob).all()
+    assert (e.verify_qv(ep, b)[0] == 0).all()
+    # encrypt / encrypt_zero: equal to the caller-supplied form on the same blocks
+    vals = np.arange(n, dtype=np.uint64) * 1000
+    wide = np.frombuffer(b"".join(item_blocks(seed, first + i, 1) for i in range(n)), np.uint8)
+    assert (e.encrypt(vals, seed=seed, counter_base=base) == e.encrypt(vals, wide)).all()
+    wide = np.frombuffer(b"".join(item_blocks(seed, first + i, 2) for i in range(n)), np.uint8)
+    c1, p1 = e.encrypt_zero(seed=seed, counter_base=base, n=n)
+    c2, p2 = e.encrypt_zero(wide)
+    assert (c1 == c2).all() and (p1 == p2).all() and (e.verify_zero(c1, p1) == 0).all()
+
+
+def check_seeded_reference_snapshots(e):
+    """counter_base = 1 and the ChaCha20 key of `ChaChaRng::seed_from_u64(12345)` (PCG32 expansion, SURVEY.md A.1): the
+    seeded provers regenerate the reference's own snapshots (tests/snapshots.rs:73-161) -- block 0 of that stream is the
+    receiver's secret key, the object's draws follow."""
+    gold, hx = _gold(), bytes.fromhex
+    rng = O.rng_from_u64(12345)
+    key = bytes(rng.key)
+    sk, pk = O.keypair(rng)
+
+    def ctb(d):
+        return hx(d["random_element"]) + hx(d["blinded_element"])
+    try:
+        e.set_receiver(pk)
+        cts, proofs = e.encrypt_bool(np.array([1], np.uint8), seed=key, counter_base=1)
+        assert cts.tobytes() == ctb(gold["bool-encryption"]["ciphertext"]) and proofs.tobytes() == hx(gold["bool-encryption-bin"])
+        cts, rings, sums = e.encrypt_choice(5, np.array([[0, 0, 0, 1, 0]], np.uint8), single=True, seed=key, counter_base=1)
+        g = gold["encrypted-choice"]
+        assert cts.tobytes() == b"".join(ctb(c) for c in g["choices"])
+        assert rings.tobytes() == hx(g["range_proof"]["common_challenge"]) + b"".join(hx(x) for x in g["range_proof"]["ring_responses"])
+        assert sums.tobytes() == hx(g["sum_proof"]["challenge"]) + hx(g["sum_proof"]["response"])
+        cts, rings, _ = e.encrypt_choice(5, np.array([[0, 1, 1, 0, 1]], np.uint8), single=False, seed=key, counter_base=1)
+        g = gold["encrypted-multi-choice"]
+        assert cts.tobytes() == b"".join(ctb(c) for c in g["choices"])
+        assert rings.tobytes() == hx(g["range_proof"]["common_challenge"]) + b"".join(hx(x) for x in g["range_proof"]["ring_responses"])
+        espec = e.range_optimal(100)
+        c, p, r = e.encrypt_range(espec, "ciphertext_range", np.array([42], np.uint64), seed=key, counter_base=1)
+        g = gold["range-encryption"]
+        assert bytes(c[0]) == ctb(g["ciphertext"])
+        assert bytes(p[0].reshape(-1)) == b"".join(ctb(x) for x in g["proof"]["partial_ciphertexts"])
+        assert bytes(r[0].reshape(-1)) == hx(g["proof"]["common_challenge"]) + b"".join(hx(x) for x in g["proof"]["ring_responses"])
+        ep = e.qv_params(5, 15)
+        ballot = bytes(e.encrypt_qv(ep, np.array([[3, 0, 1, 0, 2]], np.uint64), seed=key, counter_base=1)[0])
+        g = gold["qv-ballot"]
+
+        def rp(d):
+            pr = d["range_proof"]
+            return (ctb(d["ciphertext"]) + b"".join(ctb(x) for x in pr["partial_ciphertexts"]) + hx(pr["common_challenge"])
+                    + b"".join(hx(x) for x in pr["ring_responses"]))
+        ce = g["credit_equivalence_proof"]
+        assert ballot == (b"".join(rp(v) for v in g["votes"]) + rp(g["credit"]) + hx(ce["challenge"])
+                          + b"".join(hx(x) for x in ce["ciphertext_responses"]) + hx(ce["sum_response"]))
+        ct = bytes(e.encrypt(np.array([42], np.uint64), seed=key, counter_base=1)[0])
+        assert ct == hx(gold["ciphertext-bin"])
+        cts, proofs = e.encrypt_zero(seed=key, counter_base=1, n=1)
+        assert bytes(cts[0]) == ctb(gold["zero-encryption"]["ciphertext"]) and bytes(proofs[0]) == hx(gold["zero-encryption-bin"])
+    finally:
+        e.set_receiver(W.receiver()[1])
+
+
+def check_constant_time_prover_mode(e, pk, n=6):
+    """eg_ctx_set_prover_mode(1) changes how secret scalars walk the fixed-base tables (64 masked 4-bit windows), never
+    the group elements: every prover output is byte-identical to the default mode's."""
+    seed = W.SEED_CHOICE
+    spec = to_engine_range(e, O.range_optimal(21))
+    ep = e.qv_params(3, 9)
+    rvals = np.array([(5 * i) % 21 for i in range(n)], np.uint64)
+    votes = np.array([[(i + k) % 2 for k in range(3)] for i in range(n)], np.uint64)
+    cvals = np.zeros((n, 3), np.uint8)
+    for i in range(n):
+        cvals[i, i % 3] = 1
+
+    def run():
+        return [a for out in (e.encrypt_bool(np.array([i & 1 for i in range(n)], np.uint8), seed=seed),
+                              e.encrypt_choice(3, cvals, single=True, seed=seed),
+                              e.encrypt_range(spec, "ciphertext_range", rvals, seed=seed),
+                              (e.encrypt_qv(ep, votes, seed=seed),),
+                              (e.encrypt(np.array([0, 1, 2**40, 7, 8, 9][:n], np.uint64), seed=seed),),
+                              e.encrypt_zero(seed=seed, n=n)) for a in out]
+    fast = run()
+    e.set_prover_mode(True)
+    try:
+        slow = run()
+    finally:
+        e.set_prover_mode(False)
+    assert len(fast) == len(slow) and all((a == b).all() for a, b in zip(fast, slow))
+    assert (e.verify_bool(slow[0], slow[1]) == 0).all()
+
+
+def check_single_choice_validation(e, pk):
+    """eg_encrypt_choice_batch(single != 0) rejects rows that do not mark exactly one option (EncryptedChoice::single cannot
+    produce them, choice.rs:288-306) instead of emitting ballots that fail verification."""
+    from elastic_elgamal_b200 import EngineError, _ffi
+    for row in ([0, 0, 0], [1, 1, 0]):
+        try:
+            e.encrypt_choice(3, np.array([[1, 0, 0], row], np.uint8), single=True, seed=W.SEED_CHOICE)
+        except EngineError as exc:
+            assert exc.status == _ffi.ERR_INVALID_ARG
+        else:
+            raise AssertionError("a malformed single-choice row was accepted")
+    e.encrypt_choice(3, np.array([[1, 1, 0]], np.uint8), single=False, seed=W.SEED_CHOICE)     # fine for MultiChoice

@@ -356,3 +356,19 @@ def test_device_pointer_forms_match_host_forms(env):
     assert (f == hfound).all() and (d_vals.cpu().numpy().view(np.uint64)[f == 1] == hvals[hfound == 1]).all()
     assert hv[1, 0] == O.CHALLENGE_MISMATCH and hv[4, 2] == O.MALFORMED and hfound[4] == 2
     table.close()
+
+
+def test_seeded_provers(env):
+    PC.check_seeded_provers(env[0], env[2], env[1], n=300)
+
+
+def test_seeded_reference_snapshots(env):
+    PC.check_seeded_reference_snapshots(env[0])
+
+
+def test_constant_time_prover_mode(env):
+    PC.check_constant_time_prover_mode(env[0], env[2], n=6)
+
+
+def test_single_choice_validation(env):
+    PC.check_single_choice_validation(env[0], env[2])

@@ -192,3 +192,19 @@ def test_fuzz_differential(env, seed):
 @pytest.mark.parametrize("shares,threshold", [(5, 3), (4, 4), (3, 1)])
 def test_keysets_validate(env, shares, threshold):
     PC.check_keysets_validate(env[0], n_sets=6, shares=shares, threshold=threshold)
+
+
+def test_seeded_provers(env):
+    PC.check_seeded_provers(env[0], env[2], env[1], n=6)
+
+
+def test_seeded_reference_snapshots(env):
+    PC.check_seeded_reference_snapshots(env[0])
+
+
+def test_constant_time_prover_mode(env):
+    PC.check_constant_time_prover_mode(env[0], env[2], n=4)
+
+
+def test_single_choice_validation(env):
+    PC.check_single_choice_validation(env[0], env[2])
