@@ -357,6 +357,25 @@ class Engine:
         self._check(self.lib.eg_encrypt_qv_batch(self.h, C.byref(p), n, _addr(votes), _addr(wide_rand), _addr(ballots)))
         return ballots
 
+    # ---- SumOfSquaresProof::verify / CandidateDecryption::verify as entry points of their own
+    def verify_sumsq(self, label, cts, sum_cts, proofs):
+        cts = _u8(cts)
+        n, m = cts.shape[0], cts.shape[1]
+        cts, sum_cts, proofs = cts.reshape(n, m, 64), _u8(sum_cts, (n, 64)), _u8(proofs, (n, 2 * m + 2, 32))
+        v = np.empty(n, np.uint8)
+        self._check(self.lib.eg_verify_sumsq_batch(self.h, label.encode(), m, n, _addr(cts), _addr(sum_cts), _addr(proofs), _addr(v)))
+        return v
+
+    def verify_decryption(self, label, key, cts, dh_elements, proofs):
+        cts = _u8(cts, (-1, 64))
+        n = cts.shape[0]
+        dh_elements, proofs = _u8(dh_elements, (n, 32)), _u8(proofs, (n, 64))
+        key = _u8(np.frombuffer(bytes(key), dtype=np.uint8), (32,))
+        v = np.empty(n, np.uint8)
+        self._check(self.lib.eg_verify_decryption_batch(self.h, label.encode(), _addr(key), n, _addr(cts), _addr(dh_elements),
+                                                        _addr(proofs), _addr(v)))
+        return v
+
     # ---- threshold decryption
     def verify_shares(self, keyset, indexes, cts, shares, proofs):
         s = len(indexes)

@@ -198,6 +198,23 @@ size_t    eg_qv_ballot_size(const eg_qv_params *params);
 eg_status eg_verify_qv_batch(eg_ctx *ctx, const eg_qv_params *params, size_t n, const uint8_t *ballots,
                              uint8_t *verdicts /* n */, uint8_t *tally /* options*64 or NULL */);
 
+/* SumOfSquaresProof::verify (src/proofs/mul.rs:190-260; benched alone at benches/basics.rs:176) over a batch: item i proves
+ * that sum_cts[i] encrypts the sum of squares of the values in its `count` ciphertexts (1..15), with `Transcript::new(label)`.
+ * Proof layout = struct field order (:86-93): challenge | (r_resp, v_resp) x count | sum_resp = 32 (2 count + 2) bytes.
+ * verdicts: EG_V_OK / EG_V_MALFORMED / EG_V_CHALLENGE_MISMATCH.  (A responses / ciphertexts count mismatch,
+ * VerificationError::LenMismatch, cannot occur in a fixed-stride batch.) */
+eg_status eg_verify_sumsq_batch(eg_ctx *ctx, const char *transcript_label, uint32_t count, size_t n, const uint8_t *cts /* n*count*64 */,
+                                const uint8_t *sum_cts /* n*64 */, const uint8_t *proofs /* n*(2 count+2)*32 */, uint8_t *verdicts /* n */);
+
+/* CandidateDecryption::verify (src/decryption.rs:189-205): item i claims that dh_elements[i] = [x]R_i for the secret key x
+ * of the public `key` (custom key, not a key-set participant), proved by a LogEqualityProof with
+ * `Transcript::new(label)` + start_proof("decryption_with_custom_key").  `key` is validated like PublicKey::from_bytes
+ * (EG_ERR_INVALID_ELEMENT).  verdicts: EG_V_OK / EG_V_MALFORMED (CandidateDecryption::from_bytes :168-177, or a
+ * non-canonical scalar) / EG_V_CHALLENGE_MISMATCH.  Needs no receiver key. */
+eg_status eg_verify_decryption_batch(eg_ctx *ctx, const char *transcript_label, const uint8_t key[32], size_t n,
+                                     const uint8_t *cts /* n*64 */, const uint8_t *dh_elements /* n*32 */,
+                                     const uint8_t *proofs /* n*64 */, uint8_t *verdicts /* n */);
+
 /* PublicKeySet (src/sharing/key_set.rs:19-26) */
 typedef struct {
     uint32_t shares, threshold;

@@ -453,6 +453,45 @@ int eo_verify_share(const eo_keyset *ks, uint32_t index, const uint8_t ctb[64], 
     return eo_logeq_verify(&base, &key_share, &dh, &t, &c, &s);
 }
 
+/* VerifiableDecryption::new with a custom key, decryption.rs:89-111: dh = [sk]R, LogEqualityProof over log base R after
+ * start_proof("decryption_with_custom_key") on Transcript::new(label). */
+int eo_decryption_prove(const uint8_t secret[32], const char *transcript_label, const uint8_t ctb[64], eo_rng *rng,
+                        uint8_t dh_out[32], uint8_t proof[64]) {
+    eo_ct ct;
+    eo_sc sk, c, s;
+    eo_pt dh, key;
+    if (!eo_ct_decode(&ct, ctb) || !eo_sc_from_canonical(&sk, secret)) return -1;
+    eo_pt_mul_generator(&key, &sk);
+    eo_pt_mul(&dh, &sk, &ct.R);
+    eo_transcript t;
+    eo_transcript_new(&t, transcript_label);
+    eo_transcript_start_proof(&t, "decryption_with_custom_key");
+    eo_pk base;
+    eo_pk_from_element(&base, &ct.R);
+    eo_logeq_prove(&base, &sk, &key, &dh, &t, rng, &c, &s);
+    eo_pt_encode(dh_out, &dh);
+    eo_sc_tobytes(proof, &c);
+    eo_sc_tobytes(proof + 32, &s);
+    return 0;
+}
+
+/* CandidateDecryption::from_bytes + ::verify, decryption.rs:168-205 */
+int eo_decryption_verify(const uint8_t key[32], const char *transcript_label, const uint8_t ctb[64], const uint8_t dh_in[32],
+                         const uint8_t proof[64]) {
+    eo_ct ct;
+    eo_pt k, dh;
+    eo_sc c, s;
+    if (!eo_pt_decode(&k, key)) return -1;
+    if (!eo_ct_decode(&ct, ctb) || !eo_pt_decode(&dh, dh_in)) return EO_MALFORMED;
+    if (!eo_sc_from_canonical(&c, proof) || !eo_sc_from_canonical(&s, proof + 32)) return EO_MALFORMED;
+    eo_transcript t;
+    eo_transcript_new(&t, transcript_label);
+    eo_transcript_start_proof(&t, "decryption_with_custom_key");
+    eo_pk base;
+    eo_pk_from_element(&base, &ct.R);
+    return eo_logeq_verify(&base, &k, &dh, &t, &c, &s);
+}
+
 static void lagrange(const uint32_t *indexes, uint32_t t, eo_sc *coeffs, eo_sc *scale) {   /* sharing/mod.rs:139-170 */
     for (uint32_t a = 0; a < t; a++) {
         int sign = 0;

@@ -207,6 +207,12 @@ int  eo_decrypt_share(const eo_keyset *ks, uint32_t index, const uint8_t secret_
 /* PublicKeySet::verify_share key_set.rs:209-228 */
 int  eo_verify_share(const eo_keyset *ks, uint32_t index, const uint8_t ct[64], const uint8_t share[32],
                      const uint8_t proof[64]);
+
+/* VerifiableDecryption::new / CandidateDecryption::verify with a custom key, decryption.rs:89-111,189-205 */
+int  eo_decryption_prove(const uint8_t secret[32], const char *transcript_label, const uint8_t ct[64], eo_rng *rng,
+                         uint8_t dh_out[32], uint8_t proof[64]);
+int  eo_decryption_verify(const uint8_t key[32], const char *transcript_label, const uint8_t ct[64], const uint8_t dh[32],
+                          const uint8_t proof[64]);
 /* lagrange_coefficients sharing/mod.rs:139-170: out coeffs t*32, scale 32 */
 void eo_lagrange_coefficients(const uint32_t *indexes, uint32_t t, uint8_t *coeffs, uint8_t scale[32]);
 /* Params::combine_shares sharing/mod.rs:302-325 + VerifiableDecryption::decrypt_to_element decryption.rs:129-131:

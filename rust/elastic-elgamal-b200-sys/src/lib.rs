@@ -100,6 +100,8 @@ extern "C" {
     pub fn eg_qv_ballot_size(params: *const eg_qv_params) -> usize;
     pub fn eg_verify_qv_batch(ctx: *mut eg_ctx, params: *const eg_qv_params, n: usize, ballots: *const u8,
                               verdicts: *mut u8, tally: *mut u8) -> eg_status;
+    pub fn eg_verify_sumsq_batch(ctx: *mut eg_ctx, transcript_label: *const c_char, count: u32, n: usize, cts: *const u8, sum_cts: *const u8, proofs: *const u8, verdicts: *mut u8) -> eg_status;
+    pub fn eg_verify_decryption_batch(ctx: *mut eg_ctx, transcript_label: *const c_char, key: *const u8, n: usize, cts: *const u8, dh_elements: *const u8, proofs: *const u8, verdicts: *mut u8) -> eg_status;
     pub fn eg_verify_shares_batch(ctx: *mut eg_ctx, keyset: *const eg_keyset, n_tallies: usize, n_shares: u32,
                                   indexes: *const u32, cts: *const u8, shares: *const u8, proofs: *const u8,
                                   verdicts: *mut u8) -> eg_status;

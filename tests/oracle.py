@@ -329,6 +329,16 @@ def verify_share(ks, index, ct, share, proof):
     return lib().eo_verify_share(C.byref(ks), index, bytes(ct), bytes(share), bytes(proof))
 
 
+def decryption_prove(secret, label, ct, rng):
+    dh, proof = buf(32), buf(64)
+    assert lib().eo_decryption_prove(bytes(secret), label.encode(), bytes(ct), C.byref(rng), dh, proof) == 0
+    return raw(dh), raw(proof)
+
+
+def decryption_verify(key, label, ct, dh, proof):
+    return lib().eo_decryption_verify(bytes(key), label.encode(), bytes(ct), bytes(dh), bytes(proof))
+
+
 def lagrange_coefficients(indexes):
     t = len(indexes)
     idx = (C.c_uint32 * t)(*indexes)

@@ -1028,3 +1028,93 @@ def check_single_choice_validation(e, pk):
         else:
             raise AssertionError("a malformed single-choice row was accepted")
     e.encrypt_choice(3, np.array([[1, 1, 0]], np.uint8), single=False, seed=W.SEED_CHOICE)     # fine for MultiChoice
+
+
+# ---------------------------------------------------------------- SumOfSquaresProof::verify / CandidateDecryption::verify
+
+def _sumsq_instance(pk, values, rng, label):
+    def enc_with_value(v):
+        peek = O.Rng.from_buffer_copy(bytes(rng))
+        r = O.scalar_reduce_wide(O.rng_block(peek))        # CiphertextWithValue::new draws exactly one block
+        return O.encrypt(pk, v, rng), r
+    sum_ct, sum_r = enc_with_value(sum(v * v for v in values))
+    pairs = [enc_with_value(v) for v in values]
+    proof = O.sumsq_prove(pk, [p[0] for p in pairs], [v.to_bytes(32, "little") for v in values], [p[1] for p in pairs], sum_ct, sum_r,
+                          label, rng)
+    return b"".join(p[0] for p in pairs), sum_ct, proof
+
+
+def check_verify_sumsq(e, pk, n=16, count=5, label="test", seed=b"\x0d" * 32):
+    """eg_verify_sumsq_batch against the oracle's SumOfSquaresProof::verify, with the reference's tamper patterns
+    (mul.rs:332-361,418-437): responses of another proof, a swapped ciphertext, a wrong sum ciphertext, a wrong label."""
+    rng = O.rng_from_seed(seed)
+    rnd = random.Random(count)
+    rows = [_sumsq_instance(pk, [rnd.randrange(6) for _ in range(count)], rng, label) for _ in range(n)]
+    cts = np.frombuffer(b"".join(r[0] for r in rows), np.uint8).reshape(n, count, 64).copy()
+    sums = np.frombuffer(b"".join(r[1] for r in rows), np.uint8).reshape(n, 64).copy()
+    proofs = np.frombuffer(b"".join(r[2] for r in rows), np.uint8).reshape(n, 2 * count + 2, 32).copy()
+    if n >= 8:
+        proofs[1] = proofs[2]
+        cts[3, 0], cts[3, 1] = cts[3, 1].copy(), cts[3, 0].copy()
+        sums[4] = sums[5]
+        proofs[6, 2] = np.frombuffer(W.BAD_SCALAR, np.uint8)
+        cts[7, 0, :32] = np.frombuffer(W.BAD_POINT2, np.uint8)
+    expected = [O.sumsq_verify(pk, [bytes(c) for c in cts[i]], bytes(sums[i]), label, bytes(proofs[i].reshape(-1))) for i in range(n)]
+    got = e.verify_sumsq(label, cts, sums, proofs)
+    assert got.tolist() == expected, (got.tolist(), expected)
+    if n >= 8:
+        assert expected[0] == O.OK and expected[1] == O.CHALLENGE_MISMATCH and expected[6] == O.MALFORMED and expected[7] == O.MALFORMED
+        assert expected[3] in (O.OK, O.CHALLENGE_MISMATCH)      # swapping two equal votes' ciphertexts is still a valid statement
+    assert (e.verify_sumsq(label + "x", cts, sums, proofs) != 0).all()
+    assert e.verify_sumsq(label, cts[:0], sums[:0], proofs[:0]).shape == (0,)
+
+
+def check_verify_sumsq_reference_snapshot(e):
+    """The reference's `sum-sq-proof` snapshot (tests/snapshots.rs:132-151: values [1, 3, 3, 7, 5], seed 12345) verifies."""
+    g = _gold()["sum-sq-proof"]
+    rng = O.rng_from_u64(12345)
+    sk, pk = O.keypair(rng)
+    cts, sum_ct, proof = _sumsq_instance(pk, [1, 3, 3, 7, 5], rng, "test")
+    hx = bytes.fromhex
+    assert proof == hx(g["challenge"]) + b"".join(hx(x) for x in g["ciphertext_responses"]) + hx(g["sum_response"])
+    try:
+        e.set_receiver(pk)
+        v = e.verify_sumsq("test", np.frombuffer(cts, np.uint8).reshape(1, 5, 64), np.frombuffer(sum_ct, np.uint8).reshape(1, 64),
+                           np.frombuffer(proof, np.uint8).reshape(1, 12, 32))
+        assert v.tolist() == [0]
+    finally:
+        e.set_receiver(W.receiver()[1])
+
+
+def check_verify_decryption(e, n=14, label="custom_key_decryption", seed=b"\x0e" * 32):
+    """eg_verify_decryption_batch (CandidateDecryption::verify with a custom key, decryption.rs:189-205) against the oracle."""
+    from elastic_elgamal_b200 import EngineError, _ffi
+    rng = O.rng_from_seed(seed)
+    sk, pk = O.keypair(rng)
+    sk2, pk2 = O.keypair(rng)
+    cts = [O.encrypt(pk2, 3 * i, rng) for i in range(n)]
+    rows = [O.decryption_prove(sk, label, ct, rng) for ct in cts]
+    cts_a = np.frombuffer(b"".join(cts), np.uint8).reshape(n, 64).copy()
+    dh_a = np.frombuffer(b"".join(r[0] for r in rows), np.uint8).reshape(n, 32).copy()
+    pr_a = np.frombuffer(b"".join(r[1] for r in rows), np.uint8).reshape(n, 64).copy()
+    if n >= 8:
+        pr_a[1] = pr_a[2]                                             # proof of another ciphertext
+        dh_a[3] = dh_a[4]                                             # decryption of another ciphertext
+        dh_a[5] = np.frombuffer(W.BAD_POINT, np.uint8)                # CandidateDecryption::from_bytes -> None
+        pr_a[6, 32:] = np.frombuffer(W.BAD_SCALAR2, np.uint8)
+        cts_a[7, 32:] = np.frombuffer(O.point_add(bytes(cts_a[7, 32:]), W.G_ENC), np.uint8)     # B is not committed: still verifies
+    expected = [O.decryption_verify(pk, label, bytes(cts_a[i]), bytes(dh_a[i]), bytes(pr_a[i])) for i in range(n)]
+    got = e.verify_decryption(label, pk, cts_a, dh_a, pr_a)
+    assert got.tolist() == expected, (got.tolist(), expected)
+    if n >= 8:
+        assert expected[0] == O.OK and expected[1] == O.CHALLENGE_MISMATCH and expected[3] == O.CHALLENGE_MISMATCH
+        assert expected[5] == O.MALFORMED and expected[6] == O.MALFORMED and expected[7] == O.OK
+    assert (e.verify_decryption(label, pk2, cts_a, dh_a, pr_a) != 0).all()          # another key
+    assert (e.verify_decryption(label + "2", pk, cts_a, dh_a, pr_a) != 0).all()     # another transcript
+    for bad in (W.BAD_POINT, bytes(32)):                                           # undecodable / identity key
+        try:
+            e.verify_decryption(label, bad, cts_a, dh_a, pr_a)
+        except EngineError as exc:
+            assert exc.status == _ffi.ERR_INVALID_ELEMENT
+        else:
+            raise AssertionError("an invalid key was accepted")

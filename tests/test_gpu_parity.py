@@ -372,3 +372,16 @@ def test_constant_time_prover_mode(env):
 
 def test_single_choice_validation(env):
     PC.check_single_choice_validation(env[0], env[2])
+
+
+@pytest.mark.parametrize("count", [1, 5, 15])
+def test_verify_sumsq(env, count):
+    PC.check_verify_sumsq(env[0], env[2], n=60, count=count)
+
+
+def test_verify_sumsq_reference_snapshot(env):
+    PC.check_verify_sumsq_reference_snapshot(env[0])
+
+
+def test_verify_decryption_custom_key(env):
+    PC.check_verify_decryption(env[0], n=200)

@@ -208,3 +208,15 @@ def test_constant_time_prover_mode(env):
 
 def test_single_choice_validation(env):
     PC.check_single_choice_validation(env[0], env[2])
+
+
+def test_verify_sumsq(env):
+    PC.check_verify_sumsq(env[0], env[2], n=9, count=3)
+
+
+def test_verify_sumsq_reference_snapshot(env):
+    PC.check_verify_sumsq_reference_snapshot(env[0])
+
+
+def test_verify_decryption_custom_key(env):
+    PC.check_verify_decryption(env[0], n=9)
