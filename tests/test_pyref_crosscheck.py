@@ -87,7 +87,7 @@ def test_keyset_from_participants_oracle_equals_pyref():
         assert v == ov == R.OK and shared == oshared == bytes(ks.shared_key)
         if 1 < threshold < shares:            # (threshold 1: a constant polynomial, all participant keys are equal)
             swapped = keys[:]
-            swapped[-1], swapped[0] = swapped[0], swapped[-1]
+            swapped[-1] = swapped[0]              # (a plain swap of the end points of a line is again a line)
             assert R.keyset_from_participants(shares, threshold, swapped)[0] == O.keyset_from_participants(shares, threshold, swapped)[0] \
                 == R.MALFORMED_PARTICIPANT_KEYS
         broken = keys[:]
