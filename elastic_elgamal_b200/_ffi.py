@@ -11,6 +11,8 @@ SUCCESS, ERR_INVALID_ARG, ERR_INVALID_ELEMENT, ERR_IDENTITY_KEY, ERR_NO_RECEIVER
 STATUS_NAMES = ["SUCCESS", "ERR_INVALID_ARG", "ERR_INVALID_ELEMENT", "ERR_IDENTITY_KEY", "ERR_NO_RECEIVER",
                 "ERR_NO_DEVICE", "ERR_CUDA", "ERR_OUT_OF_MEMORY", "ERR_LEN_MISMATCH", "ERR_NCCL"]
 COMM_ID_BYTES = 128
+WIRE_CIPHERTEXT, WIRE_DECRYPTION, WIRE_LOG_EQUALITY_PROOF, WIRE_COMMITMENT_EQUIV_PROOF, WIRE_RING_PROOF, WIRE_POSSESSION_PROOF, \
+    WIRE_SUMSQ_PROOF = range(7)
 
 V_OK, V_MALFORMED, V_CHALLENGE_MISMATCH, V_CHOICE_SUM, V_CHOICE_RANGE, V_QV_CREDIT_RANGE, V_QV_CREDIT_EQUIV, \
     V_MALFORMED_PARTICIPANT_KEYS = range(8)
@@ -59,6 +61,9 @@ PROTOTYPES = {
     "eg_base64url_encode_batch": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_size_t, P8, P8]),
     "eg_base64url_decode_batch_dev": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_size_t, P8, P8, P8]),
     "eg_base64url_encode_batch_dev": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_size_t, P8, P8]),
+    "eg_wire_fields": (C.c_size_t, [C.c_int, C.c_uint32]),
+    "eg_wire_decode_batch": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_size_t, P8, P8, P8]),
+    "eg_wire_encode_batch": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_size_t, P8, P8]),
     "eg_elements_validate": (C.c_int32, [C.c_void_p, C.c_size_t, P8, P8]),
     "eg_scalars_validate": (C.c_int32, [C.c_void_p, C.c_size_t, P8, P8]),
     "eg_scalars_from_wide": (C.c_int32, [C.c_void_p, C.c_size_t, P8, P8]),

@@ -1382,6 +1382,8 @@ struct b64_params {
     uint8_t *text;
     uint8_t *raw;
     uint8_t *ok;                        // decode only: pre-set to 1, cleared by any failing group
+    uint32_t ok_group;                  // strings per object (0 = 1): ok[item / ok_group] -- struct-level decoding, every
+                                        // field of an object must decode
 };
 
 EG_HD void b64url_decode_body(const b64_params &P, size_t tid) {
@@ -1398,7 +1400,7 @@ EG_HD void b64url_decode_body(const b64_params &P, size_t tid) {
     if (nc == 3) good = good && (x & 0xffu) == 0;        // 2 unused bits of the third character
     const uint32_t nb = nc - 1;
     for (uint32_t k = 0; k < nb; k++) dst[k] = (uint8_t)(x >> (16 - 8 * k));
-    if (!good) P.ok[item] = 0;
+    if (!good) P.ok[P.ok_group > 1 ? item / P.ok_group : item] = 0;
 }
 
 EG_HD void b64url_encode_body(const b64_params &P, size_t tid) {

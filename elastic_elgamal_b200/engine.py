@@ -141,6 +141,26 @@ class Engine:
         self._check(self.lib.eg_base64url_encode_batch(self.h, n, b, _addr(raw), _addr(text)))
         return text
 
+    # ---- struct-level wire format: objects of F base64url fields of 43 characters (serde.rs:179-355)
+    def wire_fields(self, kind, count=0):
+        return self.lib.eg_wire_fields(kind, count)
+
+    def wire_decode(self, text, fields):
+        if fields == 0:     # a vector below the reference's minimum length: the library reports EG_ERR_LEN_MISMATCH
+            self._check(self.lib.eg_wire_decode_batch(self.h, 0, 1, None, None, None))
+        text = _u8(text, (-1, fields * 43))
+        n = text.shape[0]
+        raw, ok = np.empty((n, fields * 32), np.uint8), np.empty(n, np.uint8)
+        self._check(self.lib.eg_wire_decode_batch(self.h, fields, n, _addr(text), _addr(raw), _addr(ok)))
+        return raw, ok.astype(bool)
+
+    def wire_encode(self, raw, fields):
+        raw = _u8(raw, (-1, fields * 32))
+        n = raw.shape[0]
+        text = np.empty((n, fields * 43), np.uint8)
+        self._check(self.lib.eg_wire_encode_batch(self.h, fields, n, _addr(raw), _addr(text)))
+        return text
+
     # ---- group helpers
     def elements_validate(self, enc):
         enc = _u8(enc, (-1, 32))

@@ -145,6 +145,28 @@ eg_status eg_base64url_decode_batch_dev(eg_ctx *ctx, size_t n, size_t bytes_per_
                                         uint8_t *d_ok);
 eg_status eg_base64url_encode_batch_dev(eg_ctx *ctx, size_t n, size_t bytes_per_item, const uint8_t *d_raw, char *d_text);
 
+/* Struct-level form of the same wire format.  An object is F fields = F strings of 43 characters (every field is a 32-byte
+ * element or scalar), concatenated in struct-field order -- which is also the order of the flat binary layouts this header
+ * uses, so the decoded bytes feed the batch entry points directly.  eg_wire_fields gives F for the objects whose vectors
+ * carry a minimum length in the reference (`VecHelper<_, MIN>`, src/serde.rs:303-355) and returns 0 when `count` violates
+ * it -- the reference fails deserialisation there with `invalid_length`; composite objects (RangeProof = (n_rings - 1)
+ * ciphertexts + a ring proof, EncryptedChoice, QuadraticVotingBallot) are sums of these.  ok[i] = 1 iff all F strings of
+ * object i are valid base64url; fields_per_object == 0 is EG_ERR_LEN_MISMATCH. */
+enum {
+    EG_WIRE_CIPHERTEXT = 0,             /* 2 fields */
+    EG_WIRE_DECRYPTION = 1,             /* VerifiableDecryption: 1 field */
+    EG_WIRE_LOG_EQUALITY_PROOF = 2,     /* 2 fields */
+    EG_WIRE_COMMITMENT_EQUIV_PROOF = 3, /* 4 fields */
+    EG_WIRE_RING_PROOF = 4,             /* 1 + count responses, count >= 2 (src/proofs/ring.rs:285) */
+    EG_WIRE_POSSESSION_PROOF = 5,       /* 1 + count responses, count >= 1 (src/proofs/possession.rs:74) */
+    EG_WIRE_SUMSQ_PROOF = 6             /* 1 + count ciphertext responses + 1, count >= 2 (src/proofs/mul.rs:89) */
+};
+size_t    eg_wire_fields(int kind, uint32_t count);
+eg_status eg_wire_decode_batch(eg_ctx *ctx, size_t fields_per_object, size_t n, const char *text /* n*F*43 */,
+                               uint8_t *raw /* n*F*32 */, uint8_t *ok /* n */);
+eg_status eg_wire_encode_batch(eg_ctx *ctx, size_t fields_per_object, size_t n, const uint8_t *raw /* n*F*32 */,
+                               char *text /* n*F*43 */);
+
 /* ---- proofs and applications ------------------------------------------------------------------- */
 
 /* PublicKey::verify_zero (src/keys/impls.rs:59-69) -> LogEqualityProof::verify (src/proofs/log_equality.rs:153-180) */

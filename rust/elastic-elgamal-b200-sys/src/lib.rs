@@ -30,6 +30,14 @@ pub const EG_ERR_NCCL: eg_status = 9;
 /// Size of the NCCL unique id exchanged by `eg_comm_unique_id` / `eg_ctx_attach_comm`.
 pub const EG_COMM_ID_BYTES: usize = 128;
 
+pub const EG_WIRE_CIPHERTEXT: c_int = 0;
+pub const EG_WIRE_DECRYPTION: c_int = 1;
+pub const EG_WIRE_LOG_EQUALITY_PROOF: c_int = 2;
+pub const EG_WIRE_COMMITMENT_EQUIV_PROOF: c_int = 3;
+pub const EG_WIRE_RING_PROOF: c_int = 4;
+pub const EG_WIRE_POSSESSION_PROOF: c_int = 5;
+pub const EG_WIRE_SUMSQ_PROOF: c_int = 6;
+
 pub const EG_V_OK: u8 = 0;
 pub const EG_V_MALFORMED: u8 = 1;
 pub const EG_V_CHALLENGE_MISMATCH: u8 = 2;
@@ -79,6 +87,9 @@ extern "C" {
     pub fn eg_version() -> *const c_char;
     pub fn eg_ctx_set_receiver(ctx: *mut eg_ctx, key: *const u8) -> eg_status;
 
+    pub fn eg_wire_fields(kind: c_int, count: u32) -> usize;
+    pub fn eg_wire_decode_batch(ctx: *mut eg_ctx, fields_per_object: usize, n: usize, text: *const c_char, raw: *mut u8, ok: *mut u8) -> eg_status;
+    pub fn eg_wire_encode_batch(ctx: *mut eg_ctx, fields_per_object: usize, n: usize, raw: *const u8, text: *mut c_char) -> eg_status;
     pub fn eg_elements_validate(ctx: *mut eg_ctx, n: usize, encodings: *const u8, ok: *mut u8) -> eg_status;
     pub fn eg_scalars_validate(ctx: *mut eg_ctx, n: usize, scalars: *const u8, ok: *mut u8) -> eg_status;
     pub fn eg_scalars_from_wide(ctx: *mut eg_ctx, n: usize, wide: *const u8, scalars: *mut u8) -> eg_status;

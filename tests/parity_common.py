@@ -1118,3 +1118,54 @@ def check_verify_decryption(e, n=14, label="custom_key_decryption", seed=b"\x0e"
             assert exc.status == _ffi.ERR_INVALID_ELEMENT
         else:
             raise AssertionError("an invalid key was accepted")
+
+
+# ---------------------------------------------------------------- struct-level wire format (VecHelper bounds)
+
+def check_wire_objects(e, pk):
+    """eg_wire_fields / eg_wire_decode_batch: the base64url strings of the reference's own human-readable snapshots
+    (tests/snapshots/*.snap, held in tests/golden/) decode, object by object, to the flat layouts the batch entry points
+    take -- and those verify; the VecHelper minimum lengths (serde.rs:303-355) are enforced; one bad field rejects its
+    whole object."""
+    import base64
+    from elastic_elgamal_b200 import EngineError, _ffi
+    F = e.wire_fields
+    assert F(_ffi.WIRE_CIPHERTEXT) == 2 and F(_ffi.WIRE_LOG_EQUALITY_PROOF) == 2 and F(_ffi.WIRE_DECRYPTION) == 1
+    assert F(_ffi.WIRE_COMMITMENT_EQUIV_PROOF) == 4
+    assert [F(_ffi.WIRE_RING_PROOF, c) for c in (0, 1, 2, 10)] == [0, 0, 3, 11]             # ring.rs:285: at least 2 scalars
+    assert [F(_ffi.WIRE_POSSESSION_PROOF, c) for c in (0, 1, 5)] == [0, 2, 6]              # possession.rs:74: at least 1
+    assert [F(_ffi.WIRE_SUMSQ_PROOF, c) for c in (0, 1, 2, 10)] == [0, 0, 4, 12]           # mul.rs:89: at least 2
+    assert F(99, 5) == 0
+    try:
+        e.wire_decode(np.zeros((1, 0), np.uint8), 0)
+    except EngineError as exc:
+        assert exc.status == _ffi.ERR_LEN_MISMATCH
+    else:
+        raise AssertionError("zero fields accepted")
+
+    def b64(hexstr):
+        return base64.urlsafe_b64encode(bytes.fromhex(hexstr)).rstrip(b"=")
+    gold = _gold()
+    g = gold["encrypted-choice"]
+    # EncryptedChoice (5 options) = 5 ciphertexts + ring proof (10 responses) + log-equality proof: 10 + 11 + 2 fields
+    fields = 5 * F(_ffi.WIRE_CIPHERTEXT) + F(_ffi.WIRE_RING_PROOF, 10) + F(_ffi.WIRE_LOG_EQUALITY_PROOF)
+    strings = ([s for c in g["choices"] for s in (b64(c["random_element"]), b64(c["blinded_element"]))]
+               + [b64(g["range_proof"]["common_challenge"])] + [b64(x) for x in g["range_proof"]["ring_responses"]]
+               + [b64(g["sum_proof"]["challenge"]), b64(g["sum_proof"]["response"])])
+    assert len(strings) == fields == 23 and all(len(s) == 43 for s in strings)
+    text = np.frombuffer(b"".join(strings), np.uint8).reshape(1, fields * 43)
+    batch = np.tile(text, (4, 1)).copy()
+    batch[1, 43 * 7 + 5] = ord("=")                  # padding inside field 7 of object 1
+    batch[2, 43 * 22 + 42] = ord("B")                # non-zero trailing bits in the last field of object 2
+    raw, ok = e.wire_decode(batch, fields)
+    assert ok.tolist() == [True, False, False, True]
+    assert (e.wire_encode(raw[[0, 3]], fields) == batch[[0, 3]]).all()
+    rng = O.rng_from_u64(12345)
+    sk, snap_pk = O.keypair(rng)
+    try:
+        e.set_receiver(snap_pk)
+        obj = raw[[0, 3]]
+        v, t = e.verify_choice(5, obj[:, :320], obj[:, 320:672], obj[:, 672:])
+        assert v.tolist() == [0, 0]
+    finally:
+        e.set_receiver(pk)

@@ -220,3 +220,7 @@ def test_verify_sumsq_reference_snapshot(env):
 
 def test_verify_decryption_custom_key(env):
     PC.check_verify_decryption(env[0], n=9)
+
+
+def test_wire_objects(env):
+    PC.check_wire_objects(env[0], env[2])
