@@ -107,6 +107,8 @@ PROTOTYPES = {
     "eg_ctx_set_prover_mode": (C.c_int32, [C.c_void_p, C.c_int]),
     "eg_range_prover_draws": (C.c_size_t, [C.POINTER(Range)]),
     "eg_encrypt_range_batch": (C.c_int32, [C.c_void_p, C.POINTER(Range), C.c_char_p, C.c_size_t, P8, P8, P8, P8, P8]),
+    "eg_prove_range_batch": (C.c_int32, [C.c_void_p, C.POINTER(Range), C.c_char_p, C.c_size_t, P8, P8, P8, P8, P8, P8]),
+    "eg_prove_range_batch_seeded": (C.c_int32, [C.c_void_p, C.POINTER(Range), C.c_char_p, C.c_size_t, P8, P8, P8, C.c_uint64, P8, P8, P8]),
     "eg_qv_prover_draws": (C.c_size_t, [C.POINTER(QvParams)]),
     "eg_encrypt_qv_batch": (C.c_int32, [C.c_void_p, C.POINTER(QvParams), C.c_size_t, P8, P8, P8]),
     "eg_kernel_launch_count": (C.c_uint64, [C.c_void_p]),

@@ -723,6 +723,9 @@ struct rprove_params {
     const uint32_t *table_g, *table_k;
     rand_src rnd;                                    // seeded: the item's stream is the RECORD's stream (group > 1: item / group),
                                                      // its blocks start at rnd.block0 + (item % group) * wide_inner / 64
+    const uint8_t *ct_r;                             // RangeProof::from_ciphertext (range.rs:482-534): the main ciphertext exists
+                                                     // already; its randomness (canonical scalar, 32 B per item) replaces draw 0
+                                                     // and the remaining draws move up by one.  Flat batches only (group <= 1).
 };
 
 EG_HD size_t rprove_off(const rprove_params &P, size_t item, size_t stride, size_t inner) {
@@ -731,6 +734,14 @@ EG_HD size_t rprove_off(const rprove_params &P, size_t item, size_t stride, size
 
 EG_HD void rprove_draw(sc &out, const rprove_params &P, size_t item, uint32_t pos) {
     uint32_t w[16];
+    if (P.ct_r) {
+        if (pos == 0) {
+            load32_bytes(w, P.ct_r + item * 32);
+            if (!sc_from_words(out, w)) out = sc_zero();      // (validated on the host)
+            return;
+        }
+        pos -= 1;
+    }
     if (P.rnd.seeded) {
         const size_t record = P.group > 1 ? item / P.group : item;
         const uint32_t inner = P.group > 1 ? (uint32_t)((item % P.group) * (P.wide_inner / 64)) : 0u;
@@ -780,10 +791,13 @@ EG_HD void rprove_ring1_body(const rprove_params &P, size_t item, uint32_t slot,
     if (slot == Rn) {
         sc r;
         rprove_draw(r, P, item, 0);
+        if (!P.ct_out && !P.ct_sec) return;           // from_ciphertext without the optional re-encryption
         rprove_encrypt(enc_ct, r, value, tab_g, tab_k, P.rnd.ct != 0);
-        uint8_t *o = P.ct_out + rprove_off(P, item, P.ct_stride, P.out_inner);
-        store32_bytes(o, enc_ct);
-        store32_bytes(o + 32, enc_ct + 8);
+        if (P.ct_out) {
+            uint8_t *o = P.ct_out + rprove_off(P, item, P.ct_stride, P.out_inner);
+            store32_bytes(o, enc_ct);
+            store32_bytes(o + 32, enc_ct + 8);
+        }
         if (P.ct_sec) planar_store_words(P.ct_sec, P.n, 0, 8, item, r.v);
         return;
     }

@@ -346,6 +346,25 @@ class Engine:
                                                     _addr(cts), _addr(partials) if rng.n_rings > 1 else None, _addr(rings)))
         return cts, partials, rings
 
+    def prove_range(self, rng, label, values, ct_randomness, wide_rand=None, seed=None, counter_base=0, want_cts=True):
+        """RangeProof::from_ciphertext: proofs for existing ciphertexts with known values and randomness."""
+        values = np.ascontiguousarray(values, dtype=np.uint64).reshape(-1)
+        n = values.shape[0]
+        ct_randomness = _u8(ct_randomness, (n, 32))
+        draws = self.lib.eg_range_prover_draws(C.byref(rng)) - 1
+        cts = np.empty((n, 64), np.uint8) if want_cts else None
+        partials = np.empty((n, max(0, rng.n_rings - 1), 64), np.uint8)
+        rings = np.empty((n, 1 + rng.rings_size, 32), np.uint8)
+        pp = _addr(partials) if rng.n_rings > 1 else None
+        if seed is not None:
+            self._check(self.lib.eg_prove_range_batch_seeded(self.h, C.byref(rng), label.encode(), n, _addr(values), _addr(ct_randomness),
+                                                             _addr(self._seed(seed)), counter_base, _addr(cts), pp, _addr(rings)))
+        else:
+            wide_rand = _u8(wide_rand, (n, draws, 64))
+            self._check(self.lib.eg_prove_range_batch(self.h, C.byref(rng), label.encode(), n, _addr(values), _addr(ct_randomness),
+                                                      _addr(wide_rand), _addr(cts), pp, _addr(rings)))
+        return cts, partials, rings
+
     # ---- QuadraticVotingBallot
     def qv_params(self, options, credits):
         p = _ffi.QvParams()

@@ -330,6 +330,14 @@ eg_status eg_encrypt_range_batch(eg_ctx *ctx, const eg_range *range, const char 
                                  uint8_t *cts /* n*64 */, uint8_t *partials /* n*(n_rings-1)*64 */,
                                  uint8_t *ring_proofs /* n*(1+sum sizes)*32 */);
 
+/* RangeProof::from_ciphertext (src/proofs/range.rs:482-534): proofs for ciphertexts that exist already (made with
+ * CiphertextWithValue::new / eg_encrypt_batch), whose values and randomness the caller holds.  ct_randomness = one canonical
+ * scalar per item (EG_ERR_INVALID_ARG otherwise); item i consumes eg_range_prover_draws(range) - 1 blocks, in the order
+ * above without its first block.  cts (optional, may be NULL) receives the re-encryption ([r]G, [v]G + [r]K) for checking. */
+eg_status eg_prove_range_batch(eg_ctx *ctx, const eg_range *range, const char *transcript_label, size_t n, const uint64_t *values /* n */,
+                               const uint8_t *ct_randomness /* n*32 */, const uint8_t *wide_rand /* n*(draws-1)*64 */,
+                               uint8_t *cts /* n*64 or NULL */, uint8_t *partials, uint8_t *ring_proofs);
+
 /* QuadraticVotingBallot::new (src/app/quadratic_voting.rs:234-284).  votes[i*options + k] = votes of ballot i for
  * option k.  Item i consumes eg_qv_prover_draws(params) blocks: one RangeProof::new per option over the vote range, one for
  * credit = sum votes^2 over the credit range, then SumOfSquaresProof::new (src/proofs/mul.rs:107-181: e_z, then e_r, e_x per
@@ -361,6 +369,9 @@ eg_status eg_encrypt_choice_batch_seeded(eg_ctx *ctx, size_t n, uint32_t options
 eg_status eg_encrypt_range_batch_seeded(eg_ctx *ctx, const eg_range *range, const char *transcript_label, size_t n,
                                         const uint64_t *values, const uint8_t seed[32], uint64_t counter_base, uint8_t *cts,
                                         uint8_t *partials, uint8_t *ring_proofs);
+eg_status eg_prove_range_batch_seeded(eg_ctx *ctx, const eg_range *range, const char *transcript_label, size_t n, const uint64_t *values,
+                                      const uint8_t *ct_randomness /* n*32 */, const uint8_t seed[32], uint64_t counter_base,
+                                      uint8_t *cts /* or NULL */, uint8_t *partials, uint8_t *ring_proofs);
 eg_status eg_encrypt_qv_batch_seeded(eg_ctx *ctx, const eg_qv_params *params, size_t n, const uint64_t *votes, const uint8_t seed[32],
                                      uint64_t counter_base, uint8_t *ballots);
 

@@ -174,6 +174,8 @@ extern "C" {
     pub fn eg_encrypt_range_batch(ctx: *mut eg_ctx, range: *const eg_range, transcript_label: *const c_char, n: usize,
                                   values: *const u64, wide_rand: *const u8, cts: *mut u8, partials: *mut u8,
                                   ring_proofs: *mut u8) -> eg_status;
+    pub fn eg_prove_range_batch(ctx: *mut eg_ctx, range: *const eg_range, transcript_label: *const c_char, n: usize, values: *const u64, ct_randomness: *const u8, wide_rand: *const u8, cts: *mut u8, partials: *mut u8, ring_proofs: *mut u8) -> eg_status;
+    pub fn eg_prove_range_batch_seeded(ctx: *mut eg_ctx, range: *const eg_range, transcript_label: *const c_char, n: usize, values: *const u64, ct_randomness: *const u8, seed: *const u8, counter_base: u64, cts: *mut u8, partials: *mut u8, ring_proofs: *mut u8) -> eg_status;
     pub fn eg_qv_prover_draws(params: *const eg_qv_params) -> usize;
     pub fn eg_encrypt_qv_batch(ctx: *mut eg_ctx, params: *const eg_qv_params, n: usize, votes: *const u64,
                                wide_rand: *const u8, ballots: *mut u8) -> eg_status;

@@ -1055,7 +1055,8 @@ def check_verify_sumsq(e, pk, n=16, count=5, label="test", seed=b"\x0d" * 32):
     proofs = np.frombuffer(b"".join(r[2] for r in rows), np.uint8).reshape(n, 2 * count + 2, 32).copy()
     if n >= 8:
         proofs[1] = proofs[2]
-        cts[3, 0], cts[3, 1] = cts[3, 1].copy(), cts[3, 0].copy()
+        if count >= 2:
+            cts[3, 0], cts[3, 1] = cts[3, 1].copy(), cts[3, 0].copy()
         sums[4] = sums[5]
         proofs[6, 2] = np.frombuffer(W.BAD_SCALAR, np.uint8)
         cts[7, 0, :32] = np.frombuffer(W.BAD_POINT2, np.uint8)
@@ -1169,3 +1170,31 @@ def check_wire_objects(e, pk):
         assert v.tolist() == [0, 0]
     finally:
         e.set_receiver(pk)
+
+
+def check_prove_range_from_ciphertext(e, pk, upper_bound=100, n=9, label="ciphertext_range", seed=b"\x0f" * 32):
+    """eg_prove_range_batch (RangeProof::from_ciphertext, range.rs:482-534): given the randomness RangeProof::new would have
+    drawn for the ciphertext (block 0 of the item's stream) and the remaining blocks, the proof is byte-identical to
+    RangeProof::new's -- which is `CiphertextWithValue::new` followed by `from_ciphertext` (range.rs:462-473)."""
+    spec = O.range_optimal(upper_bound)
+    espec = to_engine_range(e, spec)
+    values = np.array([(37 * i) % upper_bound for i in range(n)], np.uint64)
+    oc, op, orr = O.gen_range_batch(pk, spec, label, seed, values)
+    draws = e.lib.eg_range_prover_draws(O.C.byref(espec))
+    blocks = [item_blocks(seed, i, draws) for i in range(n)]
+    ct_r = np.frombuffer(b"".join(O.scalar_reduce_wide(b[:64]) for b in blocks), np.uint8).reshape(n, 32)
+    wide = np.frombuffer(b"".join(b[64:] for b in blocks), np.uint8)
+    c, p, r = e.prove_range(espec, label, values, ct_r, wide)
+    assert (c == oc).all() and (p == op).all() and (r == orr).all()
+    c2, p2, r2 = e.prove_range(espec, label, values, ct_r, seed=seed, counter_base=1, want_cts=False)      # draws start at block 1
+    assert c2 is None and (p2 == op).all() and (r2 == orr).all()
+    assert (e.verify_range(espec, label, oc, p2, r2) == 0).all()
+    from elastic_elgamal_b200 import EngineError, _ffi
+    bad = ct_r.copy()
+    bad[0] = np.frombuffer(W.BAD_SCALAR, np.uint8)
+    try:
+        e.prove_range(espec, label, values, bad, wide)
+    except EngineError as exc:
+        assert exc.status == _ffi.ERR_INVALID_ARG
+    else:
+        raise AssertionError("non-canonical ciphertext randomness accepted")

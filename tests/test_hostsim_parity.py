@@ -224,3 +224,8 @@ def test_verify_decryption_custom_key(env):
 
 def test_wire_objects(env):
     PC.check_wire_objects(env[0], env[2])
+
+
+@pytest.mark.parametrize("ub", [5, 100])
+def test_prove_range_from_ciphertext(env, ub):
+    PC.check_prove_range_from_ciphertext(env[0], env[2], ub, n=5)
