@@ -69,3 +69,14 @@ def test_multi_launch_counts_accumulate(env):
     before = e.kernel_launches
     PC.check_verify_bool(e, env[2], n=24)
     assert e.kernel_launches > before
+
+
+def test_multi_provers_shard_with_their_own_randomness(env):
+    """Provers on a multi-device context: item i keeps block stream i (seeded) / its own slice of the caller's blocks, so the
+    outputs are byte-identical to the oracle's whatever the device count."""
+    PC.check_seeded_provers(env[0], env[2], env[1], n=7)
+    PC.check_encrypt_choice(env[0], env[2], options=3, n=7)
+    PC.check_encrypt_range(env[0], env[2], 21, n=5)
+    PC.check_encrypt_qv(env[0], env[2], env[1], n=4, options=3, credits=9)
+    PC.check_encrypt_plain_and_zero(env[0], env[2], env[1], n=7)
+    PC.check_prove_range_from_ciphertext(env[0], env[2], 21, n=5)
