@@ -3,10 +3,12 @@
 // (src/encryption.rs:96), RingProof (src/proofs/ring.rs:282), LogEqualityProof (src/proofs/log_equality.rs:96),
 // EncryptedChoice / ChoiceParams (src/app/choice.rs:276,132).  Objects are the reference's `to_bytes` forms.
 #pragma once
+#include <algorithm>
 #include <array>
 #include <cstdint>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "eg_b200.h"
@@ -42,6 +44,16 @@ struct ChoiceParams { PublicKey receiver; uint32_t options_count; bool single; }
 struct EncryptedChoice { std::vector<Ciphertext> choices; RingProof range_proof; LogEqualityProof sum_proof; };
 
 struct ChoiceBatchResult { std::vector<Verdict> verdicts; std::vector<Ciphertext> tally; };
+// src/proofs/mul.rs:86-93
+struct SumOfSquaresProof { Scalar challenge; std::vector<Scalar> ciphertext_responses; Scalar sum_response; };
+// src/app/quadratic_voting.rs:205-217 (CiphertextWithRangeProof = ciphertext + range proof)
+struct CiphertextWithRangeProof { Ciphertext ciphertext; RangeProof range_proof; };
+struct QuadraticVotingBallot { std::vector<CiphertextWithRangeProof> votes; CiphertextWithRangeProof credit; SumOfSquaresProof credit_equivalence_proof; };
+// src/sharing/key_set.rs:19-26
+struct PublicKeySet { uint32_t shares, threshold; PublicKey shared_key; std::vector<PublicKey> participant_keys; };
+// 32-byte ChaCha20 key + block counter base for the provers that generate their randomness in the kernel (eg_*_batch_seeded)
+struct Seed { std::array<uint8_t, 32> key; uint64_t counter_base = 0; };
+struct DecryptedValue { bool found; uint64_t value; };       // Option<u64> of DiscreteLogTable::get
 
 class Engine {
   public:
@@ -49,7 +61,24 @@ class Engine {
         eg_status st = eg_ctx_create(device, &ctx_);
         if (st != EG_SUCCESS) throw Error(st, "eg_ctx_create failed: no CUDA device (the engine has no CPU fallback)");
     }
-    ~Engine() { eg_ctx_destroy(ctx_); }
+    // one process, several GPUs: batches shard across them and tallies are combined inside the library (eg_ctx_create_multi)
+    explicit Engine(const std::vector<int> &devices) {
+        eg_status st = eg_ctx_create_multi(devices.data(), (int)devices.size(), &ctx_);
+        if (st != EG_SUCCESS) throw Error(st, "eg_ctx_create_multi failed (devices / libnccl.so.2?)");
+    }
+    ~Engine() {
+        for (eg_dlog_table *t : tables_) eg_dlog_table_destroy(t);
+        eg_ctx_destroy(ctx_);
+    }
+    // one process per GPU: rank 0 makes the id, the host distributes it, every rank attaches (collective)
+    static std::array<uint8_t, EG_COMM_ID_BYTES> comm_unique_id() {
+        std::array<uint8_t, EG_COMM_ID_BYTES> id{};
+        eg_status st = eg_comm_unique_id(id.data());
+        if (st != EG_SUCCESS) throw Error(st, "eg_comm_unique_id failed (libnccl.so.2?)");
+        return id;
+    }
+    void attach_comm(const std::array<uint8_t, EG_COMM_ID_BYTES> &id, int rank, int world) { check(eg_ctx_attach_comm(ctx_, id.data(), rank, world)); }
+    void set_constant_time_provers(bool on) { check(eg_ctx_set_prover_mode(ctx_, on ? 1 : 0)); }
     Engine(const Engine &) = delete;
     Engine &operator=(const Engine &) = delete;
 
@@ -144,10 +173,158 @@ class Engine {
         return to_verdicts(v);
     }
 
+    // ballots.iter().map(|b| b.verify(&params)) + the tally fold (quadratic_voting.rs:291-329)
+    ChoiceBatchResult verify_qv_batch(uint32_t options, uint64_t credits, const std::vector<QuadraticVotingBallot> &ballots) {
+        eg_qv_params qp;
+        check(eg_qv_params_new(options, credits, &qp));
+        const size_t size = eg_qv_ballot_size(&qp);
+        std::vector<uint8_t> b, v(ballots.size()), t(64 * (size_t)options);
+        for (const auto &ballot : ballots) {
+            const size_t before = b.size();
+            for (const auto &vote : ballot.votes) append(b, vote);
+            append(b, ballot.credit);
+            append(b, ballot.credit_equivalence_proof);
+            if (b.size() - before != size) throw Error(EG_ERR_LEN_MISMATCH, "number of options in the ballot");      // quadratic_voting.rs:292-298
+        }
+        check(eg_verify_qv_batch(ctx_, &qp, ballots.size(), b.data(), v.data(), t.data()));
+        ChoiceBatchResult out;
+        out.verdicts = to_verdicts(v);
+        out.tally = to_ciphertexts(t);
+        return out;
+    }
+
+    // proof.verify(cts.iter(), sum_ct, receiver, transcript) over a batch (mul.rs:190-260)
+    std::vector<Verdict> verify_sum_of_squares_batch(uint32_t count, const std::vector<Ciphertext> &cts, const std::vector<Ciphertext> &sum_cts,
+                                                     const std::vector<SumOfSquaresProof> &proofs, const std::string &label) {
+        if (cts.size() != proofs.size() * count || sum_cts.size() != proofs.size()) throw Error(EG_ERR_LEN_MISMATCH, "batch size mismatch");
+        std::vector<uint8_t> c, s, p, v(proofs.size());
+        for (const auto &ct : cts) append(c, ct);
+        for (const auto &ct : sum_cts) append(s, ct);
+        for (const auto &proof : proofs) {
+            if (proof.ciphertext_responses.size() != 2 * (size_t)count) throw Error(EG_ERR_LEN_MISMATCH, "ciphertext responses");   // mul.rs:198-203
+            append(p, proof);
+        }
+        check(eg_verify_sumsq_batch(ctx_, label.c_str(), count, proofs.size(), c.data(), s.data(), p.data(), v.data()));
+        return to_verdicts(v);
+    }
+
+    // key_set.verify_share(share, ct, index, proof) for every tally x listed participant (key_set.rs:209-228)
+    std::vector<Verdict> verify_shares_batch(const PublicKeySet &ks, const std::vector<uint32_t> &indexes, const std::vector<Ciphertext> &cts,
+                                             const std::vector<Element> &shares, const std::vector<LogEqualityProof> &proofs) {
+        const size_t n = cts.size(), s = indexes.size();
+        if (shares.size() != n * s || proofs.size() != n * s || ks.participant_keys.size() != ks.shares || ks.shares > 64)
+            throw Error(EG_ERR_LEN_MISMATCH, "batch size mismatch");
+        eg_keyset k{};
+        k.shares = ks.shares; k.threshold = ks.threshold;
+        std::copy(ks.shared_key.bytes.begin(), ks.shared_key.bytes.end(), k.shared_key);
+        for (uint32_t i = 0; i < ks.shares; i++) std::copy(ks.participant_keys[i].bytes.begin(), ks.participant_keys[i].bytes.end(), k.participant_keys[i]);
+        std::vector<uint8_t> c, sh, p, v(n * s);
+        for (const auto &ct : cts) append(c, ct);
+        for (const auto &e : shares) sh.insert(sh.end(), e.begin(), e.end());
+        for (const auto &proof : proofs) append(p, proof);
+        check(eg_verify_shares_batch(ctx_, &k, n, (uint32_t)s, indexes.data(), c.data(), sh.data(), p.data(), v.data()));
+        return to_verdicts(v);
+    }
+
+    // candidate.verify(ct, key, proof, transcript) over a batch, one custom key (decryption.rs:189-205)
+    std::vector<Verdict> verify_decryption_batch(const PublicKey &key, const std::vector<Ciphertext> &cts, const std::vector<Element> &dh_elements,
+                                                 const std::vector<LogEqualityProof> &proofs, const std::string &label) {
+        if (dh_elements.size() != cts.size() || proofs.size() != cts.size()) throw Error(EG_ERR_LEN_MISMATCH, "batch size mismatch");
+        std::vector<uint8_t> c, d, p, v(cts.size());
+        for (const auto &ct : cts) append(c, ct);
+        for (const auto &e : dh_elements) d.insert(d.end(), e.begin(), e.end());
+        for (const auto &proof : proofs) append(p, proof);
+        check(eg_verify_decryption_batch(ctx_, label.c_str(), key.bytes.data(), cts.size(), c.data(), d.data(), p.data(), v.data()));
+        return to_verdicts(v);
+    }
+
+    // DiscreteLogTable::new(lo..hi) on the device(s); owned by the engine
+    eg_dlog_table *dlog_table(uint64_t lo, uint64_t hi) {
+        eg_dlog_table *t = nullptr;
+        check(eg_dlog_table_create(ctx_, lo, hi, &t));
+        tables_.push_back(t);
+        return t;
+    }
+
+    // params.combine_shares(..) + decrypt(ct, &table) per tally (sharing/mod.rs:302-325, decryption.rs:138-144)
+    std::vector<DecryptedValue> combine_decrypt_batch(const std::vector<uint32_t> &indexes, const std::vector<Ciphertext> &cts,
+                                                      const std::vector<Element> &shares, const eg_dlog_table *table) {
+        const size_t n = cts.size(), t = indexes.size();
+        if (shares.size() != n * t) throw Error(EG_ERR_LEN_MISMATCH, "batch size mismatch");
+        std::vector<uint8_t> c, sh, found(n);
+        std::vector<uint64_t> values(n);
+        for (const auto &ct : cts) append(c, ct);
+        for (const auto &e : shares) sh.insert(sh.end(), e.begin(), e.end());
+        check(eg_combine_decrypt_batch(ctx_, (uint32_t)t, indexes.data(), n, (uint32_t)t, c.data(), sh.data(), table, values.data(), found.data()));
+        std::vector<DecryptedValue> out(n);
+        for (size_t i = 0; i < n; i++) out[i] = DecryptedValue{found[i] == 1, values[i]};
+        return out;
+    }
+
+    // key.encrypt_bool(value, rng) over a batch with in-kernel randomness (keys/impls.rs:77-89)
+    std::pair<std::vector<Ciphertext>, std::vector<RingProof>> encrypt_bool_batch(const std::vector<uint8_t> &values, const Seed &seed) {
+        const size_t n = values.size();
+        std::vector<uint8_t> c(64 * n), p(96 * n);
+        check(eg_encrypt_bool_batch_seeded(ctx_, n, values.data(), seed.key.data(), seed.counter_base, c.data(), p.data()));
+        std::vector<RingProof> proofs(n);
+        for (size_t i = 0; i < n; i++) proofs[i] = ring_proof(p.data() + 96 * i, 2);
+        return {to_ciphertexts(c), proofs};
+    }
+
+    // EncryptedChoice::single(params, choice, rng) over a batch with in-kernel randomness (choice.rs:288-306)
+    std::vector<EncryptedChoice> encrypt_single_choice_batch(uint32_t options, const std::vector<uint32_t> &choices, const Seed &seed) {
+        const size_t n = choices.size(), ring = 32 * (1 + 2 * (size_t)options);
+        std::vector<uint8_t> values(n * options, 0), c(64 * n * options), r(ring * n), s(64 * n);
+        for (size_t i = 0; i < n; i++) {
+            if (choices[i] >= options) throw Error(EG_ERR_INVALID_ARG, "invalid choice");       // choice.rs:293-297
+            values[i * options + choices[i]] = 1;
+        }
+        check(eg_encrypt_choice_batch_seeded(ctx_, n, options, 1, values.data(), seed.key.data(), seed.counter_base, c.data(), r.data(), s.data()));
+        std::vector<EncryptedChoice> out(n);
+        for (size_t i = 0; i < n; i++) {
+            std::vector<uint8_t> row(c.begin() + 64 * options * i, c.begin() + 64 * options * (i + 1));
+            out[i].choices = to_ciphertexts(row);
+            out[i].range_proof = ring_proof(r.data() + ring * i, 2 * options);
+            std::copy(s.begin() + 64 * i, s.begin() + 64 * i + 32, out[i].sum_proof.challenge.begin());
+            std::copy(s.begin() + 64 * i + 32, s.begin() + 64 * i + 64, out[i].sum_proof.response.begin());
+        }
+        return out;
+    }
+
     eg_ctx *raw() { return ctx_; }
 
   private:
     eg_ctx *ctx_ = nullptr;
+    std::vector<eg_dlog_table *> tables_;
+    static void append(std::vector<uint8_t> &o, const LogEqualityProof &p) {
+        o.insert(o.end(), p.challenge.begin(), p.challenge.end());
+        o.insert(o.end(), p.response.begin(), p.response.end());
+    }
+    static void append(std::vector<uint8_t> &o, const CiphertextWithRangeProof &x) {
+        append(o, x.ciphertext);
+        for (const auto &ct : x.range_proof.partial_ciphertexts) append(o, ct);
+        append(o, x.range_proof.inner);
+    }
+    static void append(std::vector<uint8_t> &o, const SumOfSquaresProof &p) {
+        o.insert(o.end(), p.challenge.begin(), p.challenge.end());
+        for (const auto &s : p.ciphertext_responses) o.insert(o.end(), s.begin(), s.end());
+        o.insert(o.end(), p.sum_response.begin(), p.sum_response.end());
+    }
+    static std::vector<Ciphertext> to_ciphertexts(const std::vector<uint8_t> &t) {
+        std::vector<Ciphertext> out(t.size() / 64);
+        for (size_t k = 0; k < out.size(); k++) {
+            std::copy(t.begin() + 64 * k, t.begin() + 64 * k + 32, out[k].random_element.begin());
+            std::copy(t.begin() + 64 * k + 32, t.begin() + 64 * k + 64, out[k].blinded_element.begin());
+        }
+        return out;
+    }
+    static RingProof ring_proof(const uint8_t *p, size_t responses) {
+        RingProof out;
+        std::copy(p, p + 32, out.common_challenge.begin());
+        out.ring_responses.resize(responses);
+        for (size_t k = 0; k < responses; k++) std::copy(p + 32 * (1 + k), p + 32 * (2 + k), out.ring_responses[k].begin());
+        return out;
+    }
     void check(eg_status st) { if (st != EG_SUCCESS) throw Error(st, eg_last_error(ctx_)); }
     static void append(std::vector<uint8_t> &o, const Ciphertext &ct) {
         o.insert(o.end(), ct.random_element.begin(), ct.random_element.end());
