@@ -77,7 +77,7 @@ class Workload:
     cid = 0
     metric = unit = workload = ""
     default_items = 1 << 20
-    default_unique = 2048
+    default_unique = 2053                 # a prime: the tampered positions of the tiled batch do not line up with warps / CTAs
     bytes_per_item = 0
     ref_field_ops_per_item = 0.0
     ring_mode = 2
@@ -160,7 +160,7 @@ class Choice(Workload):
     metric = "verified ballots/sec (5-option choice)"
     unit = "ballots/s"
     workload = "EncryptedChoice::single 5 options: batch verify + homomorphic tally (BASELINE configs[1])"
-    default_unique = 4096
+    default_unique = 4099
     options = 5
     bytes_per_item = 5 * 64 + 11 * 32 + 64         # 736, SURVEY.md 8(a) a12
     ref_field_ops_per_item = 4956 * 11 + 280 * (34 + 10)      # 66 836
@@ -338,7 +338,7 @@ class Shares(Workload):
     metric = "threshold-decrypted tallies/sec (3-of-5 shares verified + combined + dlog lookup)"
     unit = "tallies/s"
     workload = "3-of-5 verifiable decryption shares (LogEqualityProof) + combine_shares + DiscreteLogTable(0..2^20) (BASELINE configs[4])"
-    default_unique = 1024                 # the oracle's share prover runs item by item through ctypes
+    default_unique = 1031                 # the oracle's share prover runs item by item through ctypes
     bytes_per_item = 64 + 3 * (32 + 64)   # 352
     ref_field_ops_per_item = 27e3
     kernel = "k_msm"

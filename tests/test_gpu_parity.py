@@ -374,7 +374,7 @@ def test_single_choice_validation(env):
     PC.check_single_choice_validation(env[0], env[2])
 
 
-@pytest.mark.parametrize("count", [1, 5, 15])
+@pytest.mark.parametrize("count", [1, 5, 14])            # (the oracle restates up to 14 terms)
 def test_verify_sumsq(env, count):
     PC.check_verify_sumsq(env[0], env[2], n=60, count=count)
 
