@@ -467,6 +467,9 @@ EG_HD void ge_msm_chain_rt(ge_ext &out, int nv, const ge_ext *P, const sc *a, in
 // equations (ballot choices), 8 chunks (32 doublings per equation, 224 for the tables) for the longer rings of range
 // proofs -- measured on B200 (profiles/r1_wide_tables_ab.txt): 8 chunks -1.8 % on 5-option ballots, +3.7 % on
 // RangeProof [0, 2^16).
+#ifndef EG_VTAB_PREFETCH
+#define EG_VTAB_PREFETCH 1
+#endif
 #define EG_VCHUNKS_SHORT 4
 #define EG_VCHUNKS_LONG 8
 #define EG_VTAB_ENTRY_WORDS 32                                  // one cached point
@@ -538,6 +541,15 @@ static EG_HD_NOINLINE void ge_eval64(ge_ext &out, const uint32_t *vtab, const sc
         sc_recode4(ra, a);
 #pragma unroll 1
         for (int i = W - 1; i >= 0; i--) {
+#if defined(__CUDA_ARCH__) && EG_VTAB_PREFETCH
+            // the C table entries of this window are needed after the four doublings below: request their lines now (the
+            // per-thread tables miss L1 in ~11 % of the loads and then come from L2 / HBM, ncu long_scoreboard)
+#pragma unroll 1
+            for (int c = 0; c < C; c++) {
+                const int d = sc_digit4(ra, W * c + i);
+                if (d != 0) asm volatile("prefetch.global.L1 [%0];" :: "l"(vtab + (c * 8 + (d < 0 ? -d : d) - 1) * EG_VTAB_ENTRY_WORDS));
+            }
+#endif
             if (i != W - 1) {
 #pragma unroll 1
                 for (int k = 0; k < 4; k++) {
