@@ -32,10 +32,10 @@ def run(name, fn, sizes):
 
 
 bc, bp = O.gen_bool_batch(pk, W.SEED_CHOICE, 1024)
-run("verify_bool", lambda n: e.verify_bool(tile(bc, n), tile(bp, n)), (1000, 10000, 40000, 100000, 200000))
+run("verify_bool", lambda n: e.verify_bool(tile(bc, n), tile(bp, n)), (1000, 5000, 10000, 20000, 30000, 40000, 60000, 80000, 100000, 140000, 200000))
 cc, cr, cs = O.gen_choice_batch(pk, 5, W.SEED_CHOICE, 1024)
-run("verify_choice (5 options)", lambda n: e.verify_choice(5, tile(cc, n), tile(cr, n), tile(cs, n)), (1000, 10000, 30000, 60000))
+run("verify_choice (5 options)", lambda n: e.verify_choice(5, tile(cc, n), tile(cr, n), tile(cs, n)), (1000, 2500, 5000, 7500, 10000, 15000, 20000, 30000, 60000))
 spec = O.range_optimal(65536)
 rng = PC.to_engine_range(e, spec)
 rc, rp, rr = O.gen_range_batch(pk, spec, "range", W.SEED_QV, (np.arange(256, dtype=np.uint64) * 40503) % 65536)
-run("verify_range [0, 2^16)", lambda n: e.verify_range(rng, "range", tile(rc, n), tile(rp, n), tile(rr, n)), (1000, 5000, 20000, 40000))
+run("verify_range [0, 2^16)", lambda n: e.verify_range(rng, "range", tile(rc, n), tile(rp, n), tile(rr, n)), (500, 1000, 2000, 3000, 5000, 10000, 20000, 40000))
