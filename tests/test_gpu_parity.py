@@ -157,8 +157,8 @@ def test_ring_mode_1_still_matches(env):
 
 def test_ring_mode_auto(env):
     """Default engine choice: small chunks go through the per-equation pipeline, large ones through k_ring; a batch
-    that mixes both (a full 257 638-ballot chunk + a 42 362-ballot remainder) must still give tiled verdicts and the
-    tally of the accepted ballots."""
+    that mixes both (a 30 310-ballot ramp-up chunk and a full 257 638-ballot chunk through k_ring + a 5 052-ballot remainder,
+    a third of a wave, through the pipeline) must still give tiled verdicts and the tally of the accepted ballots."""
     e, sk, pk = env
     e.set_ring_mode(0)
     try:
@@ -166,7 +166,7 @@ def test_ring_mode_auto(env):
         PC.check_verify_choice(e, pk, options=5, n=256, single=True, frac=0.1)
         PC.check_verify_range(e, pk, 1000, n=50, frac=0.2)
         PC.check_verify_qv(e, pk, sk, n=12)
-        base, total = 1024, 300000
+        base, total = 1024, 293000
         cts, rings, sums = O.gen_choice_batch(pk, 5, W.SEED_CHOICE, base)
         cts, rings, sums = cts.copy(), rings.copy(), sums.copy()
         W.tamper_choice(cts, rings, sums, random.Random(10), frac=0.02)
