@@ -281,8 +281,13 @@ EG_HD void ge_cached_load(ge_cached &c, const uint32_t *e) {
 #ifndef EG_HOT_OPS
 #define EG_HOT_OPS fe_ops_call
 #endif
+// The shared doubling callee (ge_hot_dbl: table builds, the single-use chains of k_commit / k_msm) expands its field
+// operations in place: one 14 KB body next to the 4 KB of fe_mul / fe_sq still fits the instruction cache and drops the
+// ~20 register moves per field operation of the call ABI from 56 % of the point operations.  Measured
+// (profiles/r2_ab_inline_doubling.txt): k_msm -12 %, k_ring<256,2,8> -1.4 %, k_commit -8 %; expanding the additions or the
+// evaluation loop as well loses 1.5-4 % (instruction cache).
 #ifndef EG_HOT_DBL_OPS
-#define EG_HOT_DBL_OPS EG_HOT_OPS
+#define EG_HOT_DBL_OPS fe_ops_inline
 #endif
 #ifndef EG_HOT_DBL_PROJ_OPS
 #define EG_HOT_DBL_PROJ_OPS EG_HOT_DBL_OPS
@@ -467,6 +472,9 @@ EG_HD void ge_msm_chain_rt(ge_ext &out, int nv, const ge_ext *P, const sc *a, in
 // equations (ballot choices), 8 chunks (32 doublings per equation, 224 for the tables) for the longer rings of range
 // proofs -- measured on B200 (profiles/r1_wide_tables_ab.txt): 8 chunks -1.8 % on 5-option ballots, +3.7 % on
 // RangeProof [0, 2^16).
+#ifndef EG_EVAL_VIA_HOT_DBL
+#define EG_EVAL_VIA_HOT_DBL 0
+#endif
 #ifndef EG_VTAB_PREFETCH
 #define EG_VTAB_PREFETCH 1
 #endif
@@ -551,12 +559,16 @@ static EG_HD_NOINLINE void ge_eval64(ge_ext &out, const uint32_t *vtab, const sc
             }
 #endif
             if (i != W - 1) {
+#if EG_EVAL_VIA_HOT_DBL
+                ge_hot_dbl(acc, 4);         // A/B: the shared doubling callee (with EG_HOT_DBL_OPS=fe_ops_inline: no per-field-op calls)
+#else
 #pragma unroll 1
                 for (int k = 0; k < 4; k++) {
                     ge_dbl_p1p1<EG_EVAL_DBL_OPS>(t, acc);
                     ge_p1p1_to_proj<EG_EVAL_PROJ_OPS>(acc, t);
                     if (k == 3) fe_mul(acc.T, t.E, t.H);
                 }
+#endif
             }
 #pragma unroll 1
             for (int c = 0; c < C; c++) {
