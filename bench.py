@@ -646,7 +646,14 @@ def main():
     sampler.stop_flag = True
     sampler.join()
     t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    per_rank = None
     if world > 1:
+        # every rank's own device time and median SM clock (reporting only): the step ends in the tally all-gather, so the
+        # job runs at the pace of the slowest GPU
+        mine = torch.tensor([dev_ms / args.steps, float(sampler.summary().get("sm_mhz") or 0)], dtype=torch.float64, device=dev)
+        allr = torch.empty(2 * world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allr, mine)
+        per_rank = allr.cpu().numpy().reshape(world, 2)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms_max = float(t.item())
 
@@ -794,6 +801,8 @@ def main():
         "roofline": roofline,
         "cpu_baseline": cpu,
     }
+    if per_rank is not None:
+        line["per_rank"] = {"ms_per_step": [round(float(x), 3) for x in per_rank[:, 0]], "sm_mhz": [int(x) for x in per_rank[:, 1]]}
     if saturated:
         line["saturated"] = saturated
     if wl.cid == 5:
