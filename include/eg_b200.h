@@ -403,6 +403,18 @@ eg_status eg_verify_shares_batch_dev(eg_ctx *ctx, const eg_keyset *keyset, size_
 eg_status eg_combine_decrypt_batch_dev(eg_ctx *ctx, uint32_t threshold, const uint32_t *indexes, size_t n_tallies, uint32_t share_stride,
                                        const uint8_t *d_cts, const uint8_t *d_shares, const eg_dlog_table *table, uint64_t *d_values,
                                        uint8_t *d_found);
+/* Provers on device buffers: values in, objects out, all in HBM of the context's device.  Randomness: `seed` (32 bytes, HOST
+ * pointer) + counter_base as in the _seeded forms, or -- with seed == NULL -- blocks already resident at d_wide_rand in the
+ * layout of the host forms.  The domain checks the host forms make on the values (exactly one option for `single`, value
+ * below the range's bound) are the caller's here: a violating item yields an object that fails verification. */
+eg_status eg_encrypt_bool_batch_dev(eg_ctx *ctx, size_t n, const uint8_t *d_values, const uint8_t *d_wide_rand, const uint8_t seed[32],
+                                    uint64_t counter_base, uint8_t *d_cts, uint8_t *d_proofs);
+eg_status eg_encrypt_choice_batch_dev(eg_ctx *ctx, size_t n, uint32_t options, int single, const uint8_t *d_values,
+                                      const uint8_t *d_wide_rand, const uint8_t seed[32], uint64_t counter_base, uint8_t *d_choices,
+                                      uint8_t *d_ring_proofs, uint8_t *d_sum_proofs);
+eg_status eg_encrypt_range_batch_dev(eg_ctx *ctx, const eg_range *range, const char *transcript_label, size_t n, const uint64_t *d_values,
+                                     const uint8_t *d_wide_rand, const uint8_t seed[32], uint64_t counter_base, uint8_t *d_cts,
+                                     uint8_t *d_partials, uint8_t *d_ring_proofs);
 /* eg_ciphertexts_sum on device buffers, asynchronous on the context's stream: the local combine after the all_gather
  * of per-GPU partial tallies.  *d_bad_flag (optional, device) becomes non-zero when a part does not decode. */
 eg_status eg_ciphertexts_sum_dev(eg_ctx *ctx, size_t n_parts, size_t n_cts, const uint8_t *d_parts, uint8_t *d_out,

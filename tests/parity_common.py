@@ -1198,3 +1198,46 @@ def check_prove_range_from_ciphertext(e, pk, upper_bound=100, n=9, label="cipher
         assert exc.status == _ffi.ERR_INVALID_ARG
     else:
         raise AssertionError("non-canonical ciphertext randomness accepted")
+
+
+# ---------------------------------------------------------------- device-pointer provers
+
+def check_prover_dev_forms(e, pk, up, down, new, n=9):
+    """eg_encrypt_{bool,choice,range}_batch_dev: the same bytes as the host forms, with the seed and with blocks resident
+    in "device" memory.  up(array) -> device buffer, new(shape) -> empty uint8 device buffer, down(buffer) -> numpy; a buffer
+    exposes its address as `.ptr` (torch on the GPU, numpy in the CPU-compiled harness where device == host)."""
+    seed = _u8s(W.SEED_CHOICE)
+    # bool, seeded
+    values = np.array([i & 1 for i in range(n)], np.uint8)
+    hc, hp = e.encrypt_bool(values, seed=W.SEED_CHOICE, counter_base=5 << 20)
+    d_v, d_c, d_p = up(values), new((n, 64)), new((n, 96))
+    e._check(e.lib.eg_encrypt_bool_batch_dev(e.h, n, d_v.ptr, None, seed.ctypes.data, 5 << 20, d_c.ptr, d_p.ptr))
+    assert (down(d_c) == hc).all() and (down(d_p) == hp).all()
+    # choice (single), blocks resident on the device
+    m = 4
+    cv = np.zeros((n, m), np.uint8)
+    cv[np.arange(n), np.arange(n) % m] = 1
+    wide = np.frombuffer(b"".join(item_blocks(W.SEED_CHOICE, i, 3 * m + 1) for i in range(n)), np.uint8).reshape(n, 3 * m + 1, 64)
+    hc, hr, hs = e.encrypt_choice(m, cv, wide, single=True)
+    d_v, d_w, d_c, d_r, d_s = up(cv), up(wide), new((n, m, 64)), new((n, 1 + 2 * m, 32)), new((n, 64))
+    e._check(e.lib.eg_encrypt_choice_batch_dev(e.h, n, m, 1, d_v.ptr, d_w.ptr, None, 0, d_c.ptr, d_r.ptr, d_s.ptr))
+    assert (down(d_c) == hc).all() and (down(d_r) == hr).all() and (down(d_s) == hs).all()
+    oc, orr, oss = O.gen_choice_batch(pk, m, W.SEED_CHOICE, n)
+    assert (hc == oc).all() and (hr == orr).all() and (hs == oss).all()
+    # range, seeded, tiny chunks
+    spec = to_engine_range(e, O.range_optimal(100))
+    rv = np.array([(29 * i) % 100 for i in range(n)], np.uint64)
+    hc, hp, hr = e.encrypt_range(spec, "ciphertext_range", rv, seed=W.SEED_CHOICE)
+    d_v, d_c, d_p, d_r = up(rv.view(np.uint8)), new(hc.shape), new(hp.shape), new(hr.shape)
+    e.set_chunk_items(4)
+    try:
+        e._check(e.lib.eg_encrypt_range_batch_dev(e.h, O.C.byref(spec), b"ciphertext_range", n, d_v.ptr, None, seed.ctypes.data, 0,
+                                                  d_c.ptr, d_p.ptr, d_r.ptr))
+    finally:
+        e.set_chunk_items(0)
+    assert (down(d_c) == hc).all() and (down(d_p) == hp).all() and (down(d_r) == hr).all()
+    assert (e.verify_range(spec, "ciphertext_range", hc, hp, hr) == 0).all()
+
+
+def _u8s(b):
+    return np.frombuffer(bytes(b), np.uint8).copy()

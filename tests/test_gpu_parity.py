@@ -394,3 +394,15 @@ def test_wire_objects(env):
 @pytest.mark.parametrize("ub", [2, 100, 65536])
 def test_prove_range_from_ciphertext(env, ub):
     PC.check_prove_range_from_ciphertext(env[0], env[2], ub, n=40)
+
+
+def test_prover_dev_forms(env):
+    import torch
+    dev = torch.device("cuda", 0)
+
+    class Buf:
+        def __init__(self, t):
+            self.t = t
+            self.ptr = t.data_ptr()
+    PC.check_prover_dev_forms(env[0], env[2], lambda a: Buf(torch.from_numpy(np.ascontiguousarray(a)).to(dev)),
+                              lambda b: b.t.cpu().numpy(), lambda shape: Buf(torch.zeros(shape, dtype=torch.uint8, device=dev)), n=200)

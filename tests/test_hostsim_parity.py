@@ -229,3 +229,13 @@ def test_wire_objects(env):
 @pytest.mark.parametrize("ub", [5, 100])
 def test_prove_range_from_ciphertext(env, ub):
     PC.check_prove_range_from_ciphertext(env[0], env[2], ub, n=5)
+
+
+def test_prover_dev_forms(env):
+    import numpy as np
+
+    class Buf:          # the harness has no device: "device" buffers are host arrays
+        def __init__(self, a):
+            self.a = np.ascontiguousarray(a)
+            self.ptr = self.a.ctypes.data
+    PC.check_prover_dev_forms(env[0], env[2], lambda a: Buf(a), lambda b: b.a, lambda shape: Buf(np.zeros(shape, np.uint8)), n=6)
