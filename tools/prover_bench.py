@@ -83,6 +83,34 @@ def main():
     run("qv_ballot_5_20", e.lib.eg_qv_prover_draws(C.byref(ep)), lambda w: (e.encrypt_qv(ep, votes, w),),
         lambda: (e.encrypt_qv(ep, votes, seed=W.SEED_QV),), lambda o: (e.verify_qv(ep, o[0])[0] == 0).all(),
         lambda o: (o[0][:32] == oq).all() or (_ for _ in ()).throw(AssertionError("qv")))
+    # device-resident forms (values in, objects out, all in HBM; in-kernel randomness): the kernels' own rate
+    import torch
+    dev = torch.device("cuda", 0)
+    key = np.frombuffer(seed, np.uint8).copy()
+
+    def dev_rate(fn):
+        fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        return n * 3 / (time.perf_counter() - t0)
+    d_vals = torch.from_numpy(values).to(dev)
+    d_c, d_p = torch.empty((n, 64), dtype=torch.uint8, device=dev), torch.empty((n, 96), dtype=torch.uint8, device=dev)
+    res["encrypt_bool"]["seeded_device_resident_per_s"] = dev_rate(lambda: e._check(e.lib.eg_encrypt_bool_batch_dev(
+        e.h, n, d_vals.data_ptr(), None, key.ctypes.data, 0, d_c.data_ptr(), d_p.data_ptr())))
+    assert (e.verify_bool(d_c.cpu().numpy(), d_p.cpu().numpy()) == 0).all()
+    d_cv = torch.from_numpy(cv).to(dev)
+    d_cc, d_cr, d_cs = (torch.empty(s_, dtype=torch.uint8, device=dev) for s_ in ((n, 5, 64), (n, 11, 32), (n, 64)))
+    res["encrypted_choice_single_5"]["seeded_device_resident_per_s"] = dev_rate(lambda: e._check(e.lib.eg_encrypt_choice_batch_dev(
+        e.h, n, 5, 1, d_cv.data_ptr(), None, key.ctypes.data, 0, d_cc.data_ptr(), d_cr.data_ptr(), d_cs.data_ptr())))
+    d_rv = torch.from_numpy(rv.view(np.int64)).to(dev)
+    d_rc, d_rp, d_rr = (torch.empty(s_, dtype=torch.uint8, device=dev) for s_ in ((n, 64), (n, 7, 64), (n, 33, 32)))
+    res["range_proof_2_16"]["seeded_device_resident_per_s"] = dev_rate(lambda: e._check(e.lib.eg_encrypt_range_batch_dev(
+        e.h, C.byref(espec), b"ciphertext_range", n, d_rv.data_ptr(), None, key.ctypes.data, 0, d_rc.data_ptr(), d_rp.data_ptr(), d_rr.data_ptr())))
+    assert (e.verify_range(espec, "ciphertext_range", d_rc.cpu().numpy(), d_rp.cpu().numpy(), d_rr.cpu().numpy()) == 0).all()
+    print("device-resident:", {k: v.get("seeded_device_resident_per_s") for k, v in res.items()}, flush=True)
     if args.out:
         pathlib.Path(args.out).write_text(json.dumps(res, indent=1))
 
