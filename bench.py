@@ -118,7 +118,7 @@ class Bool(Workload):
     default_items = 10000
     bytes_per_item = 160
     ref_field_ops_per_item = 12.1e3
-    ring_mode = 0                         # the library picks the per-equation pipeline for a batch this small
+    ring_mode = 0                         # the library picks the pair engine (k_ring_pair) for a batch this small
     executed_field_ops_per_task = 1949.5
 
     def make(self, unique, threads):
@@ -625,6 +625,7 @@ def main():
     launches0 = e.kernel_launches
     k_ms, k_tasks, k_launches = 0.0, 0, 0
     o_ms, o_tasks, o_launches = 0.0, 0, 0
+    p_ms, p_tasks, p_launches = 0.0, 0, 0
     pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     with torch.cuda.stream(stream):
         for ev0, ev1 in pairs:
@@ -640,6 +641,8 @@ def main():
             if wl.kernel_kind == 1:
                 s = e.last_kernel_stats(0)
                 o_ms += s["ms"]; o_tasks += s["tasks"]; o_launches += s["launches"]
+                s = e.last_kernel_stats(3)
+                p_ms += s["ms"]; p_tasks += s["tasks"]; p_launches += s["launches"]
     barrier()
     dev_ms = sum(a.elapsed_time(b) for a, b in pairs)
     launches = e.kernel_launches - launches0
@@ -734,7 +737,9 @@ def main():
         if clk.get("sm_mhz") and peak.get("sm_clock_mhz_probed"):
             peak_ops *= clk["sm_mhz"] / peak["sm_clock_mhz_probed"]
     dom_kernel, dom_kind = wl.kernel, wl.kernel_kind
-    if wl.kernel_kind == 1 and k_ms == 0 and o_ms > 0:      # the library chose the per-equation pipeline (small batch)
+    if wl.kernel_kind == 1 and k_ms == 0 and p_ms > 0:      # the library chose the pair engine (small batch of rings only)
+        dom_kernel, k_ms, k_tasks, k_launches = "k_ring_pair (two lanes per ring, ring mode 3)", p_ms, p_tasks, p_launches
+    elif wl.kernel_kind == 1 and k_ms == 0 and o_ms > 0:    # the library chose the per-equation pipeline (small batch)
         dom_kernel, k_ms, k_tasks, k_launches, o_ms = "k_commit (per-equation pipeline, ring mode 1)", o_ms, o_tasks, o_launches, 0.0
     achieved_ops = k_tasks * wl.field_ops_per_task * IMAD_PER_FIELD_OP / (k_ms * 1e-3) if k_ms > 0 else None
     traffic, traffic_src = None, None

@@ -28,7 +28,7 @@ using namespace eg;
 
 // =================================================================== context
 
-#define EG_STAT_KINDS 3          // timed kernel kinds (eg_last_kernel_stats): 0 = k_commit, 1 = k_ring, 2 = k_msm
+#define EG_STAT_KINDS 4          // timed kernel kinds (eg_last_kernel_stats): 0 = k_commit, 1 = k_ring, 2 = k_msm, 3 = k_ring_pair
 
 struct dev_buf {
     void *p = nullptr;
@@ -47,11 +47,11 @@ struct eg_ctx {
     float timings[5] = {0, 0, 0, 0, 0};
     cudaEvent_t ev[8];
     std::vector<cudaEvent_t> commit_ev;     // pairs (start, stop) around every k_commit / k_ring launch of the current call
-    std::vector<uint8_t> commit_ev_kind;    // per pair: 0 = k_commit, 1 = k_ring, 2 = k_msm
+    std::vector<uint8_t> commit_ev_kind;    // per pair: 0 = k_commit, 1 = k_ring, 2 = k_msm, 3 = k_ring_pair
     size_t commit_ev_used = 0;
     uint64_t call_commit_tasks = 0, call_commit_launches = 0;
-    uint64_t kind_tasks[EG_STAT_KINDS] = {0, 0, 0}, kind_launches[EG_STAT_KINDS] = {0, 0, 0};   // per kind, current call
-    float kind_ms[EG_STAT_KINDS] = {0, 0, 0};
+    uint64_t kind_tasks[EG_STAT_KINDS] = {0, 0, 0, 0}, kind_launches[EG_STAT_KINDS] = {0, 0, 0, 0};   // per kind, current call
+    float kind_ms[EG_STAT_KINDS] = {0, 0, 0, 0};
     // grow-only scratch
     cudaStream_t copy_stream = nullptr;     // host -> device prefetch of the next chunk
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr};
@@ -312,6 +312,37 @@ static eg_status launch_ring(eg_ctx *ctx, ring_params &P) {
     cudaEvent_t e_stop = stat_begin(ctx, 1, sides);
     if (shape) k_ring<EG_RING2_THREADS, EG_RING2_MINBLOCKS, EG_VCHUNKS_SHORT><<<grid, threads, smem, ctx->stream>>>(P);
     else k_ring<EG_RING_THREADS, EG_RING_MINBLOCKS, EG_VCHUNKS_LONG><<<grid, threads, smem, ctx->stream>>>(P);
+#endif
+    cudaEventRecord(e_stop, ctx->stream);
+    ctx->launches++;
+    ctx->commit_launches++;
+    ctx->commit_tasks += sides;
+    ctx->call_commit_tasks += sides;
+    ctx->call_commit_launches++;
+    return EG_SUCCESS;
+}
+
+// Pair engine (ring mode 3): two lanes per ring, one launch for all equations of a small chunk.  Accounted like k_ring
+// (tasks = equation sides), under its own kind (3).
+static eg_status launch_ring_pair(eg_ctx *ctx, ring_params &P) {
+    size_t sides = 0;
+    for (uint32_t r = 0; r < P.n_rings; r++) sides += 2 * (size_t)P.sizes[r];
+    sides *= P.n;
+    const size_t total = P.n * (size_t)P.n_rings;
+    bool short_rings = true;
+    for (uint32_t r = 0; r < P.n_rings; r++) short_rings = short_rings && P.sizes[r] <= 2;
+#ifdef EG_HOSTSIM
+    TRY(ensure(ctx, ctx->ring_scratch, 2 * EG_VTAB_WORDS * 4));
+    P.scratch = (uint32_t *)ctx->ring_scratch.p;
+    cudaEvent_t e_stop = stat_begin(ctx, 3, sides);
+    if (short_rings) { EG_FOR_HOST(total, ring_pair_host<EG_VCHUNKS_SHORT>(P, tid % P.n, (uint32_t)(tid / P.n), P.scratch, P.table_g, P.table_k)) }
+    else { EG_FOR_HOST(total, ring_pair_host<EG_VCHUNKS_LONG>(P, tid % P.n, (uint32_t)(tid / P.n), P.scratch, P.table_g, P.table_k)) }
+#else
+    TRY(ensure(ctx, ctx->ring_scratch, 2 * total * EG_VTAB_WORDS * 4));
+    P.scratch = (uint32_t *)ctx->ring_scratch.p;
+    cudaEvent_t e_stop = stat_begin(ctx, 3, sides);
+    if (short_rings) k_ring_pair<EG_VCHUNKS_SHORT><<<grid_for(2 * total, EG_PAIR_THREADS), EG_PAIR_THREADS, 0, ctx->stream>>>(P);
+    else k_ring_pair<EG_VCHUNKS_LONG><<<grid_for(2 * total, EG_PAIR_THREADS), EG_PAIR_THREADS, 0, ctx->stream>>>(P);
 #endif
     cudaEventRecord(e_stop, ctx->stream);
     ctx->launches++;
@@ -731,7 +762,8 @@ extern "C" eg_status eg_last_commit_stats(const eg_ctx *ctx, uint64_t *launches,
     return EG_SUCCESS;
 }
 
-// kind 0: k_commit launches of the last call, kind 1: k_ring launches (tasks = equation sides), kind 2: k_msm (tasks = sums)
+// kind 0: k_commit launches of the last call, kind 1: k_ring launches (tasks = equation sides), kind 2: k_msm (tasks = sums),
+// kind 3: k_ring_pair launches (tasks = equation sides)
 extern "C" eg_status eg_last_kernel_stats(const eg_ctx *ctx, int kind, uint64_t *launches, uint64_t *tasks, float *ms) {
     if (!ctx || kind < 0 || kind >= EG_STAT_KINDS) return EG_ERR_INVALID_ARG;
     if (ctx_is_multi(ctx)) {
@@ -795,7 +827,7 @@ extern "C" eg_status eg_ctx_set_chunk_items(eg_ctx *ctx, size_t items) {
 }
 
 extern "C" eg_status eg_ctx_set_ring_mode(eg_ctx *ctx, int mode) {
-    if (!ctx || mode < 0 || mode > 2) return EG_ERR_INVALID_ARG;
+    if (!ctx || mode < 0 || mode > 3) return EG_ERR_INVALID_ARG;
     ctx->ring_mode = mode;
     for (eg_ctx *c : ctx->children) c->ring_mode = mode;
     return EG_SUCCESS;

@@ -447,6 +447,118 @@ EG_HD void ring_body(const ring_params &P, size_t item, uint32_t r, uint32_t *sc
     planar_store_words(P.commit, P.n, P.commit_index0 + 2 * r + 1, 8, item, ck);
 }
 
+// ---- pair engine: two adjacent lanes = one ring (small chunks) ------------------------------------------------------
+//
+// A chunk with fewer ring threads than the GPU has warp slots is latency-bound: what counts is the length of the longest
+// per-thread chain, not the amount of work.  k_ring runs both sides of every equation in one thread (2 x 192 table
+// doublings + 4 x 60), the per-equation pipeline pays 252 doublings per equation index.  Here lane 2p evaluates the G side
+// (tables of R only), lane 2p + 1 the K side (tables of B): 192 + 60 per equation doublings on the critical path, each lane
+// encodes its own commitment (one inversion) and the pair swaps the encodings by shuffle before both clone the
+// transcript for the next challenge (ring.rs:342-360).  Same group elements, same bytes.
+
+// Q = half-scalar point of side `side` of equation j: side 0: [s/2] G - [e/2] R, side 1: [s/2] K - [e/2] B + [e a_j / 2] G
+template <int C>
+EG_HD void ring_side_eval(ge_ext &q, const ring_params &P, uint32_t r, uint32_t j, int side, const uint32_t *tab, const sc &e,
+                          const sc &s, const uint32_t *tab_g, const uint32_t *tab_k) {
+    sc ne, hs, hne, hea;
+    sc_neg(ne, e);
+    sc_half(hs, s);
+    sc_half(hne, ne);
+    hea = hs;
+    int nf = 1;
+    const uint64_t a = side ? P.adm_step[r] * (uint64_t)j : 0;
+    if (a != 0) {
+        sc ea;
+        sc_mul(ea, e, sc_from_u64(a));
+        sc_half(hea, ea);
+        nf = 2;
+    }
+    ge_eval64<C>(q, tab, hne, nf, side ? tab_k : tab_g, hs, tab_g, hea);
+}
+
+static EG_HD_NOINLINE void ge_double_compress1_call(uint32_t w[8], const ge_ext &Q) { ge_double_compress1(w, Q); }
+
+#if defined(__CUDACC__) && !defined(EG_HOSTSIM)
+// `tab`: EG_VTAB_WORDS words of scratch for this lane.  Both lanes of a pair share (item, r) and therefore every branch
+// below; the shuffles name only the two lanes of the pair, so pairs of one warp may sit in different equations.
+template <int C>
+__device__ void ring_pair_body(const ring_params &P, size_t item, uint32_t r, int side, uint32_t *tab, const uint32_t *tab_g,
+                               const uint32_t *tab_k) {
+    {
+        ge_ext pt;
+        planar_load_point(pt, P.pts, P.n, P.ct_p_index[r] + (uint32_t)side, item);
+        ge_vtab_build<C>(tab, pt);
+    }
+    const unsigned pair_mask = 3u << (threadIdx.x & 30u);
+    const uint8_t *proof = in_ptr(P.in, P.proof_buf, item) + P.proof_offset;
+    uint32_t w[16];
+    sc e;
+    load32_bytes(w, proof);
+    if (!sc_from_words(e, w)) e = sc_zero();
+    planar_load_words(w, P.enc, P.n, P.ct_enc_index[r], 8, item);
+    planar_load_words(w + 8, P.enc, P.n, P.ct_enc_index[r] + 1, 8, item);
+    const uint32_t size = P.sizes[r];
+    transcript rt;
+    ring_transcript_start(rt, P.prefix, w, r);
+    uint32_t mine[8], other[8];
+#pragma unroll 1
+    for (uint32_t j = 0; j < size; j++) {
+        sc s;
+        load32_bytes(w, proof + 32 * (1 + P.starts[r] + j));
+        if (!sc_from_words(s, w)) s = sc_zero();
+        ge_ext q;
+        ring_side_eval<C>(q, P, r, j, side, tab, e, s, tab_g, tab_k);
+        if (j + 1 == size && P.term_pts) {
+            planar_store_point(P.term_pts, P.n, 2 * r + (uint32_t)side, item, q);
+            return;
+        }
+        ge_double_compress1_call(mine, q);
+        if (j + 1 < size) {
+            for (int k = 0; k < 8; k++) other[k] = __shfl_xor_sync(pair_mask, mine[k], 1);
+            ring_next_challenge(e, rt, j, side ? other : mine, side ? mine : other);
+        }
+    }
+    planar_store_words(P.commit, P.n, P.commit_index0 + 2 * r + (uint32_t)side, 8, item, mine);
+}
+#endif
+
+// the same engine for the host harness: the two lanes of a pair one after the other (scratch: 2 * EG_VTAB_WORDS words)
+template <int C>
+EG_HD void ring_pair_host(const ring_params &P, size_t item, uint32_t r, uint32_t *scratch, const uint32_t *tab_g, const uint32_t *tab_k) {
+    uint32_t *tab[2] = {scratch, scratch + EG_VTAB_WORDS};
+    for (int side = 0; side < 2; side++) {
+        ge_ext pt;
+        planar_load_point(pt, P.pts, P.n, P.ct_p_index[r] + (uint32_t)side, item);
+        ge_vtab_build<C>(tab[side], pt);
+    }
+    const uint8_t *proof = in_ptr(P.in, P.proof_buf, item) + P.proof_offset;
+    uint32_t w[16];
+    sc e;
+    load32_bytes(w, proof);
+    if (!sc_from_words(e, w)) e = sc_zero();
+    planar_load_words(w, P.enc, P.n, P.ct_enc_index[r], 8, item);
+    planar_load_words(w + 8, P.enc, P.n, P.ct_enc_index[r] + 1, 8, item);
+    const uint32_t size = P.sizes[r];
+    transcript rt;
+    ring_transcript_start(rt, P.prefix, w, r);
+    uint32_t c[2][8];
+    for (uint32_t j = 0; j < size; j++) {
+        sc s;
+        load32_bytes(w, proof + 32 * (1 + P.starts[r] + j));
+        if (!sc_from_words(s, w)) s = sc_zero();
+        for (int side = 0; side < 2; side++) {
+            ge_ext q;
+            ring_side_eval<C>(q, P, r, j, side, tab[side], e, s, tab_g, tab_k);
+            if (j + 1 == size && P.term_pts) planar_store_point(P.term_pts, P.n, 2 * r + (uint32_t)side, item, q);
+            else ge_double_compress1_call(c[side], q);
+        }
+        if (j + 1 == size && P.term_pts) return;
+        if (j + 1 < size) ring_next_challenge(e, rt, j, c[0], c[1]);
+    }
+    planar_store_words(P.commit, P.n, P.commit_index0 + 2 * r, 8, item, c[0]);
+    planar_store_words(P.commit, P.n, P.commit_index0 + 2 * r + 1, 8, item, c[1]);
+}
+
 // ---- terminal commitments: encode(2 Q_k) for all deferred points of an item with ONE field inversion ---------------
 //
 // The commitments of a ring's last equation (and of an EncryptedChoice's sum proof) are only read by the outer

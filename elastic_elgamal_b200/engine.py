@@ -90,7 +90,8 @@ class Engine:
         return {"launches": launches.value, "tasks": tasks.value, "ms": ms.value}
 
     def last_kernel_stats(self, kind):
-        """kind 0: k_commit, 1: k_ring -- launches, equation sides and summed device ms in the last batch call."""
+        """kind 0: k_commit, 1: k_ring, 2: k_msm, 3: k_ring_pair -- launches, tasks (equation sides / sums) and summed device
+        ms in the last batch call."""
         launches, tasks, ms = C.c_uint64(0), C.c_uint64(0), C.c_float(0)
         self._check(self.lib.eg_last_kernel_stats(self.h, kind, C.byref(launches), C.byref(tasks), C.byref(ms)))
         return {"launches": launches.value, "tasks": tasks.value, "ms": ms.value}

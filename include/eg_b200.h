@@ -431,7 +431,8 @@ eg_status eg_last_timings(const eg_ctx *ctx, float out_ms[5]);
  * verification-equation sides evaluated, summed device time of those launches (one CUDA event pair per launch). */
 eg_status eg_last_commit_stats(const eg_ctx *ctx, uint64_t *launches, uint64_t *tasks, float *ms);
 /* The same split by kernel: kind 0 = k_commit (single-use equation sides), kind 1 = k_ring (one thread per ring),
- * kind 2 = k_msm (general multi-scalar sums: share proofs, sum-of-squares, Lagrange recombination; tasks = sums). */
+ * kind 2 = k_msm (general multi-scalar sums: share proofs, sum-of-squares, Lagrange recombination; tasks = sums),
+ * kind 3 = k_ring_pair (two lanes per ring, small chunks; tasks = equation sides). */
 eg_status eg_last_kernel_stats(const eg_ctx *ctx, int kind, uint64_t *launches, uint64_t *tasks, float *ms);
 /* On-device self-test of the tuned GF(2^255-19) multiply / square / add / sub against the portable formulation on
  * n pseudo-random and edge-case operands; *mismatches must come back 0. */
@@ -440,9 +441,11 @@ eg_status eg_selftest_field(eg_ctx *ctx, size_t n, uint64_t seed, uint64_t *mism
 eg_status eg_ctx_set_chunk_items(eg_ctx *ctx, size_t items);
 /* Tuning / A-B knob for RingProof verification: 2 = one thread per ring with per-point chunked window tables (k_ring,
  * 64 doublings per equation; the engine for large batches); 1 = one launch per equation index with one thread per
- * equation side (k_commit + k_ring_hash, 252 doublings; lower latency for small batches); 0 (default) = chosen per
- * chunk: 1 when the chunk has too few ring threads to fill the persistent k_ring grid (measured crossovers).  Results do not depend
- * on it. */
+ * equation side (k_commit + k_ring_hash, 252 doublings); 3 = two lanes per ring, one per equation side, each with the
+ * chunked tables of its own point (k_ring_pair: the shortest per-thread chain, for chunks smaller than the GPU);
+ * 0 (default) = chosen per chunk from the measured crossovers: 3 for small chunks that are rings only (bool, range, QV),
+ * 1 for small chunks with extra single-use equations (the sum proof of an EncryptedChoice), 2 otherwise.  Results do
+ * not depend on it. */
 eg_status eg_ctx_set_ring_mode(eg_ctx *ctx, int mode);
 /* Raw CUDA stream handle (cudaStream_t) so callers can order their own work / time with events on it. */
 void     *eg_ctx_stream(const eg_ctx *ctx);

@@ -120,10 +120,10 @@ def test_shares_3_of_5_at_262k(env):
     table.close()
 
 
-@pytest.mark.parametrize("mode", [2, 1])
+@pytest.mark.parametrize("mode", [2, 1, 3])
 def test_fuzz_differential_20k(env, mode):
     """Random bit flips anywhere in the inputs of EncryptedChoice / bool / RangeProof / QV ballot / CommitmentEquivalenceProof /
-    ProofOfPossession batches of 20 000 items: every GPU verdict and tally equals the oracle's, under both ring engines."""
+    ProofOfPossession batches of 20 000 items: every GPU verdict and tally equals the oracle's, under each of the three ring engines."""
     e, sk, pk = env
     e.set_ring_mode(mode)
     try:

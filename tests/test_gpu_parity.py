@@ -155,8 +155,28 @@ def test_ring_mode_1_still_matches(env):
         e.set_ring_mode(2)
 
 
+def test_ring_mode_3_pair_engine(env):
+    """The pair engine (ring mode 3: lanes 2p / 2p + 1 evaluate the two sides of ring p and swap their encodings by shuffle)
+    agrees with the oracle on every ring shape: bool, choice (terminal points + sum proof), multi-choice, range proofs with
+    rings of 2 to 16 equations (pairs of one warp in different equations), QV ballots, the reference's tamper patterns."""
+    e, sk, pk = env
+    e.set_ring_mode(3)
+    try:
+        PC.check_verify_bool(e, pk, n=333, seed=7)
+        PC.check_verify_bool(e, pk, n=31, seed=8)          # a partial warp: 62 lanes, the last pair next to exited lanes
+        PC.check_verify_choice(e, pk, options=5, n=203, single=True, frac=0.2)
+        PC.check_verify_choice(e, pk, options=3, n=37, single=False, frac=0.3)
+        for bound in (2, 5, 100, 1000, 65536):
+            PC.check_verify_range(e, pk, bound, n=45, frac=0.25)
+        PC.check_verify_qv(e, pk, sk, n=12)
+        PC.check_fuzz_differential(e, pk, n=600, seed=303)
+    finally:
+        e.set_ring_mode(2)
+
+
 def test_ring_mode_auto(env):
-    """Default engine choice: small chunks go through the per-equation pipeline, large ones through k_ring; a batch
+    """Default engine choice: small chunks go through the pair engine (rings only) or the per-equation pipeline (choice
+    ballots: rings + sum proof), large ones through k_ring; a batch
     that mixes both (a 30 310-ballot ramp-up chunk and a full 257 638-ballot chunk through k_ring + a 5 052-ballot remainder,
     a third of a wave, through the pipeline) must still give tiled verdicts and the tally of the accepted ballots."""
     e, sk, pk = env

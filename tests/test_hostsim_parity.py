@@ -55,6 +55,22 @@ def test_per_equation_pipeline(env):
         e.set_ring_mode(0)
 
 
+def test_pair_engine(env):
+    """Ring mode 3 (two lanes per ring, for small chunks): the per-side evaluation, single-point encoding and transcript
+    hand-over of the CUDA kernel, run lane after lane on the CPU-compiled bodies -- bool, choice (deferred terminal
+    encodings + sum proof), range proofs with rings of different lengths, QV ballots."""
+    e = env[0]
+    e.set_ring_mode(3)
+    try:
+        PC.check_verify_bool(e, env[2], n=24)
+        PC.check_verify_choice(e, env[2], options=3, n=8, single=True, frac=0.5)
+        PC.check_verify_choice(e, env[2], options=2, n=6, single=False, frac=0.5)
+        PC.check_verify_range(e, env[2], 21, n=6, frac=0.3)
+        PC.check_verify_range(e, env[2], 100, n=4, frac=0.5)
+    finally:
+        e.set_ring_mode(0)
+
+
 def test_choice_tally_round_trip(env):
     PC.check_choice_tally_decrypts(env[0], env[2], env[1], options=3, n=7)
 

@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
 """Latency of small batches (BASELINE configs[0]: 10 000 Boolean ciphertexts) under the three ring-engine settings:
-0 = chosen per chunk (library default), 1 = per-equation pipeline, 2 = one thread per ring (k_ring)."""
+0 = chosen per chunk (library default), 1 = per-equation pipeline, 2 = one thread per ring (k_ring), 3 = two lanes per ring
+(k_ring_pair)."""
 import pathlib, sys, time
 ROOT = pathlib.Path(__file__).resolve().parent.parent
 sys.path[:0] = [str(ROOT), str(ROOT / "tests")]
@@ -21,14 +22,15 @@ def tile(a, n):
 def run(name, fn, sizes):
     for n in sizes:
         row = []
-        for mode in (0, 1, 2):
+        for mode in (0, 1, 2, 3):
             e.set_ring_mode(mode)
             fn(n)
             t0 = time.perf_counter()
             for _ in range(5):
                 fn(n)
             row.append((time.perf_counter() - t0) / 5)
-        print("%-28s n=%7d  auto %.2f ms  pipeline %.2f ms  k_ring %.2f ms  (%.0f items/s auto)" % (name, n, row[0] * 1e3, row[1] * 1e3, row[2] * 1e3, n / row[0]))
+        print("%-28s n=%7d  auto %.2f ms  pipeline %.2f ms  k_ring %.2f ms  pair %.2f ms  (%.0f items/s auto)" % (name, n, row[0] * 1e3, row[1] * 1e3, row[2] * 1e3, row[3] * 1e3, n / row[0]))
+    e.set_ring_mode(0)
 
 
 bc, bp = O.gen_bool_batch(pk, W.SEED_CHOICE, 1024)
