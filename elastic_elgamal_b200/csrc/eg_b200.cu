@@ -322,33 +322,36 @@ static eg_status launch_ring(eg_ctx *ctx, ring_params &P) {
     return EG_SUCCESS;
 }
 
-// Pair engine (ring mode 3): two lanes per ring, one launch for all equations of a small chunk.  Accounted like k_ring
-// (tasks = equation sides), under its own kind (3).
-static eg_status launch_ring_pair(eg_ctx *ctx, ring_params &P) {
+// Pair engine (ring mode 3): two lanes per ring, one launch for all equations of a small chunk; the job's extra single-use
+// equation sides (X.n_slots > 0: the sum proof of an EncryptedChoice) ride along as further lanes of the same launch, so the
+// longest chain of the launch stays the ring's.  Accounted like k_ring (tasks = equation sides), under its own kind (3).
+static eg_status launch_ring_pair(eg_ctx *ctx, ring_params &P, const commit_params &X) {
     size_t sides = 0;
     for (uint32_t r = 0; r < P.n_rings; r++) sides += 2 * (size_t)P.sizes[r];
     sides *= P.n;
-    const size_t total = P.n * (size_t)P.n_rings;
+    const size_t total = P.n * (size_t)P.n_rings, extra = P.n * (size_t)X.n_slots;
     bool short_rings = true;
     for (uint32_t r = 0; r < P.n_rings; r++) short_rings = short_rings && P.sizes[r] <= 2;
 #ifdef EG_HOSTSIM
     TRY(ensure(ctx, ctx->ring_scratch, 2 * EG_VTAB_WORDS * 4));
     P.scratch = (uint32_t *)ctx->ring_scratch.p;
-    cudaEvent_t e_stop = stat_begin(ctx, 3, sides);
+    cudaEvent_t e_stop = stat_begin(ctx, 3, sides + extra);
     if (short_rings) { EG_FOR_HOST(total, ring_pair_host<EG_VCHUNKS_SHORT>(P, tid % P.n, (uint32_t)(tid / P.n), P.scratch, P.table_g, P.table_k)) }
     else { EG_FOR_HOST(total, ring_pair_host<EG_VCHUNKS_LONG>(P, tid % P.n, (uint32_t)(tid / P.n), P.scratch, P.table_g, P.table_k)) }
+    EG_FOR_HOST(extra, commit_body(X, tid % X.n, (int)(tid / X.n), X.table_g, X.table_k))
 #else
     TRY(ensure(ctx, ctx->ring_scratch, 2 * total * EG_VTAB_WORDS * 4));
     P.scratch = (uint32_t *)ctx->ring_scratch.p;
-    cudaEvent_t e_stop = stat_begin(ctx, 3, sides);
-    if (short_rings) k_ring_pair<EG_VCHUNKS_SHORT><<<grid_for(2 * total, EG_PAIR_THREADS), EG_PAIR_THREADS, 0, ctx->stream>>>(P);
-    else k_ring_pair<EG_VCHUNKS_LONG><<<grid_for(2 * total, EG_PAIR_THREADS), EG_PAIR_THREADS, 0, ctx->stream>>>(P);
+    cudaEvent_t e_stop = stat_begin(ctx, 3, sides + extra);
+    const unsigned grid = grid_for(2 * total + extra, EG_PAIR_THREADS);
+    if (short_rings) k_ring_pair<EG_VCHUNKS_SHORT><<<grid, EG_PAIR_THREADS, 0, ctx->stream>>>(P, X);
+    else k_ring_pair<EG_VCHUNKS_LONG><<<grid, EG_PAIR_THREADS, 0, ctx->stream>>>(P, X);
 #endif
     cudaEventRecord(e_stop, ctx->stream);
     ctx->launches++;
     ctx->commit_launches++;
-    ctx->commit_tasks += sides;
-    ctx->call_commit_tasks += sides;
+    ctx->commit_tasks += sides + extra;
+    ctx->call_commit_tasks += sides + extra;
     ctx->call_commit_launches++;
     return EG_SUCCESS;
 }

@@ -1441,14 +1441,16 @@ EG_HD void scalars_validate_body(size_t i, const uint8_t *s, uint8_t *ok) {
 }
 
 // planar encoding 0 of every item -> 32-byte records; ok = 0 and the identity encoding for flagged (malformed) items
-struct unpack_params { size_t n; const uint32_t *commit; const uint32_t *flags; uint8_t *out; uint8_t *ok; };
+struct unpack_params { size_t n; uint32_t n_out; const uint32_t *commit; const uint32_t *flags; uint8_t *out; uint8_t *ok; };   // n_out encodings per item
 
 EG_HD void unpack_body(const unpack_params &P, size_t item) {
     uint32_t w[8];
     const bool bad = (P.flags[item] & 1u) != 0;
-    planar_load_words(w, P.commit, P.n, 0, 8, item);
-    if (bad) for (int k = 0; k < 8; k++) w[k] = 0;
-    store32_bytes(P.out + 32 * item, w);
+    for (uint32_t q = 0; q < P.n_out; q++) {
+        planar_load_words(w, P.commit, P.n, q, 8, item);
+        if (bad) for (int k = 0; k < 8; k++) w[k] = 0;
+        store32_bytes(P.out + 32 * (item * P.n_out + q), w);
+    }
     P.ok[item] = bad ? 0 : 1;
 }
 

@@ -203,6 +203,15 @@ class Engine:
         self._check(self.lib.eg_multi_mul_batch(self.h, n, t, _addr(scalars), _addr(points), _addr(out), _addr(ok)))
         return out, ok.astype(bool)
 
+    def ciphertexts_lincomb(self, scalars, cts):
+        """Ciphertext Add / Sub / Neg / Mul<&Scalar> (encryption.rs:160-226) as out[i] = sum_j [scalars[i][j]] cts[i][j]."""
+        scalars = _u8(scalars)
+        n, t = scalars.shape[0], scalars.shape[1]
+        scalars, cts = scalars.reshape(n, t, 32), _u8(cts, (n, t, 64))
+        out, ok = np.empty((n, 64), np.uint8), np.empty(n, np.uint8)
+        self._check(self.lib.eg_ciphertexts_lincomb_batch(self.h, n, t, _addr(scalars), _addr(cts), _addr(out), _addr(ok)))
+        return out, ok.astype(bool)
+
     def ciphertexts_sum(self, parts):
         parts = _u8(parts)
         n_parts, n_cts = parts.shape[0], parts.shape[1]

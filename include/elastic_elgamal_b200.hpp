@@ -174,6 +174,22 @@ class Engine {
     }
 
     // ballots.iter().map(|b| b.verify(&params)) + the tally fold (quadratic_voting.rs:291-329)
+    // The Ciphertext operators (src/encryption.rs:160-226) over a batch: out[i] = sum_j rows[i][j].first * rows[i][j].second.
+    // a + b = {(1, a), (1, b)}; a - b = {(1, a), (l - 1, b)}; -a = {(l - 1, a)}; a * k = {(k, a)}.
+    std::vector<Ciphertext> combine_ciphertexts(const std::vector<std::vector<std::pair<Scalar, Ciphertext>>> &rows) {
+        const size_t n = rows.size(), terms = n ? rows[0].size() : 1;
+        std::vector<uint8_t> s, c, out(n * 64), ok(n);
+        for (const auto &row : rows) {
+            if (row.size() != terms) throw Error(EG_ERR_INVALID_ARG, "rows must have the same number of terms");
+            for (const auto &t : row) s.insert(s.end(), t.first.begin(), t.first.end());
+            for (const auto &t : row) append(c, t.second);
+        }
+        check(eg_ciphertexts_lincomb_batch(ctx_, n, (uint32_t)terms, s.data(), c.data(), out.data(), ok.data()));
+        for (size_t i = 0; i < n; i++)
+            if (!ok[i]) throw Error(EG_ERR_INVALID_ARG, "malformed element or scalar in a ciphertext combination");
+        return to_ciphertexts(out);
+    }
+
     ChoiceBatchResult verify_qv_batch(uint32_t options, uint64_t credits, const std::vector<QuadraticVotingBallot> &ballots) {
         eg_qv_params qp;
         check(eg_qv_params_new(options, credits, &qp));

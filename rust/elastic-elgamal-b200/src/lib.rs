@@ -23,7 +23,7 @@ use elastic_elgamal::{
         ChoiceParams, ChoiceVerificationError, EncryptedChoice, MultiChoice, QuadraticVotingBallot, QuadraticVotingError,
         QuadraticVotingParams, SingleChoice,
     },
-    group::{ElementOps, Ristretto},
+    group::{ElementOps, Ristretto, ScalarOps},
     sharing::{self, PublicKeySet},
     CandidateDecryption, Ciphertext, CommitmentEquivalenceProof, LogEqualityProof, ProofOfPossession, PublicKey,
     RangeDecomposition, RangeProof, RingProof, SumOfSquaresProof, VerifiableDecryption, VerificationError,
@@ -36,6 +36,7 @@ use std::{
 };
 
 type Element = <Ristretto as ElementOps>::Element;
+type Scalar = <Ristretto as ScalarOps>::Scalar;
 
 /// API / CUDA / NCCL failures (never a per-item outcome).
 #[derive(Debug)]
@@ -598,6 +599,32 @@ impl Engine {
             sys::eg_combine_decrypt_batch(self.ctx, t as u32, idx.as_ptr(), n, t as u32, c.as_ptr(), sh.as_ptr(), table.table, values.as_mut_ptr(), found.as_mut_ptr())
         })?;
         Ok(values.iter().zip(found).map(|(&v, f)| (f == 1).then_some(v)).collect())
+    }
+
+    // ------------------------------------------------------------------ ciphertext operators
+
+    /// `Σ_j ciphertexts[i][j] * scalars[i][j]` for every row `i` (rows of equal length ≤ 16): the `Add`, `Sub`, `Neg` and
+    /// `Mul<&Scalar>` impls of `Ciphertext` (encryption.rs:160-226) over a batch — `a + b` = scalars `(1, 1)`,
+    /// `a - b` = `(1, -1)`, `-a` = `(-1)`, `a * k` = `(k)`.
+    pub fn combine_ciphertexts(&self, rows: &[(Vec<Scalar>, Vec<Ciphertext<Ristretto>>)]) -> Result<Vec<Ciphertext<Ristretto>>, EngineError> {
+        let n = rows.len();
+        let terms = rows.first().map_or(1, |r| r.0.len());
+        let (mut s, mut c) = (Vec::with_capacity(n * terms * 32), Vec::with_capacity(n * terms * 64));
+        for (scalars, cts) in rows {
+            assert!(scalars.len() == terms && cts.len() == terms, "rows must have the same number of terms");
+            for k in scalars {
+                let mut b = [0_u8; 32];
+                Ristretto::serialize_scalar(k, &mut b);
+                s.extend_from_slice(&b);
+            }
+            for ct in cts {
+                c.extend_from_slice(&ct.to_bytes());
+            }
+        }
+        let (mut out, mut ok) = (vec![0_u8; n * 64], vec![0_u8; n]);
+        self.check(unsafe { sys::eg_ciphertexts_lincomb_batch(self.ctx, n, terms as u32, s.as_ptr(), c.as_ptr(), out.as_mut_ptr(), ok.as_mut_ptr()) })?;
+        debug_assert!(ok.iter().all(|&f| f == 1), "typed inputs are canonical");
+        Ok(ciphertexts(&out))
     }
 
     // ------------------------------------------------------------------ creation side

@@ -779,6 +779,46 @@ def check_multi_mul(e, n=12):
                 assert ok[i] and bytes(out[i]) == expected[i], (terms, i)
 
 
+def check_ciphertext_ops(e, pk, n=12):
+    """Ciphertext Add / Sub / Neg / Mul<&Scalar> (encryption.rs:160-226) through eg_ciphertexts_lincomb_batch against the
+    oracle's point arithmetic, incl. a - a = the identity ciphertext, an undecodable element and a non-canonical scalar."""
+    rng = O.rng_from_seed(bytes([11] * 32))
+    one, minus_one = sc(1), sc(W.L - 1)
+    cts = [O.encrypt(pk, i, rng) for i in range(2 * n)]
+    ks = [O.scalar_reduce_wide(O.rng_block(rng)) for _ in range(n)]
+
+    def lin(terms):                                     # [(scalar, ct)] -> 64 bytes
+        r, b = bytes(32), bytes(32)
+        for s_, ct in terms:
+            r = O.point_add(r, O.point_mul(s_, ct[:32]))
+            b = O.point_add(b, O.point_mul(s_, ct[32:]))
+        return r + b
+
+    def run(rows):
+        t = len(rows[0])
+        S = np.frombuffer(b"".join(s_ for row in rows for s_, _ in row), np.uint8).reshape(len(rows), t, 32)
+        C_ = np.frombuffer(b"".join(ct for row in rows for _, ct in row), np.uint8).reshape(len(rows), t, 64)
+        out, ok = e.ciphertexts_lincomb(S, C_)
+        return [bytes(o) for o in out], ok
+
+    add = [[(one, cts[2 * i]), (one, cts[2 * i + 1])] for i in range(n)]
+    sub = [[(one, cts[2 * i]), (minus_one, cts[2 * i + 1])] for i in range(n)]
+    sub[0] = [(one, cts[0]), (minus_one, cts[0])]       # a - a
+    neg = [[(minus_one, cts[i])] for i in range(n)]
+    mul = [[(ks[i], cts[i])] for i in range(n)]
+    mul[0] = [(sc(0), cts[0])]
+    for rows in (add, sub, neg, mul):
+        out, ok = run(rows)
+        assert ok.all() and out == [lin(row) for row in rows]
+    assert run(sub)[0][0] == bytes(64) and run(mul)[0][0] == bytes(64)
+    # a + b decrypts to the sum of the plaintexts: homomorphism (encryption.rs:96-112), checked on the encodings
+    bad = [row[:] for row in add]
+    bad[1][0] = (one, W.BAD_POINT + cts[2][32:])
+    bad[2][1] = (W.BAD_SCALAR, cts[5])
+    out, ok = run(bad)
+    assert not ok[1] and not ok[2] and out[1] == bytes(64) and out[2] == bytes(64) and ok[0] and all(ok[3:])
+
+
 # ---------------------------------------------------------------- randomized differential tests
 
 def _flip_random(arrs, rnd, items, flips_per_item=1):

@@ -196,6 +196,10 @@ def test_encrypt_plain_and_zero(env):
         env[0].set_receiver(env[2])
 
 
+def test_ciphertext_ops(env):
+    PC.check_ciphertext_ops(env[0], env[2], n=6)
+
+
 def test_multi_mul(env):
     PC.check_multi_mul(env[0], n=6)
 
