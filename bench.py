@@ -44,6 +44,9 @@ for p in (str(ROOT), str(ROOT / "tests")):
 FIELD_OPS_PER_SIDE = 4956 / 2 + 280                      # 2758
 FIELD_OPS_3TERM_SUM = 0.75 * 4956                        # a 3-term multi-scalar sum (Lagrange recombination)
 IMAD_PER_FIELD_OP = 144
+# executed work: one fixed-base term = one mixed addition (7 field operations) per window of the wide tables (24-bit windows:
+# 11; elastic_elgamal_b200/csrc/ge.cuh EG_WIDE_BITS)
+FIXED_TERM_OPS = 11 * 7
 L2_BYTES = 126 << 20
 
 
@@ -59,7 +62,7 @@ def parse_args():
     ap.add_argument("--unique", type=int, default=0, help="distinct oracle-generated items that are tiled (0 = per config)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="items in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--ring-mode", type=int, default=-1, choices=[-1, 0, 1, 2], help="-1: per config (2 = k_ring for the large batches)")
+    ap.add_argument("--ring-mode", type=int, default=-1, choices=[-1, 0, 1, 2, 3], help="-1: per config (2 = k_ring for the large batches)")
     ap.add_argument("--chunk", type=int, default=0, help="items per internal chunk (0 = library default)")
     return ap.parse_args()
 
@@ -119,7 +122,7 @@ class Bool(Workload):
     bytes_per_item = 160
     ref_field_ops_per_item = 12.1e3
     ring_mode = 0                         # the library picks the pair engine (k_ring_pair) for a batch this small
-    executed_field_ops_per_task = 1949.5
+    executed_field_ops_per_task = 1949.5 - 1.25 * (112 - FIXED_TERM_OPS)      # as config 2's ring sides
 
     def make(self, unique, threads):
         import oracle as O
@@ -167,7 +170,7 @@ class Choice(Workload):
     has_tally = True
     # what k_ring executes per equation side of a two-equation ring: 2 x 1603 table build + 4 sides x (435 + 497
     # + 112) + 112 for [e a]G + 304 for encoding the first equation's pair
-    executed_field_ops_per_task = (2 * 1603 + 4 * (435 + 497 + 112) + 112 + 304) / 4
+    executed_field_ops_per_task = (2 * 1603 + 4 * (435 + 497 + FIXED_TERM_OPS) + FIXED_TERM_OPS + 304) / 4
 
     def make(self, unique, threads):
         import oracle as O
@@ -289,7 +292,7 @@ class Range(Workload):
     ref_field_ops_per_item = 185.5e3
     # k_ring<256,2,8> per side of a four-equation ring: 2 x 2072 table build (224 doublings + 56 additions per point) + 8 sides
     # x (196 + 497 + 112) + 3 x 112 for [e a]G + 3 x 304 encodings, over 8 sides
-    executed_field_ops_per_task = (2 * 2072 + 8 * (196 + 497 + 112) + 3 * 112 + 3 * 304) / 8
+    executed_field_ops_per_task = (2 * 2072 + 8 * (196 + 497 + FIXED_TERM_OPS) + 3 * FIXED_TERM_OPS + 3 * 304) / 8
 
     def make(self, unique, threads):
         import numpy as np

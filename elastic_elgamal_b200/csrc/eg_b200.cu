@@ -523,17 +523,25 @@ static void launch_verdict(eg_ctx *ctx, const verdict_params &P) {
 
 // wide fixed-base table of one base (ge.cuh): EG_WIDE_TABLE_WORDS words, followed by EG_WIDE_SCRATCH_WORDS of window bases
 #define EG_TABLE_ALLOC_BYTES ((EG_WIDE_TABLE_WORDS + EG_WIDE_SCRATCH_WORDS) * 4)
-static void launch_build_table(eg_ctx *ctx, const uint32_t *enc_words, int use_generator, uint32_t *table, uint32_t *status) {
-    uint32_t *bases = table + EG_WIDE_TABLE_WORDS;
-    const size_t fill = (size_t)EG_WIDE_WINDOWS * (EG_WIDE_ENTRIES / EG_WIDE_BLOCK);
+template <int BITS>
+static void launch_build_table_b(eg_ctx *ctx, const uint32_t *enc_words, int use_generator, uint32_t *table, uint32_t *status) {
+    uint32_t *bases = table + EG_BITS_TABLE_WORDS(BITS);
+    const size_t fill = (size_t)EG_BITS_WINDOWS(BITS) * (EG_BITS_ENTRIES(BITS) / EG_WIDE_BLOCK);
 #ifdef EG_HOSTSIM
-    wide_bases_body(enc_words, use_generator, bases, status);
-    EG_FOR_HOST(fill, wide_fill_body(tid, bases, table))
+    wide_bases_body<BITS>(enc_words, use_generator, bases, status);
+    EG_FOR_HOST(fill, wide_fill_body<BITS>(tid, bases, table))
 #else
-    k_wide_bases<<<1, 1, 0, ctx->stream>>>(enc_words, use_generator, bases, status);
-    k_wide_fill<<<grid_for(fill, 64), 64, 0, ctx->stream>>>(bases, table);
+    k_wide_bases<BITS><<<1, 1, 0, ctx->stream>>>(enc_words, use_generator, bases, status);
+    k_wide_fill<BITS><<<grid_for(fill, 64), 64, 0, ctx->stream>>>(bases, table);
 #endif
     ctx->launches += 2;
+}
+static void launch_build_table(eg_ctx *ctx, const uint32_t *enc_words, int use_generator, uint32_t *table, uint32_t *status) {
+    launch_build_table_b<EG_WIDE_BITS>(ctx, enc_words, use_generator, table, status);
+}
+// narrow (EG_NARROW_BITS) table of a per-call base: EG_NARROW_ALLOC_WORDS words at `table`
+static void launch_build_narrow_table(eg_ctx *ctx, const uint32_t *enc_words, uint32_t *table, uint32_t *status) {
+    launch_build_table_b<EG_NARROW_BITS>(ctx, enc_words, 0, table, status);
 }
 
 static void launch_admissible(eg_ctx *ctx, const uint64_t *values, int count, uint32_t *adm) {

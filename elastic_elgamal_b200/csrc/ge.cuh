@@ -195,14 +195,26 @@ EG_HD void ge_encode(uint32_t w[8], const ge_ext &p) {
 //
 // [b] F for the batch-constant bases (G, the receiver key K, the Pedersen base H) never doubles: the scalar is cut into
 // EG_WIDE_WINDOWS signed windows of EG_WIDE_BITS bits, b = sum_i d_i 2^(W i) with d_i in [-2^(W-1), 2^(W-1)), and the table
-// holds every |d| 2^(W i) F as an affine Niels point (96 B).  W = 16: 16 windows x 32768 entries = 48 MiB per base; G and
-// K together stay mostly resident in the 126 MB L2 (each lookup is three 32-byte sectors); [b] F costs 16 mixed additions
-// (7 multiplications each).  Measured on B200 (profiles/r1_wide_tables_ab.txt): W = 11 / 13 / 15 / 16 ->
-// 1.860 / 1.895 / 1.922 / 1.934 M ballots/s against 1.865 M with 8-bit windows over 4 chunks staged in shared memory.
+// holds every |d| 2^(W i) F as an affine Niels point (96 B); [b] F costs one mixed addition (7 multiplications) per window.
+// The width is a memory-for-arithmetic trade that HBM decides: every lookup is an independent 96-byte read (three 32-byte
+// sectors) that is requested one window ahead, so the tables need not fit the L2.  Measured on B200, 5-option ballots/s:
+//   W = 11 / 13 / 15 / 16 (24 .. 16 windows, <= 48 MiB per base): 1.860 / 1.895 / 1.922 / 1.934 M (profiles/r1_wide_tables_ab.txt;
+//     8-bit windows over 4 chunks staged in shared memory: 1.865 M);
+//   W = 16 / 20 / 24 (16 / 13 / 11 windows; 48 MiB / 0.61 GiB / 8.25 GiB per base): 2.072 / 2.100 / 2.128 M, range proofs
+//     905 / 922 / 934 k/s (profiles/r2_ab_wide_bits.txt).
+// W = 24 is the device default: 11 additions per fixed-base term, 2 x 8.25 GiB for G and K (+ 8.25 GiB with a Pedersen base)
+// out of 180 GB of HBM, built on the device in tens of milliseconds.  W = 26 .. 31 would save one more addition (10 windows)
+// for 4 x .. 128 x the memory.  A build with -DEG_WIDE_BITS=16 (or 20) keeps the small tables; the CPU test harness
+// (tests/hostsim) uses 16.  W must be a multiple of 4 (ge_fixed_adds_ct).
 
 #ifndef EG_WIDE_BITS
+#ifdef EG_HOSTSIM
 #define EG_WIDE_BITS 16
+#else
+#define EG_WIDE_BITS 24
 #endif
+#endif
+static_assert(EG_WIDE_BITS % 4 == 0 && EG_WIDE_BITS >= 8 && EG_WIDE_BITS <= 28, "EG_WIDE_BITS: a multiple of 4 in 8..28");
 #ifndef EG_WIDE_PREFETCH
 #define EG_WIDE_PREFETCH 1
 #endif
@@ -211,6 +223,13 @@ EG_HD void ge_encode(uint32_t w[8], const ge_ext &p) {
 #define EG_WIDE_TABLE_WORDS ((size_t)EG_WIDE_WINDOWS * EG_WIDE_ENTRIES * 24)
 #define EG_WIDE_BLOCK 32                                              // entries normalised together by the table builder
 #define EG_WIDE_SCRATCH_WORDS (EG_WIDE_WINDOWS * 32)                  // window bases 2^(W i) F (extended), behind the table
+// Narrow tables (16-bit windows, 48 MiB, ~1 ms to build) for bases that are constant for one call only -- the participant
+// keys of a key set (PublicKeySet::verify_share): same layout and walk, built per call and cached by key bytes.
+#define EG_NARROW_BITS 16
+#define EG_BITS_WINDOWS(B) ((254 + (B) - 1) / (B))
+#define EG_BITS_ENTRIES(B) (1 << ((B) - 1))
+#define EG_BITS_TABLE_WORDS(B) ((size_t)EG_BITS_WINDOWS(B) * EG_BITS_ENTRIES(B) * 24)
+#define EG_NARROW_ALLOC_WORDS (EG_BITS_TABLE_WORDS(EG_NARROW_BITS) + EG_BITS_WINDOWS(EG_NARROW_BITS) * 32)
 
 EG_HD void ge_niels_load(ge_niels &n, const uint32_t *tbl, int idx) {
     const uint32_t *e = tbl + idx * 24;
@@ -349,14 +368,16 @@ EG_HD int sc_digit8(const uint32_t r[8], int i) { return (int)((r[i >> 2] >> ((i
 
 // EG_WIDE_BITS-bit signed windows, produced low to high with a running carry: digit i of `a` in [-2^(W-1), 2^(W-1)).
 // a < 2^253 and W * EG_WIDE_WINDOWS >= 254, so the top window never carries out.
-EG_HD int sc_wide_digit(const sc &a, int i, uint32_t &carry) {
-    const int o = i * EG_WIDE_BITS, word = o >> 5, sh = o & 31;
+template <int BITS>
+EG_HD int sc_wide_digit_b(const sc &a, int i, uint32_t &carry) {
+    const int o = i * BITS, word = o >> 5, sh = o & 31;
     uint32_t v = word < 8 ? a.v[word] >> sh : 0u;
-    if (sh + EG_WIDE_BITS > 32 && word + 1 < 8) v |= a.v[word + 1] << (32 - sh);
-    v = (v & ((1u << EG_WIDE_BITS) - 1u)) + carry;
-    carry = (v >> (EG_WIDE_BITS - 1)) != 0u;         // v >= 2^(W-1) (v <= 2^W): borrow 2^W from the next window
-    return (int)v - (int)(carry << EG_WIDE_BITS);
+    if (sh + BITS > 32 && word + 1 < 8) v |= a.v[word + 1] << (32 - sh);
+    v = (v & ((1u << BITS) - 1u)) + carry;
+    carry = (v >> (BITS - 1)) != 0u;                 // v >= 2^(W-1) (v <= 2^W): borrow 2^W from the next window
+    return (int)v - (int)(carry << BITS);
 }
+EG_HD int sc_wide_digit(const sc &a, int i, uint32_t &carry) { return sc_wide_digit_b<EG_WIDE_BITS>(a, i, carry); }
 
 // the (at most two) 128-byte lines of a 96-byte table entry, requested ahead of its use
 EG_HD void ge_wide_prefetch(const uint32_t *entry) {
@@ -395,13 +416,19 @@ EG_HD void ge_window_table(ge_cached tbl[8], const ge_ext &P) {
 }
 
 // acc += [b] F from the wide table of F (EG_WIDE_WINDOWS mixed additions, no doublings)
-static EG_HD_NOINLINE void ge_fixed_accumulate(ge_ext &acc, const uint32_t *wide, const sc &b) {
+template <int BITS>
+static EG_HD_NOINLINE void ge_fixed_accumulate_b(ge_ext &acc, const uint32_t *wide, const sc &b) {
     uint32_t carry = 0;
 #pragma unroll 1
-    for (int i = 0; i < EG_WIDE_WINDOWS; i++) {
-        const int d = sc_wide_digit(b, i, carry);
-        if (d != 0) ge_hot_add_niels(acc, wide + (size_t)i * (EG_WIDE_ENTRIES * 24), (d < 0 ? -d : d) - 1, d < 0);
+    for (int i = 0; i < EG_BITS_WINDOWS(BITS); i++) {
+        const int d = sc_wide_digit_b<BITS>(b, i, carry);
+        if (d != 0) ge_hot_add_niels(acc, wide + (size_t)i * (EG_BITS_ENTRIES(BITS) * 24), (d < 0 ? -d : d) - 1, d < 0);
     }
+}
+// `narrow`: the table has EG_NARROW_BITS-bit windows (a per-call base) instead of the context's EG_WIDE_BITS
+EG_HD void ge_fixed_accumulate(ge_ext &acc, const uint32_t *wide, const sc &b, bool narrow = false) {
+    if (EG_NARROW_BITS != EG_WIDE_BITS && narrow) ge_fixed_accumulate_b<EG_NARROW_BITS>(acc, wide, b);
+    else ge_fixed_accumulate_b<EG_WIDE_BITS>(acc, wide, b);
 }
 
 template <int NV, int NF>
@@ -435,7 +462,8 @@ EG_HD void ge_msm_chain(ge_ext &out, const ge_ext *P, const sc *a, const uint32_
 // share verification (two per-item bases), SumOfSquaresProof (G, K and one per-item base; (n+2)-term sums) and
 // Lagrange recombination.  Replaces the general vartime_multi_mul (ristretto.rs:139-146).
 template <int MAXV>
-EG_HD void ge_msm_chain_rt(ge_ext &out, int nv, const ge_ext *P, const sc *a, int nf, const uint32_t *const *ftab, const sc *b) {
+EG_HD void ge_msm_chain_rt(ge_ext &out, int nv, const ge_ext *P, const sc *a, int nf, const uint32_t *const *ftab, const sc *b,
+                           const bool *narrow = nullptr) {
     EG_ALIGN16 ge_cached tbl[MAXV][8];
     uint32_t ra[MAXV][8];
 #pragma unroll 1
@@ -456,7 +484,7 @@ EG_HD void ge_msm_chain_rt(ge_ext &out, int nv, const ge_ext *P, const sc *a, in
         }
     }
 #pragma unroll 1
-    for (int f = 0; f < nf; f++) ge_fixed_accumulate(acc, ftab[f], b[f]);
+    for (int f = 0; f < nf; f++) ge_fixed_accumulate(acc, ftab[f], b[f], narrow && narrow[f]);
     out = acc;
 }
 
@@ -589,10 +617,11 @@ static EG_HD_NOINLINE void ge_eval64(ge_ext &out, const uint32_t *vtab, const sc
 
 // Constant-time form of ge_fixed_adds for SECRET scalars (the provers' randomness r and nonces x; the reference uses the
 // constant-time G::mul_generator / multi_mul there, src/proofs/ring.rs:99,115-116).  The scalar is cut into 64 signed
-// 4-bit windows; window i needs |d| * 16^i F with |d| <= 8, which is entry |d| * 16^(i mod 4) of wide window i / 4, so no
-// second table is needed.  Every window reads all eight candidates and keeps one with masks, conditionally negates with
-// masks and always adds (d = 0 adds the identity in Niels form): no branch and no address depends on the scalar.  64 mixed
-// additions and 512 entry reads per base instead of 16 and 16: about 4 x the fixed-base work (eg_ctx_set_prover_mode).
+// 4-bit windows; window i needs |d| * 16^i F with |d| <= 8, which is entry |d| * 16^(i mod N) of wide window i / N
+// (N = EG_WIDE_BITS / 4 nibbles per wide window), so no second table is needed.  Every window reads all eight candidates and
+// keeps one with masks, conditionally negates with masks and always adds (d = 0 adds the identity in Niels form): no branch
+// and no address depends on the scalar.  64 mixed additions and 512 entry reads per base instead of EG_WIDE_WINDOWS of each:
+// four to six times the fixed-base work (eg_ctx_set_prover_mode).
 EG_HD void ge_fixed_adds_ct(ge_ext &acc, ge_p1p1 &t, int nf, const uint32_t *ftab0, const sc &b0, const uint32_t *ftab1, const sc &b1) {
 #pragma unroll 1
     for (int f = 0; f < nf; f++) {
@@ -604,8 +633,9 @@ EG_HD void ge_fixed_adds_ct(ge_ext &acc, ge_p1p1 &t, int nf, const uint32_t *fta
             const int d = sc_digit4(ra, i);                         // secret, in [-8, 7]
             const uint32_t sign = (uint32_t)(d >> 31);              // all ones when negative
             const uint32_t mag = ((uint32_t)d ^ sign) - sign;       // |d|
-            const uint32_t *win = ft + (size_t)(i >> 2) * (EG_WIDE_ENTRIES * 24);
-            const uint32_t stride = 1u << (4 * (i & 3));
+            constexpr int NIB = EG_WIDE_BITS / 4;                    // 4-bit windows per wide window
+            const uint32_t *win = ft + (size_t)(i / NIB) * (EG_WIDE_ENTRIES * 24);
+            const uint32_t stride = 1u << (4 * (i % NIB));
             uint32_t e[24];
             for (int w = 0; w < 24; w++) e[w] = 0;
             e[0] = 1; e[8] = 1;                                     // identity: (y + x, y - x, 2dxy) = (1, 1, 0)

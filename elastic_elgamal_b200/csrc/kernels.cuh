@@ -242,7 +242,7 @@ struct msm_slot {
     uint32_t out_index;
     uint32_t p_index[EG_MSM_MAXV];   // planar point index, or index into const_pts when bit 31 is set
     scalar_src vs[EG_MSM_MAXV];
-    uint8_t fbase[2];           // 0: G, 1: K, 2: H (Pedersen blinding base, eg_ctx_set_blinding_base)
+    uint8_t fbase[2];           // 0: G, 1: K, 2: H (Pedersen blinding base, eg_ctx_set_blinding_base), 3 + j: per-call narrow table j
     uint8_t term;               // out_enc == 2: index of the half-scalar point in msm_params::term_pts (encoded by k_terminal)
     uint8_t pad2;
     scalar_src fs[2];
@@ -261,6 +261,7 @@ struct msm_params {
     uint32_t *pts_out;          // planar points out
     const uint32_t *table_g, *table_k;
     const uint32_t *table_h;    // may be null when no slot uses base 2
+    const uint32_t *table_x;    // per-call narrow tables (EG_NARROW_ALLOC_WORDS apart), null when no slot uses a base >= 3
     uint32_t *term_pts;         // planar points of the deferred encodings (slots with out_enc == 2)
 };
 
@@ -281,6 +282,7 @@ EG_HD void msm_body(const msm_params &P, size_t item, int slot, const uint32_t *
     ge_ext pts[EG_MSM_MAXV];
     sc a[EG_MSM_MAXV], b[2];
     const uint32_t *ft[2];
+    bool narrow[2] = {false, false};
 #pragma unroll 1
     for (int v = 0; v < s.nv; v++) {
         if (s.p_index[v] & 0x80000000u) point_from_words32(pts[v], P.const_pts + (size_t)(s.p_index[v] & 0x7fffffffu) * 32);
@@ -289,17 +291,18 @@ EG_HD void msm_body(const msm_params &P, size_t item, int slot, const uint32_t *
     }
     for (int f = 0; f < s.nf; f++) {
         ft[f] = s.fbase[f] == 0 ? tab_g : (s.fbase[f] == 1 ? tab_k : tab_h);
+        if (s.fbase[f] >= 3) { ft[f] = P.table_x + (size_t)(s.fbase[f] - 3) * EG_NARROW_ALLOC_WORDS; narrow[f] = true; }
         load_scalar(b[f], P, s.fs[f], item);
     }
     ge_ext acc;
     if (s.out_enc == 2) {       // all scalars halved: acc = Q with 2 Q = the commitment, encoded later with its siblings
         for (int v = 0; v < s.nv; v++) { sc h; sc_half(h, a[v]); a[v] = h; }
         for (int f = 0; f < s.nf; f++) { sc h; sc_half(h, b[f]); b[f] = h; }
-        ge_msm_chain_rt<EG_MSM_MAXV>(acc, s.nv, pts, a, s.nf, ft, b);
+        ge_msm_chain_rt<EG_MSM_MAXV>(acc, s.nv, pts, a, s.nf, ft, b, narrow);
         planar_store_point(P.term_pts, P.n, s.term, item, acc);
         return;
     }
-    ge_msm_chain_rt<EG_MSM_MAXV>(acc, s.nv, pts, a, s.nf, ft, b);
+    ge_msm_chain_rt<EG_MSM_MAXV>(acc, s.nv, pts, a, s.nf, ft, b, narrow);
     if (s.out_point) planar_store_point(P.pts_out, P.n, s.out_index, item, acc);
     if (s.out_enc) {
         uint32_t w[8];
@@ -1356,6 +1359,7 @@ namespace eg {
 
 // Wide fixed-base table of F (ge.cuh "fixed-base tables"), F given as an encoding; two stages.
 // Stage 1 (one thread): status = 0 ok / 1 undecodable / 2 identity; bases[i] = 2^(W i) F, extended, 32 words each.
+template <int BITS>
 EG_HD void wide_bases_body(const uint32_t *enc_words, int use_generator, uint32_t *bases, uint32_t *status) {
     ge_ext F;
     bool ok = true;
@@ -1367,16 +1371,17 @@ EG_HD void wide_bases_body(const uint32_t *enc_words, int use_generator, uint32_
     }
     *status = !ok ? 1u : (ge_is_identity(F) ? 2u : 0u);
 #pragma unroll 1
-    for (int i = 0; i < EG_WIDE_WINDOWS; i++) {
+    for (int i = 0; i < EG_BITS_WINDOWS(BITS); i++) {
         point_to_words32(bases + i * 32, F);
-        if (i + 1 < EG_WIDE_WINDOWS) ge_hot_dbl(F, EG_WIDE_BITS);
+        if (i + 1 < EG_BITS_WINDOWS(BITS)) ge_hot_dbl(F, BITS);
     }
 }
 
 // Stage 2: thread tidx = (window i, block jb) writes entries m = jb * EG_WIDE_BLOCK + 1 .. + EG_WIDE_BLOCK of window i:
 // table[(i * EG_WIDE_ENTRIES + m - 1) * 24 ..] = affine Niels form of m 2^(W i) F; one inversion per block.
+template <int BITS>
 EG_HD void wide_fill_body(size_t tidx, const uint32_t *bases, uint32_t *table) {
-    const int blocks = EG_WIDE_ENTRIES / EG_WIDE_BLOCK;
+    const int blocks = EG_BITS_ENTRIES(BITS) / EG_WIDE_BLOCK;
     const int i = (int)(tidx / blocks), jb = (int)(tidx % blocks);
     ge_ext B, acc = ge_identity();
     point_from_words32(B, bases + i * 32);
@@ -1385,7 +1390,7 @@ EG_HD void wide_fill_body(size_t tidx, const uint32_t *bases, uint32_t *table) {
     const uint32_t first = (uint32_t)jb * EG_WIDE_BLOCK + 1;
     ge_p1p1 t;
 #pragma unroll 1
-    for (int bit = EG_WIDE_BITS - 1; bit >= 0; bit--) {
+    for (int bit = BITS - 1; bit >= 0; bit--) {
         ge_dbl(acc, acc);
         if ((first >> bit) & 1u) { ge_add_cached_p1p1(t, acc, cb, false); ge_p1p1_to_ext(acc, t); }
     }
@@ -1399,7 +1404,7 @@ EG_HD void wide_fill_body(size_t tidx, const uint32_t *bases, uint32_t *table) {
     }
     fe inv;
     fe_invert(inv, prod[EG_WIDE_BLOCK - 1]);
-    uint32_t *out = table + ((size_t)i * EG_WIDE_ENTRIES + first - 1) * 24;
+    uint32_t *out = table + ((size_t)i * EG_BITS_ENTRIES(BITS) + first - 1) * 24;
 #pragma unroll 1
     for (int k = EG_WIDE_BLOCK - 1; k >= 0; k--) {
         fe zi, x, y, u;

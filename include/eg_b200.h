@@ -67,7 +67,8 @@ enum {
 /* ---- context ------------------------------------------------------------------------------------ */
 
 /* Creates a context on CUDA device `device_id` (one context per GPU / per process rank).
- * Owns a stream, the fixed-base tables for G and for the receiver key, transcript prefixes, scratch. */
+ * Owns a stream, the fixed-base tables for G and for the receiver key (8.25 GiB of device memory each: 24-bit windows,
+ * DESIGN.md "Data layout"), transcript prefixes, scratch. */
 eg_status eg_ctx_create(int device_id, eg_ctx **out);
 void      eg_ctx_destroy(eg_ctx *ctx);
 /* Human-readable description of the last failure on this context ("" if none). Never NULL. */
@@ -383,11 +384,11 @@ eg_status eg_encrypt_qv_batch_seeded(eg_ctx *ctx, const eg_qv_params *params, si
 
 /* Side-channel posture of the encryption side (the reference: constant-time G::mul_generator / multi_mul and zeroizing
  * secret wrappers, src/proofs/ring.rs:97-116, src/group/mod.rs:79).
- *   constant_time = 0 (default): secret scalars (randomness r, nonces x) walk the 16-bit-window fixed-base tables with
+ *   constant_time = 0 (default): secret scalars (randomness r, nonces x) walk the wide-window (24-bit) fixed-base tables with
  *     secret-dependent addresses and skip zero digits -- fastest; appropriate when the GPU is not shared with an adversary.
  *   constant_time = 1: every fixed-base multiplication by a secret scalar uses 64 signed 4-bit windows, reads all eight
  *     candidate entries of a window and selects with masks, always adds; no branch or address depends on a secret scalar
- *     (about 4 x the fixed-base work).  Scalar arithmetic mod l is branch-free in both modes.  As in the reference, the
+ *     (64 instead of 11 additions per base).  Scalar arithmetic mod l is branch-free in both modes.  As in the reference, the
  *     *shape* of a ring proof's computation (which equation is the real one) follows the encrypted value.
  * In both modes the device scratch that held randomness, nonces, plaintext values and staged randomness blocks is zeroed
  * before a prover call returns.  Verification entry points only handle public data and stay variable-time. */

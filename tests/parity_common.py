@@ -16,15 +16,21 @@ def sc(x):
 
 
 def wide_window_edge_scalars():
-    """Scalars that sit on the digit boundaries of the signed fixed-base windows (ge.cuh sc_wide_digit: 16-bit windows,
-    digits in [-2^15, 2^15), carries rippling through runs of 0xffff / 0x7fff / 0x8000 chunks), all canonical (< l)."""
+    """Scalars that sit on the digit boundaries of the signed fixed-base windows (ge.cuh sc_wide_digit: W-bit windows,
+    digits in [-2^(W-1), 2^(W-1)), carries rippling through runs of all-ones / 0x7f..f / 0x80..0 chunks) for every window
+    width the library is built with (24 on the device, 16 in the CPU harness, 20 as a build option), all canonical (< l)."""
     out = []
-    for chunk in (0x8000, 0x7fff, 0xffff, 0x8001, 0x0001, 0xfffe):
-        x = sum(chunk << (16 * i) for i in range(16)) % L
-        out += [sc(x), sc(L - x)]
-    for k in (15, 16, 17, 31, 32, 47, 48, 63, 64, 127, 128, 239, 240, 247, 251, 252):
-        out += [sc(2**k), sc(2**k - 1), sc(L - 2**k), sc((2**k) + 0x8000), sc((0x7fff8000ffff0000 << k) % L)]
-    out += [sc(L - 2), sc((L - 1) // 2), sc((L + 1) // 2), sc(2**252 + 2**15), sc(2**252 - 2**15)]
+    for w in (16, 20, 24):
+        top, ones = 1 << (w - 1), (1 << w) - 1
+        for chunk in (top, top - 1, ones, top + 1, 1, ones - 1):
+            x = sum(chunk << (w * i) for i in range(256 // w + 1)) % L
+            out += [sc(x), sc(L - x)]
+        for k in (w - 1, w, w + 1, 2 * w - 1, 2 * w, 3 * w - 1, 3 * w, 5 * w, 240 - w, 240 - 1, 240):
+            out += [sc(2**k), sc(2**k - 1), sc(L - 2**k), sc((2**k) + top), sc(((((top - 1) << (3 * w)) | (top << (2 * w)) | (ones << w)) << k) % L)]
+        out += [sc(2**252 + top), sc(2**252 - top)]
+    for k in (31, 32, 63, 64, 127, 128, 247, 251, 252):
+        out += [sc(2**k), sc(2**k - 1), sc(L - 2**k)]
+    out += [sc(L - 2), sc((L - 1) // 2), sc((L + 1) // 2)]
     return out
 
 
