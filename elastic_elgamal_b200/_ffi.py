@@ -123,6 +123,7 @@ PROTOTYPES = {
     "eg_selftest_field": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_uint64, C.POINTER(C.c_uint64)]),
     "eg_ctx_set_chunk_items": (C.c_int32, [C.c_void_p, C.c_size_t]),
     "eg_ctx_set_ring_mode": (C.c_int32, [C.c_void_p, C.c_int]),
+    "eg_ctx_set_key_table_min": (C.c_int32, [C.c_void_p, C.c_size_t]),
 }
 
 

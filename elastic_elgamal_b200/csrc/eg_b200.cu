@@ -71,6 +71,11 @@ struct eg_ctx {
     int rprove_grid[3] = {0, 0, 0};
     int sumsq_prove_grid = 0, encrypt_grid = 0;
     dev_buf ring_scratch;
+    // per-call narrow fixed-base tables of the participant keys of a key set (api_sharing.inc), cached by key bytes
+    dev_buf xtab;
+    uint8_t xtab_key[8][32];
+    bool xtab_valid[8] = {false, false, false, false, false, false, false, false};
+    size_t key_table_min = 16384;   // eg_ctx_set_key_table_min
     // multi-GPU (comm.inc): NCCL communicator of a per-rank context (eg_ctx_attach_comm) or of a child of a multi-device
     // context (eg_ctx_create_multi); `children` is non-empty only for the latter's parent, which owns no device state
     void *comm = nullptr;
@@ -844,6 +849,13 @@ extern "C" eg_status eg_ctx_set_ring_mode(eg_ctx *ctx, int mode) {
     return EG_SUCCESS;
 }
 
+extern "C" eg_status eg_ctx_set_key_table_min(eg_ctx *ctx, size_t min_tallies) {
+    if (!ctx) return EG_ERR_INVALID_ARG;
+    ctx->key_table_min = min_tallies;
+    for (eg_ctx *c : ctx->children) c->key_table_min = min_tallies;
+    return EG_SUCCESS;
+}
+
 extern "C" eg_status eg_ctx_set_prover_mode(eg_ctx *ctx, int constant_time) {
     if (!ctx || constant_time < 0 || constant_time > 1) return EG_ERR_INVALID_ARG;
     ctx->prover_ct = constant_time;
@@ -897,7 +909,7 @@ extern "C" void eg_ctx_destroy(eg_ctx *ctx) {
     dev_buf *bufs[] = {&ctx->pts, &ctx->enc, &ctx->commit, &ctx->chal, &ctx->flags, &ctx->res[0], &ctx->res[1], &ctx->res[2],
                        &ctx->in[0], &ctx->in[1], &ctx->in[2], &ctx->in[3], &ctx->verdicts, &ctx->partial, &ctx->running,
                        &ctx->adm, &ctx->misc, &ctx->slots, &ctx->consts, &ctx->res_big, &ctx->ring_scratch,
-                       &ctx->in2[0], &ctx->in2[1], &ctx->in2[2], &ctx->term, &ctx->gather};
+                       &ctx->in2[0], &ctx->in2[1], &ctx->in2[2], &ctx->term, &ctx->gather, &ctx->xtab};
     for (dev_buf *b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->d_table_g) cudaFree(ctx->d_table_g);
     if (ctx->d_table_k) cudaFree(ctx->d_table_k);

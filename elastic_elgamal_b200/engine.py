@@ -107,6 +107,10 @@ class Engine:
     def set_ring_mode(self, mode):
         self._check(self.lib.eg_ctx_set_ring_mode(self.h, mode))
 
+    def set_key_table_min(self, min_tallies):
+        """Tallies per call from which verify_shares / verify_decryption build fixed-base tables for the keys (0 = always)."""
+        self._check(self.lib.eg_ctx_set_key_table_min(self.h, min_tallies))
+
     def set_prover_mode(self, constant_time):
         """True: constant-time fixed-base arithmetic for the provers' secret scalars (include/eg_b200.h)."""
         self._check(self.lib.eg_ctx_set_prover_mode(self.h, 1 if constant_time else 0))

@@ -134,6 +134,7 @@ extern "C" {
 
     pub fn eg_ctx_set_blinding_base(ctx: *mut eg_ctx, base: *const u8) -> eg_status;
     pub fn eg_ctx_set_ring_mode(ctx: *mut eg_ctx, mode: c_int) -> eg_status;
+    pub fn eg_ctx_set_key_table_min(ctx: *mut eg_ctx, min_tallies: usize) -> eg_status;
 
     pub fn eg_multi_mul_batch(ctx: *mut eg_ctx, n: usize, terms: u32, scalars: *const u8, points: *const u8, out: *mut u8,
                               ok: *mut u8) -> eg_status;
