@@ -5,9 +5,9 @@
 // VartimeMultiscalarMul as reached through src/group/ristretto.rs:72-146:
 //   serialize_element :88 -> ge_encode, deserialize_element :93 -> ge_decode,
 //   vartime_double_mul_generator :131 and vartime_multi_mul :139 -> ge_msm_chain (Straus with shared
-//   doublings; fixed 4-bit signed windows for per-item bases, 8-bit signed windows over a 128-entry
-//   affine table for the fixed bases G and K).  Results are group elements, so the choice of algorithm
-//   is invisible in the canonical encodings the verifier hashes.
+//   doublings and fixed 4-bit signed windows for per-item bases; doubling-free walks over wide-window
+//   affine tables for the batch-constant bases G, K, H).  Results are group elements, so the choice of
+//   algorithm is invisible in the canonical encodings the verifier hashes.
 #pragma once
 #include "fe.cuh"
 #include "sc.cuh"
@@ -358,13 +358,7 @@ EG_HD void sc_recode4(uint32_t out[8], const sc &a) {
     uint64_t c = 0;
     for (int i = 0; i < 8; i++) { c += (uint64_t)a.v[i] + 0x88888888u; out[i] = (uint32_t)c; c >>= 32; }
 }
-// 8-bit signed windows: a + 0x8080...80, digit_i = byte_i - 128 in [-128, 127]
-EG_HD void sc_recode8(uint32_t out[8], const sc &a) {
-    uint64_t c = 0;
-    for (int i = 0; i < 8; i++) { c += (uint64_t)a.v[i] + 0x80808080u; out[i] = (uint32_t)c; c >>= 32; }
-}
 EG_HD int sc_digit4(const uint32_t r[8], int i) { return (int)((r[i >> 3] >> ((i & 7) * 4)) & 15u) - 8; }
-EG_HD int sc_digit8(const uint32_t r[8], int i) { return (int)((r[i >> 2] >> ((i & 3) * 8)) & 255u) - 128; }
 
 // EG_WIDE_BITS-bit signed windows, produced low to high with a running carry: digit i of `a` in [-2^(W-1), 2^(W-1)).
 // a < 2^253 and W * EG_WIDE_WINDOWS >= 254, so the top window never carries out.
@@ -396,8 +390,8 @@ EG_HD void ge_wide_prefetch(const uint32_t *entry) {
 
 // acc = sum_{v<NV} a_v P_v + sum_{f<NF} b_f F_f
 //   P_v : per-item points (extended), windows of 4 bits over a per-thread table of [1..8]P_v
-//   F_f : fixed bases with 128-entry affine tables (shared or global memory), windows of 8 bits
-// One shared doubling chain of 252 doublings (Straus).  NV, NF are compile-time.
+//   F_f : fixed bases, added afterwards from their wide-window tables (ge_fixed_accumulate: no doublings)
+// One shared doubling chain of 252 doublings (Straus) for the per-item points.  NV, NF are compile-time.
 #if defined(__CUDACC__)
 #define EG_ALIGN16 __align__(16)
 #else
