@@ -75,7 +75,7 @@ struct eg_ctx {
     dev_buf xtab;
     uint8_t xtab_key[8][32];
     bool xtab_valid[8] = {false, false, false, false, false, false, false, false};
-    size_t key_table_min = 16384;   // eg_ctx_set_key_table_min
+    size_t key_table_min = 32768;   // eg_ctx_set_key_table_min
     // multi-GPU (comm.inc): NCCL communicator of a per-rank context (eg_ctx_attach_comm) or of a child of a multi-device
     // context (eg_ctx_create_multi); `children` is non-empty only for the latter's parent, which owns no device state
     void *comm = nullptr;

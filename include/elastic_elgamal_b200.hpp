@@ -79,6 +79,10 @@ class Engine {
     }
     void attach_comm(const std::array<uint8_t, EG_COMM_ID_BYTES> &id, int rank, int world) { check(eg_ctx_attach_comm(ctx_, id.data(), rank, world)); }
     void set_constant_time_provers(bool on) { check(eg_ctx_set_prover_mode(ctx_, on ? 1 : 0)); }
+    // tuning knobs (results never depend on them): ring-proof engine 0..3, tallies per call from which share verification
+    // builds fixed-base tables for the keys
+    void set_ring_engine(int mode) { check(eg_ctx_set_ring_mode(ctx_, mode)); }
+    void set_key_table_min(size_t min_tallies) { check(eg_ctx_set_key_table_min(ctx_, min_tallies)); }
     Engine(const Engine &) = delete;
     Engine &operator=(const Engine &) = delete;
 

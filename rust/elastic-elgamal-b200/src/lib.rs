@@ -187,9 +187,19 @@ impl Engine {
         self.check(unsafe { sys::eg_ctx_set_blinding_base(self.ctx, bytes.as_ptr()) })
     }
 
-    /// `true`: constant-time fixed-base arithmetic for the provers' secret scalars (about 4x the fixed-base work).
+    /// `true`: constant-time fixed-base arithmetic for the provers' secret scalars (64 instead of 11 additions per base).
     pub fn set_constant_time_provers(&self, constant_time: bool) -> Result<(), EngineError> {
         self.check(unsafe { sys::eg_ctx_set_prover_mode(self.ctx, constant_time as i32) })
+    }
+
+    /// Tuning knobs (results never depend on them): the ring-proof engine (0 = chosen per chunk, 1 = one launch per equation
+    /// index, 2 = one thread per ring, 3 = two lanes per ring) and the number of tallies per call from which
+    /// `verify_shares` / `verify_decryptions` build fixed-base tables for the keys (default 32 768, 0 = always).
+    pub fn set_ring_engine(&self, mode: i32) -> Result<(), EngineError> {
+        self.check(unsafe { sys::eg_ctx_set_ring_mode(self.ctx, mode) })
+    }
+    pub fn set_key_table_min(&self, min_tallies: usize) -> Result<(), EngineError> {
+        self.check(unsafe { sys::eg_ctx_set_key_table_min(self.ctx, min_tallies) })
     }
 
     fn tally(&self, bytes: &[u8]) -> Vec<Ciphertext<Ristretto>> {

@@ -126,7 +126,7 @@ def test_shares_config5_shape(env):
 
 def test_shares_with_key_tables(env):
     """PublicKeySet::verify_share / CandidateDecryption::verify with per-call fixed-base tables for the participant keys
-    (the library's choice from 16 384 tallies per call on; forced here): same verdicts and decrypted values as the oracle, for
+    (the library's choice from 32 768 tallies per call on; forced here): same verdicts and decrypted values as the oracle, for
     several key sets in a row on one context (the table cache is keyed by the key bytes), then back on the default path."""
     e = env[0]
     e.set_key_table_min(0)
@@ -137,7 +137,7 @@ def test_shares_with_key_tables(env):
         PC.check_shares_and_decrypt(e, n=200, shares=5, threshold=3, used=(0, 2, 4), table_hi=1 << 12)
         PC.check_verify_decryption(e, n=40)
     finally:
-        e.set_key_table_min(16384)
+        e.set_key_table_min(32768)
     PC.check_shares_and_decrypt(e, n=16, shares=5, threshold=3, used=(0, 2, 4), table_hi=64)
 
 

@@ -243,14 +243,14 @@ def test_verify_decryption_custom_key(env):
 
 
 def test_key_tables_forced(env):
-    """The per-call fixed-base tables of the keys shares are checked against (default: from 16 384 tallies per call on),
+    """The per-call fixed-base tables of the keys shares are checked against (default: from 32 768 tallies per call on),
     forced for tiny batches: one table for the custom-key form (the CPU build of a 48 MiB table takes seconds, hence one)."""
     e = env[0]
     e.set_key_table_min(0)
     try:
         PC.check_verify_decryption(e, n=9)
     finally:
-        e.set_key_table_min(16384)
+        e.set_key_table_min(32768)
 
 
 def test_wire_objects(env):
