@@ -31,7 +31,12 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", str(LIB)] + [str(s) for s in SOURCES]
+    # EG_B200_WIDE_BITS=16|20 at build time: the small-footprint variant (48 MiB / 0.61 GiB per fixed-base table instead of
+    # the default 8.25 GiB of 24-bit windows; csrc/ge.cuh), e.g. for several processes sharing one GPU
+    import os
+    bits = os.environ.get("EG_B200_WIDE_BITS")
+    extra = ["-DEG_WIDE_BITS=%d" % int(bits)] if bits else []
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", str(LIB)] + [str(s) for s in SOURCES]
     proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + proc.stdout)
