@@ -126,8 +126,8 @@ eg_status eg_mul_generator_batch(eg_ctx *ctx, size_t n, const uint8_t *k /* n*32
  * ok[i] = 0 (and out[i] = identity encoding) if a point does not decode or a scalar is not canonical. */
 eg_status eg_multi_mul_batch(eg_ctx *ctx, size_t n, uint32_t terms, const uint8_t *scalars /* n*terms*32 */,
                              const uint8_t *points /* n*terms*32 */, uint8_t *out /* n*32 */, uint8_t *ok /* n */);
-/* The Ciphertext operators of src/encryption.rs:160-226 (Add :163, Sub :181, Neg :199, Mul<&Scalar> :213) over a batch,
- * as one linear combination per item: out[i] = sum_j [scalars[i][j]] cts[i][j] on the R and the B parts, 1 <= terms <= 16.
+/* The Ciphertext operators of src/encryption.rs:163-226 (Add :163, Sub :180, Mul<&Scalar> :197, Mul<u64> :208, Neg :217)
+ * over a batch, as one linear combination per item: out[i] = sum_j [scalars[i][j]] cts[i][j] on the R and the B parts, 1 <= terms <= 16.
  * a + b = scalars (1, 1); a - b = (1, l - 1); -a = (l - 1); a * k = (k).  ok[i] = 0 (and out[i] = two identity encodings)
  * if an element does not decode or a scalar is not canonical. */
 eg_status eg_ciphertexts_lincomb_batch(eg_ctx *ctx, size_t n, uint32_t terms, const uint8_t *scalars /* n*terms*32 */,
