@@ -54,6 +54,18 @@ def test_multi_shares_and_decrypt(env):
 def test_multi_helpers_run_on_first_device(env):
     PC.check_group_helpers(env[0], n=4)
     PC.check_ciphertexts_sum(env[0], env[2])
+    PC.check_ciphertext_ops(env[0], env[2], n=5)
+
+
+def test_multi_knobs_reach_every_child(env):
+    """Tuning knobs set on the parent apply to all children: the pair engine pinned on every shard gives the same verdicts."""
+    e = env[0]
+    e.set_ring_mode(3)
+    try:
+        PC.check_verify_bool(e, env[2], n=24)
+        PC.check_verify_range(e, env[2], 21, n=7, frac=0.3)
+    finally:
+        e.set_ring_mode(0)
 
 
 def test_multi_rejects_device_pointer_calls_and_attach(env):
